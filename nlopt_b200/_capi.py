@@ -160,7 +160,9 @@ class Library:
         if not os.path.exists(self.path):
             raise OSError(
                 f"{self.path} not found -- build it first: python -c 'import __graft_entry__ as g; g.build()'")
-        self.dll = C.CDLL(self.path, mode=C.RTLD_GLOBAL if path is None else C.RTLD_LOCAL)
+        # RTLD_LOCAL: the reference library (tests) exports the same nlopt_* names; neither may
+        # interpose on the other
+        self.dll = C.CDLL(self.path, mode=C.RTLD_LOCAL)
         self.has_extensions = (path is None) if extensions is None else extensions
         for name, (res, args) in _STD.items():
             fn = getattr(self.dll, name)

@@ -1,0 +1,432 @@
+// ccsa_kernels.cuh -- the CUDA kernels of the MMA/CCSAQ hot path (sm_100a).
+//
+//   dual_eval_kernel  : one dual evaluation  y -> x*(y), val, g0, w, g_1..g_m over this rank's shard
+//                       (reference: static dual_func, src/algs/mma/mma.c:59-137 and
+//                        src/algs/mma/ccsa_quadratic.c:79-148)
+//   sigma_init_kernel : mma.c:202-210
+//   end_outer_kernel  : nlopt_stop_x norms (src/util/stop.c:98-108) + sigma update (mma.c:431-442,
+//                       ccsa_quadratic.c:577-590) + xprev/xprevprev rotation (mma.c:264-265), one pass
+//
+// Arithmetic contract: every per-variable expression is evaluated with the reference's operation
+// order using __dmul_rn/__dadd_rn/__dsub_rn/__ddiv_rn/__dsqrt_rn, which nvcc never contracts into
+// FMAs -- the reference is built with -ffp-contract=off (CMakeLists.txt:281-284).  x*(y) is
+// therefore bit-identical to the reference; only the ORDER of the n-term sums differs (fixed
+// tree, see below), which is the documented parity tolerance.
+//
+// Reduction contract (deterministic and independent of the number of GPUs): the global index
+// space is cut into S = 8*P segments whose boundaries depend on n only.  One CTA reduces one
+// segment with a fixed thread->element map and a fixed shuffle/shared-memory tree and stores
+// m+3 partials.  The last CTA to finish a "virtual shard" (P consecutive segments; 8 of them,
+// each rank owns 8/world) folds that shard's partials in a fixed order; the last virtual shard
+// to finish folds the rank's shard sums in index order and publishes them -- to mapped host
+// memory when the rank is alone, else to the exchange buffer that the all-gather reads.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+namespace nb200 {
+
+constexpr int kBlock = 256;              // threads per CTA of every kernel here
+constexpr int kWarps = kBlock / 32;
+constexpr int kVirtualShards = 8;        // V: fixed, so 1/2/4/8 ranks give bit-identical sums
+constexpr int kMaxParamM = 32;           // multipliers that travel as kernel parameters
+constexpr int kMaxNV = 3 + 16;           // accumulators one CTA carries: val, g0, w, <=16 g_i
+
+// ---- exact-rounding arithmetic (never fused) ---------------------------------------------
+__device__ __forceinline__ double mulx(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double addx(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double subx(double a, double b) { return __dsub_rn(a, b); }
+__device__ __forceinline__ double divx(double a, double b) { return __ddiv_rn(a, b); }
+
+// streaming loads: read-once data must not displace anything in L1
+__device__ __forceinline__ double2 ld_stream(const double2 *p)
+{
+    double2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void st_stream(double2 *p, double2 v)
+{
+    asm volatile("st.global.L1::no_allocate.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(v.x), "d"(v.y) : "memory");
+}
+
+// ---- arguments of one dual evaluation -------------------------------------------------------
+struct DualArgs {
+    // shard-local arrays (16-byte aligned, padded with sigma = 0 lanes)
+    const double *x, *lb, *ub, *sigma, *g;
+    const double *G;              // m rows of ld doubles
+    double *xcur;                 // written iff STORE
+    unsigned long long ld;        // row stride of G in doubles
+    // segment geometry (global, depends on n only)
+    unsigned long long npairs;    // ceil(n / 2) over ALL ranks
+    unsigned long long pair0;     // first global pair of this rank
+    unsigned nseg_total;          // S = 8 * P
+    unsigned seg0;                // first global segment of this rank
+    unsigned segs_per_vshard;     // P
+    unsigned local_vshards;       // 8 / world
+    // reduction workspace
+    double *partials;             // [local segments][nvp]
+    double *vsums;                // [local_vshards][nvp]
+    unsigned *tickets;            // [local_vshards + 1], zero between launches
+    double *out_dev;              // [8][nvp] all-rank exchange buffer (this rank's slots filled)
+    volatile double *out_host;    // mapped pinned [nvp]; written when publish_host
+    volatile unsigned long long *flag_host;
+    unsigned long long seq;
+    int publish_host;             // 1: single rank, results + flag go straight to the host
+    int nvp;                      // stride of one partial record (>= 3 + chunk size)
+    // the multipliers and penalties
+    int m;                        // total number of constraints (rows of G)
+    int chunk0, chunk_n;          // this launch accumulates g_i for i in [chunk0, chunk0 + chunk_n)
+    unsigned active;              // bit i clear: constraint i switched off (MMA, NaN value)
+    double rho, half_rho, u_ccsaq;    // u_ccsaq = rho + sum_i rhoc_i y_i (ccsa_quadratic.c:116-120)
+    double y[kMaxParamM], rhoc[kMaxParamM], half_rhoc[kMaxParamM];
+};
+
+// ---- block-level reduction with a fixed tree --------------------------------------------------
+template <int NV>
+__device__ __forceinline__ void block_reduce_to(double (&acc)[NV], double *smem /* [kWarps*NV] */, double *out)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        double v = acc[k];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) v = addx(v, __shfl_xor_sync(0xffffffffu, v, off));
+        if (lane == 0) smem[warp * NV + k] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < NV) {
+        double s = smem[threadIdx.x];
+#pragma unroll
+        for (int w = 1; w < kWarps; ++w) s = addx(s, smem[w * NV + threadIdx.x]);
+        out[threadIdx.x] = s;
+    }
+    __syncthreads();
+}
+
+// true in exactly one CTA: the one whose ticket completes `total`
+__device__ __forceinline__ bool is_last_arrival(unsigned *ticket, unsigned total, int *s_flag)
+{
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) *s_flag = (atomicAdd(ticket, 1u) == total - 1u);
+    __syncthreads();
+    return *s_flag != 0;
+}
+
+// ---- per-variable closed forms ------------------------------------------------------------------
+// MMA: mma.c:96-129.  G[i] holds d c_i / d x_j for the rows kept in registers.
+template <int MAXM>
+__device__ __forceinline__ double mma_point(const DualArgs &a, double x, double lb, double ub, double s, double g,
+                                            const double (&Gr)[MAXM > 0 ? MAXM : 1], const double *Gcol,
+                                            unsigned long long ld, double (&acc)[3 + (MAXM > 0 ? MAXM : 1)])
+{
+    if (s == 0) return x;                                    // fixed variable, mma.c:96-99
+    const double ag_s = mulx(fabs(g), s);
+    double u = g;
+    double v = addx(ag_s, a.half_rho);
+    if (a.m <= MAXM) {
+#pragma unroll
+        for (int i = 0; i < MAXM; ++i)
+            if (i < a.m && ((a.active >> i) & 1u)) {
+                u = addx(u, mulx(Gr[i], a.y[i]));
+                v = addx(v, mulx(addx(mulx(fabs(Gr[i]), s), a.half_rhoc[i]), a.y[i]));
+            }
+    } else {
+        for (int i = 0; i < a.m; ++i)
+            if ((a.active >> i) & 1u) {
+                const double gi = Gcol[(unsigned long long) i * ld];
+                u = addx(u, mulx(gi, a.y[i]));
+                v = addx(v, mulx(addx(mulx(fabs(gi), s), a.half_rhoc[i]), a.y[i]));
+            }
+    }
+    const double s2 = mulx(s, s);
+    u = mulx(u, s2);
+    const double r = divx(u, mulx(v, s));
+    double dx = divx(divx(u, v), subx(-1.0, __dsqrt_rn(fabs(subx(1.0, mulx(r, r))))));   // mma.c:108
+    double xc = addx(x, dx);
+    if (xc > ub) xc = ub; else if (xc < lb) xc = lb;        // mma.c:110-111
+    const double lim = mulx(0.9, s), hi = addx(x, lim), lo = subx(x, lim);
+    if (xc > hi) xc = hi; else if (xc < lo) xc = lo;        // mma.c:112-113
+    dx = subx(xc, x);
+    const double dx2 = mulx(dx, dx);
+    const double dinv = divx(1.0, subx(s2, dx2));
+    acc[0] = addx(acc[0], mulx(addx(mulx(u, dx), mulx(v, dx2)), dinv));                  // mma.c:119
+    const double c = mulx(s2, dx);
+    acc[1] = addx(acc[1], mulx(addx(mulx(g, c), mulx(addx(ag_s, a.half_rho), dx2)), dinv));   // mma.c:123
+    acc[2] = addx(acc[2], mulx(mulx(0.5, dx2), dinv));                                  // mma.c:125
+#pragma unroll
+    for (int k = 0; k < MAXM; ++k) {
+        const int i = a.chunk0 + k;
+        if (k < a.chunk_n && ((a.active >> i) & 1u)) {
+            const double gi = (a.m <= MAXM) ? Gr[k] : Gcol[(unsigned long long) i * ld];
+            acc[3 + k] = addx(acc[3 + k],
+                              mulx(addx(mulx(gi, c), mulx(addx(mulx(fabs(gi), s), a.half_rhoc[i]), dx2)), dinv));   // mma.c:127
+        }
+    }
+    return xc;
+}
+
+// CCSAQ: ccsa_quadratic.c:111-140
+template <int MAXM>
+__device__ __forceinline__ double ccsaq_point(const DualArgs &a, double x, double lb, double ub, double s, double g,
+                                              const double (&Gr)[MAXM > 0 ? MAXM : 1], const double *Gcol,
+                                              unsigned long long ld, double (&acc)[3 + (MAXM > 0 ? MAXM : 1)])
+{
+    if (s == 0) return x;                                    // ccsa_quadratic.c:111-114
+    double v = g;
+    if (a.m <= MAXM) {
+#pragma unroll
+        for (int i = 0; i < MAXM; ++i)
+            if (i < a.m) v = addx(v, mulx(Gr[i], a.y[i]));
+    } else {
+        for (int i = 0; i < a.m; ++i) v = addx(v, mulx(Gcol[(unsigned long long) i * ld], a.y[i]));
+    }
+    const double u = a.u_ccsaq;
+    const double s2 = mulx(s, s);
+    double dx = divx(mulx(-s2, v), u);                       // ccsa_quadratic.c:122
+    if (fabs(dx) > s) dx = copysign(s, dx);                  // ccsa_quadratic.c:126
+    double xc = addx(x, dx);
+    if (xc > ub) xc = ub; else if (xc < lb) xc = lb;
+    dx = subx(xc, x);
+    const double dx2 = mulx(dx, dx);
+    acc[0] = addx(acc[0], addx(mulx(v, dx), divx(mulx(mulx(0.5, u), dx2), s2)));         // ccsa_quadratic.c:134
+    const double q = divx(mulx(0.5, dx2), s2);
+    acc[1] = addx(acc[1], addx(mulx(g, dx), mulx(a.rho, q)));                            // :137
+    acc[2] = addx(acc[2], q);                                                            // :138
+#pragma unroll
+    for (int k = 0; k < MAXM; ++k) {
+        const int i = a.chunk0 + k;
+        if (k < a.chunk_n) {
+            const double gi = (a.m <= MAXM) ? Gr[k] : Gcol[(unsigned long long) i * ld];
+            acc[3 + k] = addx(acc[3 + k], addx(mulx(gi, dx), mulx(a.rhoc[i], q)));       // :139-140
+        }
+    }
+    return xc;
+}
+
+// ---- the dual evaluation kernel -----------------------------------------------------------------
+// grid = number of local segments; CTA b owns global segment seg0 + b.
+template <int VARIANT, int MAXM, bool STORE>
+__global__ void __launch_bounds__(kBlock) dual_eval_kernel(const __grid_constant__ DualArgs a)
+{
+    constexpr int MR = MAXM > 0 ? MAXM : 1;
+    constexpr int NV = 3 + MR;
+    __shared__ double s_red[kWarps * NV];
+    __shared__ int s_flag;
+
+    const unsigned seg = a.seg0 + blockIdx.x;
+    // pair range of this segment, relative to the shard start
+    const unsigned long long p_lo = (unsigned long long) seg * a.npairs / a.nseg_total - a.pair0;
+    const unsigned long long p_hi = (unsigned long long) (seg + 1) * a.npairs / a.nseg_total - a.pair0;
+
+    double acc[NV];
+#pragma unroll
+    for (int k = 0; k < NV; ++k) acc[k] = 0.0;
+
+    const double2 *x2 = reinterpret_cast<const double2 *>(a.x);
+    const double2 *lb2 = reinterpret_cast<const double2 *>(a.lb);
+    const double2 *ub2 = reinterpret_cast<const double2 *>(a.ub);
+    const double2 *s2v = reinterpret_cast<const double2 *>(a.sigma);
+    const double2 *g2 = reinterpret_cast<const double2 *>(a.g);
+    const bool in_regs = a.m <= MAXM;
+
+    for (unsigned long long p = p_lo + threadIdx.x; p < p_hi; p += kBlock) {
+        const double2 vx = ld_stream(x2 + p), vlb = ld_stream(lb2 + p), vub = ld_stream(ub2 + p),
+                      vs = ld_stream(s2v + p), vg = ld_stream(g2 + p);
+        double Ga[MR], Gb[MR];
+#pragma unroll
+        for (int i = 0; i < MR; ++i) {
+            Ga[i] = 0.0;
+            Gb[i] = 0.0;
+            if (MAXM > 0 && in_regs && i < a.m) {
+                const double2 t = ld_stream(reinterpret_cast<const double2 *>(a.G + (unsigned long long) i * a.ld) + p);
+                Ga[i] = t.x;
+                Gb[i] = t.y;
+            }
+        }
+        const double *col = a.G + 2 * p;
+        double2 xc;
+        if (VARIANT == 0) {
+            xc.x = mma_point<MAXM>(a, vx.x, vlb.x, vub.x, vs.x, vg.x, Ga, col, a.ld, acc);
+            xc.y = mma_point<MAXM>(a, vx.y, vlb.y, vub.y, vs.y, vg.y, Gb, col + 1, a.ld, acc);
+        } else {
+            xc.x = ccsaq_point<MAXM>(a, vx.x, vlb.x, vub.x, vs.x, vg.x, Ga, col, a.ld, acc);
+            xc.y = ccsaq_point<MAXM>(a, vx.y, vlb.y, vub.y, vs.y, vg.y, Gb, col + 1, a.ld, acc);
+        }
+        if (STORE) st_stream(reinterpret_cast<double2 *>(a.xcur) + p, xc);
+    }
+
+    // segment partial
+    block_reduce_to<NV>(acc, s_red, a.partials + (unsigned long long) blockIdx.x * a.nvp);
+
+    // virtual-shard fold by the last CTA of the shard
+    const unsigned vs_local = blockIdx.x / a.segs_per_vshard;
+    if (!is_last_arrival(a.tickets + vs_local, a.segs_per_vshard, &s_flag)) return;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) acc[k] = 0.0;
+    {
+        const double *base = a.partials + (unsigned long long) vs_local * a.segs_per_vshard * a.nvp;
+        for (unsigned sgi = threadIdx.x; sgi < a.segs_per_vshard; sgi += kBlock)
+#pragma unroll
+            for (int k = 0; k < NV; ++k) acc[k] = addx(acc[k], __ldcg(base + (unsigned long long) sgi * a.nvp + k));
+    }
+    block_reduce_to<NV>(acc, s_red, a.vsums + (unsigned long long) vs_local * a.nvp);
+
+    // rank fold by the last virtual shard
+    if (!is_last_arrival(a.tickets + a.local_vshards, a.local_vshards, &s_flag)) return;
+    if (threadIdx.x < NV) {
+        if (a.publish_host) {
+            double s = __ldcg(a.vsums + threadIdx.x);
+            for (unsigned v = 1; v < a.local_vshards; ++v) s = addx(s, __ldcg(a.vsums + (unsigned long long) v * a.nvp + threadIdx.x));
+            a.out_host[threadIdx.x] = s;
+            __threadfence_system();
+        } else {
+            // several ranks: hand this rank's shard sums to the exchange buffer, untouched
+            const unsigned v0 = a.seg0 / a.segs_per_vshard;
+            for (unsigned v = 0; v < a.local_vshards; ++v)
+                a.out_dev[(unsigned long long) (v0 + v) * a.nvp + threadIdx.x] = __ldcg(a.vsums + (unsigned long long) v * a.nvp + threadIdx.x);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (unsigned v = 0; v <= a.local_vshards; ++v) a.tickets[v] = 0;    // ready for the next launch
+        if (a.publish_host) {
+            *a.flag_host = a.seq;
+            __threadfence_system();
+        }
+    }
+}
+
+// After the all-gather (several ranks): fold the 8 shard sums in index order and publish.
+__global__ void publish_kernel(const double *all_vsums /* [8][nvp] */, int nv, int nvp, volatile double *out_host,
+                               volatile unsigned long long *flag_host, unsigned long long seq)
+{
+    if (threadIdx.x < nv) {
+        double s = all_vsums[threadIdx.x];
+        for (int v = 1; v < kVirtualShards; ++v) s = addx(s, all_vsums[v * nvp + threadIdx.x]);
+        out_host[threadIdx.x] = s;
+        __threadfence_system();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        *flag_host = seq;
+        __threadfence_system();
+    }
+}
+
+// ---- sigma initialisation, mma.c:202-210 ---------------------------------------------------------
+__device__ __forceinline__ bool dev_isinf(double v) { return fabs(v) >= HUGE_VAL * 0.99 || isinf(v); }
+
+__global__ void sigma_init_kernel(double *sigma, const double *lb, const double *ub, const double *sigma_init,
+                                  double sigma_min, unsigned long long n_local)
+{
+    for (unsigned long long j = blockIdx.x * (unsigned long long) blockDim.x + threadIdx.x; j < n_local;
+         j += (unsigned long long) gridDim.x * blockDim.x) {
+        double s;
+        if (sigma_init && sigma_init[j] > 0) s = sigma_init[j];
+        else if (dev_isinf(ub[j]) || dev_isinf(lb[j])) s = 1.0;
+        else s = mulx(0.5, subx(ub[j], lb[j]));
+        sigma[j] = s > sigma_min ? s : sigma_min;
+    }
+}
+
+// ---- fused end-of-outer-iteration pass -------------------------------------------------------------
+struct EndOuterArgs {
+    const double *xcur;
+    double *xprev, *xprevprev, *sigma;
+    const double *lb, *ub;
+    const double *w;          // x weights or null (stop.c:37-79)
+    const double *xtol_abs;   // or null
+    unsigned long long n_local, npairs, pair0;
+    unsigned nseg_total, seg0, segs_per_vshard, local_vshards;
+    double *partials, *vsums;
+    unsigned *tickets;
+    double *out_dev;
+    volatile double *out_host;
+    volatile unsigned long long *flag_host;
+    unsigned long long seq;
+    int publish_host, nvp;
+    int update_sigma;         // k > 1
+    double kappa;             // 0.01 (mma.c:439) or 1e-8 (ccsa_quadratic.c:587)
+    double sigma_min;
+};
+
+__global__ void __launch_bounds__(kBlock) end_outer_kernel(const __grid_constant__ EndOuterArgs a)
+{
+    constexpr int NV = 3;     // sum w|dx|, sum w|x|, count of |dx| >= xtol_abs
+    __shared__ double s_red[kWarps * NV];
+    __shared__ int s_flag;
+    const unsigned seg = a.seg0 + blockIdx.x;
+    const unsigned long long p_lo = (unsigned long long) seg * a.npairs / a.nseg_total - a.pair0;
+    const unsigned long long p_hi = (unsigned long long) (seg + 1) * a.npairs / a.nseg_total - a.pair0;
+    double acc[NV] = {0.0, 0.0, 0.0};
+    for (unsigned long long p = p_lo + threadIdx.x; p < p_hi; p += kBlock) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const unsigned long long j = 2 * p + h;
+            if (j >= a.n_local) break;
+            const double xc = a.xcur[j], xp = a.xprev[j];
+            const double d = fabs(subx(xc, xp));
+            if (a.w) {
+                acc[0] = addx(acc[0], mulx(a.w[j], d));
+                acc[1] = addx(acc[1], mulx(a.w[j], fabs(xc)));
+            } else {
+                acc[0] = addx(acc[0], d);
+                acc[1] = addx(acc[1], fabs(xc));
+            }
+            if (a.xtol_abs && d >= a.xtol_abs[j]) acc[2] = addx(acc[2], 1.0);
+            if (a.update_sigma) {
+                const double xpp = a.xprevprev[j];
+                const double osc = mulx(subx(xc, xp), subx(xp, xpp));
+                double s = mulx(a.sigma[j], osc < 0 ? 0.7 : (osc > 0 ? 1.2 : 1.0));
+                const double lo = a.lb[j], hi = a.ub[j];
+                if (!dev_isinf(hi) && !dev_isinf(lo)) {
+                    const double range = subx(hi, lo);
+                    const double top = mulx(10.0, range), bot = mulx(a.kappa, range);
+                    s = s < top ? s : top;
+                    s = s > bot ? s : bot;
+                }
+                a.sigma[j] = s > a.sigma_min ? s : a.sigma_min;
+            }
+            a.xprevprev[j] = xp;
+            a.xprev[j] = xc;
+        }
+    }
+    block_reduce_to<NV>(acc, s_red, a.partials + (unsigned long long) blockIdx.x * a.nvp);
+    const unsigned vs_local = blockIdx.x / a.segs_per_vshard;
+    if (!is_last_arrival(a.tickets + vs_local, a.segs_per_vshard, &s_flag)) return;
+    acc[0] = acc[1] = acc[2] = 0.0;
+    {
+        const double *base = a.partials + (unsigned long long) vs_local * a.segs_per_vshard * a.nvp;
+        for (unsigned sgi = threadIdx.x; sgi < a.segs_per_vshard; sgi += kBlock)
+#pragma unroll
+            for (int k = 0; k < NV; ++k) acc[k] = addx(acc[k], __ldcg(base + (unsigned long long) sgi * a.nvp + k));
+    }
+    block_reduce_to<NV>(acc, s_red, a.vsums + (unsigned long long) vs_local * a.nvp);
+    if (!is_last_arrival(a.tickets + a.local_vshards, a.local_vshards, &s_flag)) return;
+    if (threadIdx.x < NV) {
+        if (a.publish_host) {
+            double s = __ldcg(a.vsums + threadIdx.x);
+            for (unsigned v = 1; v < a.local_vshards; ++v) s = addx(s, __ldcg(a.vsums + (unsigned long long) v * a.nvp + threadIdx.x));
+            a.out_host[threadIdx.x] = s;
+            __threadfence_system();
+        } else {
+            const unsigned v0 = a.seg0 / a.segs_per_vshard;
+            for (unsigned v = 0; v < a.local_vshards; ++v)
+                a.out_dev[(unsigned long long) (v0 + v) * a.nvp + threadIdx.x] = __ldcg(a.vsums + (unsigned long long) v * a.nvp + threadIdx.x);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (unsigned v = 0; v <= a.local_vshards; ++v) a.tickets[v] = 0;
+        if (a.publish_host) {
+            *a.flag_host = a.seq;
+            __threadfence_system();
+        }
+    }
+}
+
+}  // namespace nb200

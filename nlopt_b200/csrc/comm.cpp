@@ -1,0 +1,141 @@
+// comm.cpp -- see comm.hpp.  NCCL entry points are resolved with dlsym; the handful of enum
+// values used (ncclFloat64 = 8, ncclSum = 0, ncclSuccess = 0) are ABI constants of nccl.h.
+#include "comm.hpp"
+
+#include <dlfcn.h>
+
+#include <cstdio>
+#include <cstring>
+
+#include "../../include/nlopt_b200.h"
+
+namespace nb200 {
+
+namespace {
+struct NcclId { char internal[128]; };
+typedef int (*fn_get_id)(NcclId *);
+typedef int (*fn_init_rank)(void **, int, NcclId, int);
+typedef int (*fn_destroy)(void *);
+typedef int (*fn_all_gather)(const void *, void *, size_t, int, void *, cudaStream_t);
+typedef int (*fn_all_reduce)(const void *, void *, size_t, int, int, void *, cudaStream_t);
+typedef const char *(*fn_errstr)(int);
+
+struct Api {
+    void *lib = nullptr;
+    fn_get_id get_id = nullptr;
+    fn_init_rank init_rank = nullptr;
+    fn_destroy destroy = nullptr;
+    fn_all_gather all_gather = nullptr;
+    fn_all_reduce all_reduce = nullptr;
+    fn_errstr errstr = nullptr;
+};
+
+Api &api() { static Api a; return a; }
+
+bool load(std::string *err)
+{
+    Api &a = api();
+    if (a.lib) return true;
+    const char *names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char *nm : names)
+        if ((a.lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL))) break;
+    if (!a.lib) { if (err) *err = std::string("cannot dlopen libnccl: ") + dlerror(); return false; }
+    a.get_id = (fn_get_id) dlsym(a.lib, "ncclGetUniqueId");
+    a.init_rank = (fn_init_rank) dlsym(a.lib, "ncclCommInitRank");
+    a.destroy = (fn_destroy) dlsym(a.lib, "ncclCommDestroy");
+    a.all_gather = (fn_all_gather) dlsym(a.lib, "ncclAllGather");
+    a.all_reduce = (fn_all_reduce) dlsym(a.lib, "ncclAllReduce");
+    a.errstr = (fn_errstr) dlsym(a.lib, "ncclGetErrorString");
+    if (!a.get_id || !a.init_rank || !a.destroy || !a.all_gather || !a.all_reduce) {
+        if (err) *err = "libnccl is missing expected symbols";
+        return false;
+    }
+    return true;
+}
+
+std::string nccl_msg(const char *what, int code)
+{
+    std::string s = what;
+    s += ": ";
+    s += api().errstr ? api().errstr(code) : "NCCL error";
+    return s;
+}
+}  // namespace
+
+Comm &Comm::instance() { static Comm c; return c; }
+
+int Comm::unique_id(unsigned char id[128], std::string *err)
+{
+    if (!load(err)) return -1;
+    NcclId nid;
+    int rc = api().get_id(&nid);
+    if (rc) { if (err) *err = nccl_msg("ncclGetUniqueId", rc); return -1; }
+    std::memcpy(id, nid.internal, 128);
+    return 0;
+}
+
+int Comm::init(const unsigned char id[128], int r, int w, int dev, std::string *err)
+{
+    if (w < 1 || r < 0 || r >= w || (8 % w) != 0) {
+        if (err) *err = "world size must be 1, 2, 4 or 8 (it has to divide the 8 virtual shards)";
+        return -1;
+    }
+    if (comm_) finalize();
+    rank = r; world = w; device = dev;
+    if (w == 1) return 0;
+    if (!load(err)) return -1;
+    if (cudaSetDevice(dev) != cudaSuccess) { if (err) *err = "cudaSetDevice failed"; return -1; }
+    NcclId nid;
+    std::memcpy(nid.internal, id, 128);
+    int rc = api().init_rank(&comm_, w, nid, r);
+    if (rc) { comm_ = nullptr; world = 1; rank = 0; if (err) *err = nccl_msg("ncclCommInitRank", rc); return -1; }
+    return 0;
+}
+
+int Comm::finalize()
+{
+    if (comm_) api().destroy(comm_);
+    comm_ = nullptr;
+    rank = 0; world = 1;
+    return 0;
+}
+
+int Comm::all_gather_inplace(double *buf, size_t count_per_rank, cudaStream_t s, std::string *err)
+{
+    if (world == 1) return 0;
+    int rc = api().all_gather(buf + (size_t) rank * count_per_rank, buf, count_per_rank, /*ncclFloat64*/ 8, comm_, s);
+    if (rc) { if (err) *err = nccl_msg("ncclAllGather", rc); return -1; }
+    return 0;
+}
+
+int Comm::all_reduce_sum(double *buf, size_t count, cudaStream_t s, std::string *err)
+{
+    if (world == 1) return 0;
+    int rc = api().all_reduce(buf, buf, count, 8, /*ncclSum*/ 0, comm_, s);
+    if (rc) { if (err) *err = nccl_msg("ncclAllReduce", rc); return -1; }
+    return 0;
+}
+
+}  // namespace nb200
+
+extern "C" {
+
+int nlopt_b200_comm_unique_id(unsigned char id128[128])
+{
+    std::string e;
+    return nb200::Comm::unique_id(id128, &e);
+}
+
+int nlopt_b200_comm_init(const unsigned char id128[128], int rank, int world, int device)
+{
+    std::string e;
+    int rc = nb200::Comm::instance().init(id128, rank, world, device, &e);
+    if (rc) std::fprintf(stderr, "nlopt_b200_comm_init: %s\n", e.c_str());
+    return rc;
+}
+
+int nlopt_b200_comm_finalize(void) { return nb200::Comm::instance().finalize(); }
+int nlopt_b200_comm_rank(void) { return nb200::Comm::instance().rank; }
+int nlopt_b200_comm_world(void) { return nb200::Comm::instance().world; }
+
+}  // extern "C"

@@ -1,0 +1,845 @@
+// device_backend.cu -- DeviceBackend: the n-dimensional state of an MMA/CCSAQ run in HBM and the
+// launches that act on it.  See device_backend.hpp for the layout and ccsa_kernels.cuh for the
+// kernels.  One instance = one rank's shard (the whole problem when there is a single rank).
+#include "device_backend.hpp"
+
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+
+#include "ccsa_kernels.cuh"
+#include "comm.hpp"
+#include "dual_mma.hpp"
+#include "synth.cuh"
+
+namespace nb200 {
+
+namespace {
+
+#define NB_CUDA(call)                                   \
+    do {                                                \
+        cudaError_t e__ = (call);                       \
+        if (e__ != cudaSuccess) return fail(#call, e__);\
+    } while (0)
+
+int grid_for(unsigned long long n) { unsigned long long g = (n + kBlock - 1) / kBlock; return (int) (g < 1 ? 1 : (g > 148ull * 16 ? 148ull * 16 : g)); }
+
+template <int VARIANT, int MAXM>
+void launch_variant(bool store, int grid, cudaStream_t s, const DualArgs &a)
+{
+    if (store) dual_eval_kernel<VARIANT, MAXM, true><<<grid, kBlock, 0, s>>>(a);
+    else dual_eval_kernel<VARIANT, MAXM, false><<<grid, kBlock, 0, s>>>(a);
+}
+
+template <int VARIANT>
+void launch_by_m(int maxm, bool store, int grid, cudaStream_t s, const DualArgs &a)
+{
+    switch (maxm) {
+    case 0: launch_variant<VARIANT, 0>(store, grid, s, a); break;
+    case 1: launch_variant<VARIANT, 1>(store, grid, s, a); break;
+    case 2: launch_variant<VARIANT, 2>(store, grid, s, a); break;
+    case 4: launch_variant<VARIANT, 4>(store, grid, s, a); break;
+    case 8: launch_variant<VARIANT, 8>(store, grid, s, a); break;
+    default: launch_variant<VARIANT, 16>(store, grid, s, a); break;
+    }
+}
+
+int pick_maxm(int m) { return m == 0 ? 0 : m <= 1 ? 1 : m <= 2 ? 2 : m <= 4 ? 4 : m <= 8 ? 8 : 16; }
+
+}  // namespace
+
+DeviceBackend::DeviceBackend() {}
+
+DeviceBackend::~DeviceBackend()
+{
+    drain_events();
+    for (cudaEvent_t e : ev_pool_) cudaEventDestroy(e);
+    free_state();
+}
+
+bool DeviceBackend::fail(const char *what, cudaError_t e)
+{
+    err_ = std::string(what) + ": " + cudaGetErrorString(e);
+    return false;
+}
+
+bool DeviceBackend::fail(const std::string &what)
+{
+    err_ = what;
+    return false;
+}
+
+void DeviceBackend::free_state()
+{
+    if (pool_) cudaFree(pool_);
+    if (w_dev_) cudaFree(w_dev_);
+    if (xtol_abs_dev_) cudaFree(xtol_abs_dev_);
+    if (partials_) cudaFree(partials_);
+    if (vsums_) cudaFree(vsums_);
+    if (out_dev_) cudaFree(out_dev_);
+    if (tickets_) cudaFree(tickets_);
+    if (xfull_dev_) cudaFree(xfull_dev_);
+    if (scalar_dev_) cudaFree(scalar_dev_);
+    if (out_host_) cudaFreeHost(out_host_);
+    if (flag_host_) cudaFreeHost(flag_host_);
+    if (h_x_) cudaFreeHost(h_x_);
+    for (int b = 0; b < 2; ++b) {
+        if (h_grad_[b]) cudaFreeHost(h_grad_[b]);
+        if (h_grad_done_[b]) cudaEventDestroy(h_grad_done_[b]);
+    }
+    if (copied_) cudaEventDestroy(copied_);
+    if (stream_) cudaStreamDestroy(stream_);
+    if (copy_stream_) cudaStreamDestroy(copy_stream_);
+    pool_ = w_dev_ = xtol_abs_dev_ = partials_ = vsums_ = out_dev_ = xfull_dev_ = scalar_dev_ = nullptr;
+    tickets_ = nullptr;
+    out_host_ = nullptr;
+    flag_host_ = nullptr;
+    h_x_ = nullptr;
+    h_grad_[0] = h_grad_[1] = nullptr;
+    h_grad_done_[0] = h_grad_done_[1] = nullptr;
+    copied_ = nullptr;
+    stream_ = copy_stream_ = nullptr;
+}
+
+bool DeviceBackend::alloc_state()
+{
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(std::string("no usable CUDA device (") + cudaGetErrorString(e) +
+                    "); libnlopt_b200 runs NLOPT_LD_MMA/NLOPT_LD_CCSAQ on the GPU only");
+    Comm &comm = Comm::instance();
+    if (comm.active()) {
+        device_ = comm.device;
+        NB_CUDA(cudaSetDevice(device_));
+    } else {
+        NB_CUDA(cudaGetDevice(&device_));
+    }
+    geo_ = Geometry::make(geo_.n, comm.world, comm.rank, target_pairs_, pmax_);
+    shard_cap_ = 0;
+    for (int r = 0; r < comm.world; ++r) {
+        Geometry gr = Geometry::make(geo_.n, comm.world, r, target_pairs_, pmax_);
+        if (gr.ld > shard_cap_) shard_cap_ = gr.ld;
+    }
+    if (m_ > (unsigned) kMaxParamM)
+        return fail("more than 32 inequality constraints are not supported by this build of the dual kernel");
+
+    NB_CUDA(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
+    NB_CUDA(cudaStreamCreateWithFlags(&copy_stream_, cudaStreamNonBlocking));
+    NB_CUDA(cudaEventCreateWithFlags(&copied_, cudaEventDisableTiming));
+
+    const size_t ld = geo_.ld;
+    const size_t total = (9 + 2 * (size_t) m_) * ld;
+    NB_CUDA(cudaMalloc(&pool_, total * sizeof(double)));
+    NB_CUDA(cudaMemsetAsync(pool_, 0, total * sizeof(double), stream_));
+    double *p = pool_;
+    x_ = p; p += ld;  xcur_ = p; p += ld;  xprev_ = p; p += ld;  xprevprev_ = p; p += ld;
+    lb_ = p; p += ld; ub_ = p; p += ld;    sigma_ = p; p += ld;  g_ = p; p += ld;  gcur_ = p; p += ld;
+    G_ = p; p += (size_t) m_ * ld;
+    Gcur_ = p;
+    cand_in_x_ = true;
+    return alloc_workspace();
+}
+
+bool DeviceBackend::alloc_workspace()
+{
+    if (partials_) { cudaFree(partials_); partials_ = nullptr; }
+    if (vsums_) { cudaFree(vsums_); vsums_ = nullptr; }
+    nvp_ = 24;   // >= kMaxNV, keeps records 64-byte aligned
+    NB_CUDA(cudaMalloc(&partials_, (size_t) geo_.nseg_local * nvp_ * sizeof(double)));
+    NB_CUDA(cudaMalloc(&vsums_, (size_t) kV * nvp_ * sizeof(double)));
+    if (!out_dev_) NB_CUDA(cudaMalloc(&out_dev_, (size_t) kV * nvp_ * sizeof(double)));
+    if (!tickets_) {
+        NB_CUDA(cudaMalloc(&tickets_, (kV + 1) * sizeof(unsigned)));
+        NB_CUDA(cudaMemsetAsync(tickets_, 0, (kV + 1) * sizeof(unsigned), stream_));
+    }
+    if (!out_host_) {
+        NB_CUDA(cudaHostAlloc(&out_host_, nvp_ * sizeof(double), cudaHostAllocMapped));
+        NB_CUDA(cudaHostAlloc(&flag_host_, 64, cudaHostAllocMapped));
+        *flag_host_ = 0;
+    }
+    NB_CUDA(cudaStreamSynchronize(stream_));
+    return true;
+}
+
+bool DeviceBackend::setup_raw(Variant v, unsigned n, unsigned m)
+{
+    variant_ = v;
+    m_ = m;
+    geo_.n = n;
+    cfg_ = BackendConfig();
+    cfg_.variant = v;
+    cfg_.n = n;
+    return alloc_state();
+}
+
+bool DeviceBackend::setup(const BackendConfig &cfg)
+{
+    cfg_ = cfg;
+    variant_ = cfg.variant;
+    geo_.n = cfg.n;
+    m_ = 0;
+    max_cdim_ = 1;
+    for (const FuncSpec &c : cfg.constraints) {
+        m_ += c.m;
+        if (c.m > max_cdim_) max_cdim_ = c.m;
+    }
+    if (cfg.stats) stats_ = cfg.stats;
+    if (!alloc_state()) return false;
+    const size_t nl = geo_.n_local, j0 = geo_.j0;
+    // bounds and start point
+    NB_CUDA(cudaMemcpyAsync(lb_, cfg.lb + j0, nl * sizeof(double), cudaMemcpyHostToDevice, stream_));
+    NB_CUDA(cudaMemcpyAsync(ub_, cfg.ub + j0, nl * sizeof(double), cudaMemcpyHostToDevice, stream_));
+    stats_->h2d_bytes += 2 * nl * sizeof(double);
+    bool any_host_cb = cfg.objective.f != nullptr;
+    for (const FuncSpec &c : cfg.constraints) any_host_cb = any_host_cb || c.f || c.mf;
+    if (any_host_cb) {
+        NB_CUDA(cudaHostAlloc(&h_x_, (size_t) geo_.n * sizeof(double), cudaHostAllocDefault));
+        h_grad_cap_ = (size_t) max_cdim_ * geo_.n;
+        for (int b = 0; b < 2; ++b) {
+            NB_CUDA(cudaHostAlloc(&h_grad_[b], h_grad_cap_ * sizeof(double), cudaHostAllocDefault));
+            NB_CUDA(cudaEventCreateWithFlags(&h_grad_done_[b], cudaEventDisableTiming));
+        }
+        if (Comm::instance().active())
+            NB_CUDA(cudaMalloc(&xfull_dev_, (size_t) Comm::instance().world * shard_cap_ * sizeof(double)));
+    }
+    if (Comm::instance().active()) NB_CUDA(cudaMalloc(&scalar_dev_, 64 * sizeof(double)));
+    if (cfg.x0_host) {
+        NB_CUDA(cudaMemcpyAsync(x_, cfg.x0_host + j0, nl * sizeof(double), cudaMemcpyHostToDevice, stream_));
+        stats_->h2d_bytes += nl * sizeof(double);
+    } else if (cfg.x_dev) {
+        NB_CUDA(cudaMemcpyAsync(x_, cfg.x_dev, nl * sizeof(double), cudaMemcpyDeviceToDevice, stream_));
+    } else
+        return fail("no start point");
+    if (!set_norm_arrays(cfg.x_weights, cfg.xtol_abs)) return false;
+    NB_CUDA(cudaStreamSynchronize(stream_));
+    cand_in_x_ = true;                       // xcur == x at the start (mma.c:220)
+    return true;
+}
+
+bool DeviceBackend::set_norm_arrays(const double *w_host, const double *xtol_abs_host)
+{
+    const size_t nl = geo_.n_local, j0 = geo_.j0;
+    if (w_dev_) { cudaFree(w_dev_); w_dev_ = nullptr; }
+    if (xtol_abs_dev_) { cudaFree(xtol_abs_dev_); xtol_abs_dev_ = nullptr; }
+    if (w_host) {
+        NB_CUDA(cudaMalloc(&w_dev_, geo_.ld * sizeof(double)));
+        NB_CUDA(cudaMemcpyAsync(w_dev_, w_host + j0, nl * sizeof(double), cudaMemcpyHostToDevice, stream_));
+    }
+    if (xtol_abs_host) {
+        NB_CUDA(cudaMalloc(&xtol_abs_dev_, geo_.ld * sizeof(double)));
+        NB_CUDA(cudaMemcpyAsync(xtol_abs_dev_, xtol_abs_host + j0, nl * sizeof(double), cudaMemcpyHostToDevice, stream_));
+    }
+    NB_CUDA(cudaStreamSynchronize(stream_));
+    return true;
+}
+
+// ------------------------------------------------------------------------------------------------
+// sigma
+
+bool DeviceBackend::sigma_init_from(const double *sigma_init_host, double sigma_min)
+{
+    const size_t nl = geo_.n_local;
+    const double *init_dev = nullptr;
+    if (sigma_init_host) {           // xprevprev is free until the second outer iteration: use it as scratch
+        NB_CUDA(cudaMemcpyAsync(xprevprev_, sigma_init_host + geo_.j0, nl * sizeof(double), cudaMemcpyHostToDevice, stream_));
+        stats_->h2d_bytes += nl * sizeof(double);
+        init_dev = xprevprev_;
+    }
+    sigma_init_kernel<<<grid_for(nl), kBlock, 0, stream_>>>(sigma_, lb_, ub_, init_dev, sigma_min, nl);
+    ++stats_->kernel_launches;
+    NB_CUDA(cudaGetLastError());
+    return true;
+}
+
+bool DeviceBackend::init_sigma(double sigma_min) { return sigma_init_from(cfg_.sigma_init, sigma_min); }
+
+// ------------------------------------------------------------------------------------------------
+// user functions
+
+double *DeviceBackend::staging(unsigned rows)
+{
+    (void) rows;
+    const int b = h_grad_next_;
+    h_grad_next_ ^= 1;
+    cudaEventSynchronize(h_grad_done_[b]);    // the previous upload out of this buffer has finished
+    return h_grad_[b];
+}
+
+bool DeviceBackend::host_x_for(Slot slot)
+{
+    // Host callbacks see the full x.  Single rank: one D2H of the shard (= everything).
+    // Several ranks: all-gather the shards on the device, then each rank copies all of it down.
+    if (h_x_slot_ == (int) slot && h_x_epoch_ == x_epoch_) return true;    // already mirrored
+    double *src = slot == kBase ? x_ : xcur_view();
+    Comm &comm = Comm::instance();
+    if (!comm.active()) {
+        NB_CUDA(cudaMemcpyAsync(h_x_, src, geo_.n_local * sizeof(double), cudaMemcpyDeviceToHost, stream_));
+        stats_->d2h_bytes += geo_.n_local * sizeof(double);
+    } else {
+        NB_CUDA(cudaMemcpyAsync(xfull_dev_ + (size_t) comm.rank * shard_cap_, src, geo_.n_local * sizeof(double),
+                                cudaMemcpyDeviceToDevice, stream_));
+        if (comm.all_gather_inplace(xfull_dev_, shard_cap_, stream_, &err_)) return false;
+        for (int r = 0; r < comm.world; ++r) {
+            Geometry gr = Geometry::make(geo_.n, comm.world, r, target_pairs_, pmax_);
+            NB_CUDA(cudaMemcpyAsync(h_x_ + gr.j0, xfull_dev_ + (size_t) r * shard_cap_, gr.n_local * sizeof(double),
+                                    cudaMemcpyDeviceToHost, stream_));
+        }
+        stats_->d2h_bytes += geo_.n * sizeof(double);
+    }
+    NB_CUDA(cudaStreamSynchronize(stream_));
+    h_x_slot_ = (int) slot;
+    h_x_epoch_ = x_epoch_;
+    return true;
+}
+
+bool DeviceBackend::push_grad_rows(Slot slot, int row0, unsigned rows, bool is_objective, const double *host_grad)
+{
+    double *dst = is_objective ? (slot == kBase ? g_ : gcur_) : (slot == kBase ? G_ : Gcur_) + (size_t) row0 * geo_.ld;
+    const int b = host_grad == h_grad_[0] ? 0 : 1;
+    NB_CUDA(cudaMemcpy2DAsync(dst, geo_.ld * sizeof(double), host_grad + geo_.j0, (size_t) geo_.n * sizeof(double),
+                              geo_.n_local * sizeof(double), rows, cudaMemcpyHostToDevice, copy_stream_));
+    NB_CUDA(cudaEventRecord(h_grad_done_[b], copy_stream_));
+    NB_CUDA(cudaStreamWaitEvent(stream_, h_grad_done_[b], 0));     // kernels wait for the upload, the host does not
+    stats_->h2d_bytes += (size_t) rows * geo_.n_local * sizeof(double);
+    return true;
+}
+
+bool DeviceBackend::eval_objective(Slot slot, bool want_grad, double *value)
+{
+    const FuncSpec &fs = cfg_.objective;
+    if (fs.df) {
+        double *xs = slot == kBase ? x_ : xcur_view();
+        double *gs = want_grad ? (slot == kBase ? g_ : gcur_) : nullptr;
+        const double t0 = wall_seconds();
+        double v = fs.df((unsigned) geo_.n_local, geo_.j0, xs, gs, fs.data, stream_);
+        cb_seconds_ += wall_seconds() - t0;
+        Comm &comm = Comm::instance();
+        if (comm.active()) {           // shard contributions add up
+            NB_CUDA(cudaMemcpyAsync(scalar_dev_, &v, sizeof(double), cudaMemcpyHostToDevice, stream_));
+            if (comm.all_reduce_sum(scalar_dev_, 1, stream_, &err_)) return false;
+            NB_CUDA(cudaMemcpyAsync(&v, scalar_dev_, sizeof(double), cudaMemcpyDeviceToHost, stream_));
+            NB_CUDA(cudaStreamSynchronize(stream_));
+        }
+        *value = v;
+        return true;
+    }
+    if (!fs.f) return fail("no objective function");
+    if (!host_x_for(slot)) return false;
+    double *grad = want_grad ? staging(1) : nullptr;
+    const double t0 = wall_seconds();
+    *value = fs.f((unsigned) geo_.n, h_x_, grad, fs.data);
+    cb_seconds_ += wall_seconds() - t0;
+    if (want_grad) return push_grad_rows(slot, 0, 1, true, grad);
+    return true;
+}
+
+bool DeviceBackend::eval_constraint(Slot slot, unsigned ic, unsigned row0, bool want_grad, double *values)
+{
+    const FuncSpec &fs = cfg_.constraints[ic];
+    if (fs.df) {
+        double *xs = slot == kBase ? x_ : xcur_view();
+        double *gs = want_grad ? (slot == kBase ? G_ : Gcur_) + (size_t) row0 * geo_.ld : nullptr;
+        const double t0 = wall_seconds();
+        double v = fs.df((unsigned) geo_.n_local, geo_.j0, xs, gs, fs.data, stream_);
+        cb_seconds_ += wall_seconds() - t0;
+        Comm &comm = Comm::instance();
+        if (comm.active()) {
+            NB_CUDA(cudaMemcpyAsync(scalar_dev_, &v, sizeof(double), cudaMemcpyHostToDevice, stream_));
+            if (comm.all_reduce_sum(scalar_dev_, 1, stream_, &err_)) return false;
+            NB_CUDA(cudaMemcpyAsync(&v, scalar_dev_, sizeof(double), cudaMemcpyDeviceToHost, stream_));
+            NB_CUDA(cudaStreamSynchronize(stream_));
+        }
+        values[0] = v;
+        return true;
+    }
+    if (!host_x_for(slot)) return false;       // usually a no-op: the objective call mirrored x already
+    double *grad = want_grad ? staging(fs.m) : nullptr;
+    const double t0 = wall_seconds();
+    if (fs.f) values[0] = fs.f((unsigned) geo_.n, h_x_, grad, fs.data);        // nlopt_eval_constraint, stop.c:178-184
+    else fs.mf(fs.m, values, (unsigned) geo_.n, h_x_, grad, fs.data);
+    cb_seconds_ += wall_seconds() - t0;
+    if (want_grad) return push_grad_rows(slot, (int) row0, fs.m, false, grad);
+    return true;
+}
+
+// ------------------------------------------------------------------------------------------------
+// dual evaluation
+
+bool DeviceBackend::wait_flag()
+{
+    // The kernel's last CTA writes the sums and then the sequence number into mapped pinned
+    // memory; polling it is a few microseconds cheaper than a stream synchronise per evaluation.
+    const auto t0 = std::chrono::steady_clock::now();
+    unsigned long spins = 0;
+    for (;;) {
+        if (__atomic_load_n(flag_host_, __ATOMIC_ACQUIRE) == seq_) return true;
+        if ((++spins & 0x3fff) == 0) {
+            cudaError_t q = cudaStreamQuery(stream_);
+            if (q != cudaSuccess && q != cudaErrorNotReady) return fail("dual kernel", q);
+            if (q == cudaSuccess) {
+                if (__atomic_load_n(flag_host_, __ATOMIC_ACQUIRE) == seq_) return true;
+                return fail("dual kernel finished without publishing its result");
+            }
+            if (std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > 120.0)
+                return fail("timed out waiting for the dual kernel");
+        }
+    }
+}
+
+bool DeviceBackend::launch_dual(const double *y, const DualScalars &sc, bool store, int chunk0, int chunk_n, bool wait)
+{
+    DualArgs a;
+    std::memset(&a, 0, sizeof a);
+    a.x = x_; a.lb = lb_; a.ub = ub_; a.sigma = sigma_; a.g = g_; a.G = G_;
+    a.xcur = xcur_;
+    a.ld = geo_.ld;
+    a.npairs = geo_.npairs; a.pair0 = geo_.pair0;
+    a.nseg_total = geo_.S; a.seg0 = geo_.seg0; a.segs_per_vshard = geo_.P; a.local_vshards = geo_.local_vshards;
+    a.partials = partials_; a.vsums = vsums_; a.tickets = tickets_; a.out_dev = out_dev_;
+    a.out_host = out_host_; a.flag_host = flag_host_;
+    a.seq = ++seq_;
+    a.publish_host = Comm::instance().active() ? 0 : 1;
+    a.nvp = nvp_;
+    a.m = (int) m_;
+    a.chunk0 = chunk0; a.chunk_n = chunk_n;
+    a.rho = sc.rho;
+    a.half_rho = 0.5 * sc.rho;
+    a.active = 0;
+    double u = sc.rho;                                   // ccsa_quadratic.c:116-120, j-independent
+    for (unsigned i = 0; i < m_; ++i) {
+        a.y[i] = y[i];
+        a.rhoc[i] = sc.rhoc[i];
+        a.half_rhoc[i] = 0.5 * sc.rhoc[i];
+        if (!(variant_ == kMMA && std::isnan(sc.fcval[i]))) a.active |= 1u << i;
+        u += sc.rhoc[i] * y[i];
+    }
+    a.u_ccsaq = u;
+
+    const int maxm = pick_maxm((int) m_);
+    const int grid = (int) geo_.nseg_local;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (time_kernels_) {
+        if (ev_used_ + 2 > ev_pool_.size()) {
+            if (ev_pool_.size() >= 8192) drain_events();
+            else
+                for (int k = 0; k < 512; ++k) { cudaEvent_t e; cudaEventCreate(&e); ev_pool_.push_back(e); }
+        }
+        e0 = ev_pool_[ev_used_++];
+        e1 = ev_pool_[ev_used_++];
+        cudaEventRecord(e0, stream_);
+    }
+    if (variant_ == kMMA) launch_by_m<0>(maxm, store, grid, stream_, a);
+    else launch_by_m<1>(maxm, store, grid, stream_, a);
+    if (time_kernels_) cudaEventRecord(e1, stream_);
+    ++stats_->kernel_launches;
+    NB_CUDA(cudaGetLastError());
+    if (!a.publish_host) {
+        const int nv = 3 + (maxm > 0 ? maxm : 1);
+        if (Comm::instance().all_gather_inplace(out_dev_, (size_t) geo_.local_vshards * nvp_, stream_, &err_)) return false;
+        publish_kernel<<<1, 32, 0, stream_>>>(out_dev_, nv, nvp_, out_host_, flag_host_, a.seq);
+        ++stats_->kernel_launches;
+        NB_CUDA(cudaGetLastError());
+    }
+    return wait ? wait_flag() : true;
+}
+
+bool DeviceBackend::dual_eval(const double *y, const DualScalars &sc, bool materialize, DualSums *out)
+{
+    if (materialize) { cand_in_x_ = false; ++x_epoch_; }   // xcur_ is about to hold the candidate
+    const int maxm = pick_maxm((int) m_);
+    const int step = maxm > 0 ? maxm : 1;
+    int c0 = 0;
+    do {
+        const int cn = (int) m_ - c0 < step ? (int) m_ - c0 : step;
+        if (!launch_dual(y, sc, materialize && c0 == 0, c0, cn, true)) return false;
+        if (c0 == 0) {
+            out->val = out_host_[0];
+            out->gval = out_host_[1];
+            out->wval = out_host_[2];
+        }
+        for (int k = 0; k < cn; ++k) out->gc[c0 + k] = out_host_[3 + k];
+        c0 += step;
+    } while (c0 < (int) m_);
+    return true;
+}
+
+void DeviceBackend::drain_events()
+{
+    if (!ev_used_) return;
+    cudaStreamSynchronize(stream_);
+    double ms = 0;
+    for (size_t i = 0; i + 1 < ev_used_; i += 2) {
+        float t = 0;
+        if (cudaEventElapsedTime(&t, ev_pool_[i], ev_pool_[i + 1]) == cudaSuccess) ms += t;
+    }
+    stats_->seconds_dual_kernel += ms * 1e-3;
+    ev_used_ = 0;
+}
+
+bool DeviceBackend::time_dual(const double *y, const DualScalars &sc, bool materialize, int iters, double *ms_avg)
+{
+    cudaEvent_t e0, e1;
+    NB_CUDA(cudaEventCreate(&e0));
+    NB_CUDA(cudaEventCreate(&e1));
+    const int cn = (int) m_ < 16 ? (int) m_ : 16;
+    NB_CUDA(cudaEventRecord(e0, stream_));
+    for (int it = 0; it < iters; ++it)
+        if (!launch_dual(y, sc, materialize, 0, cn, false)) return false;
+    NB_CUDA(cudaEventRecord(e1, stream_));
+    NB_CUDA(cudaStreamSynchronize(stream_));
+    float ms = 0;
+    NB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (materialize) cand_in_x_ = false;
+    *ms_avg = (double) ms / iters;
+    return true;
+}
+
+// ------------------------------------------------------------------------------------------------
+// acceptance and outer-iteration bookkeeping
+
+void DeviceBackend::accept_candidate()
+{
+    // mma.c:374-377 copies xcur, dfdx_cur, dfcdx_cur over x, dfdx, dfcdx: here three pointer swaps
+    std::swap(x_, xcur_);
+    std::swap(g_, gcur_);
+    std::swap(G_, Gcur_);
+    cand_in_x_ = true;
+    if (h_x_slot_ == (int) kCandidate && h_x_epoch_ == x_epoch_) h_x_slot_ = (int) kBase;   // same values, new name
+}
+
+bool DeviceBackend::first_outer()
+{
+    NB_CUDA(cudaMemcpyAsync(xprev_, xcur_view(), geo_.ld * sizeof(double), cudaMemcpyDeviceToDevice, stream_));
+    return true;
+}
+
+bool DeviceBackend::end_outer(unsigned k, double sigma_min, double *dnorm, double *xnorm, bool *all_below_abs)
+{
+    EndOuterArgs a;
+    std::memset(&a, 0, sizeof a);
+    a.xcur = xcur_view();
+    a.xprev = xprev_; a.xprevprev = xprevprev_; a.sigma = sigma_;
+    a.lb = lb_; a.ub = ub_; a.w = w_dev_; a.xtol_abs = xtol_abs_dev_;
+    a.n_local = geo_.n_local; a.npairs = geo_.npairs; a.pair0 = geo_.pair0;
+    a.nseg_total = geo_.S; a.seg0 = geo_.seg0; a.segs_per_vshard = geo_.P; a.local_vshards = geo_.local_vshards;
+    a.partials = partials_; a.vsums = vsums_; a.tickets = tickets_; a.out_dev = out_dev_;
+    a.out_host = out_host_; a.flag_host = flag_host_;
+    a.seq = ++seq_;
+    a.publish_host = Comm::instance().active() ? 0 : 1;
+    a.nvp = nvp_;
+    a.update_sigma = k > 1;
+    a.kappa = variant_ == kMMA ? 0.01 : 1e-8;
+    a.sigma_min = sigma_min;
+    end_outer_kernel<<<(int) geo_.nseg_local, kBlock, 0, stream_>>>(a);
+    ++stats_->kernel_launches;
+    NB_CUDA(cudaGetLastError());
+    if (!a.publish_host) {
+        if (Comm::instance().all_gather_inplace(out_dev_, (size_t) geo_.local_vshards * nvp_, stream_, &err_)) return false;
+        publish_kernel<<<1, 32, 0, stream_>>>(out_dev_, 3, nvp_, out_host_, flag_host_, a.seq);
+        ++stats_->kernel_launches;
+        NB_CUDA(cudaGetLastError());
+    }
+    if (!wait_flag()) return false;
+    *dnorm = out_host_[0];
+    *xnorm = out_host_[1];
+    *all_below_abs = out_host_[2] == 0.0;
+    return true;
+}
+
+bool DeviceBackend::fetch_x(double *x_out)
+{
+    drain_events();
+    if (cfg_.x_dev && x_out == cfg_.x_dev) {
+        NB_CUDA(cudaMemcpyAsync(x_out, x_, geo_.n_local * sizeof(double), cudaMemcpyDeviceToDevice, stream_));
+        NB_CUDA(cudaStreamSynchronize(stream_));
+        return true;
+    }
+    Comm &comm = Comm::instance();
+    if (!comm.active()) {
+        NB_CUDA(cudaMemcpyAsync(x_out, x_, geo_.n_local * sizeof(double), cudaMemcpyDeviceToHost, stream_));
+        NB_CUDA(cudaStreamSynchronize(stream_));
+        stats_->d2h_bytes += geo_.n_local * sizeof(double);
+        return true;
+    }
+    if (!h_x_) NB_CUDA(cudaHostAlloc(&h_x_, (size_t) geo_.n * sizeof(double), cudaHostAllocDefault));
+    if (!xfull_dev_) NB_CUDA(cudaMalloc(&xfull_dev_, (size_t) comm.world * shard_cap_ * sizeof(double)));
+    h_x_slot_ = -1;
+    if (!host_x_for(kBase)) return false;
+    std::memcpy(x_out, h_x_, (size_t) geo_.n * sizeof(double));
+    return true;
+}
+
+// ------------------------------------------------------------------------------------------------
+// kernel-level access
+
+double *DeviceBackend::array(const char *which)
+{
+    const std::string w = which;
+    if (w == "x") return x_;
+    if (w == "xcur") return xcur_view();
+    if (w == "xprev") return xprev_;
+    if (w == "xprevprev") return xprevprev_;
+    if (w == "lb") return lb_;
+    if (w == "ub") return ub_;
+    if (w == "sigma") return sigma_;
+    if (w == "grad_f") return g_;
+    if (w == "grad_f_cur") return gcur_;
+    return nullptr;
+}
+
+bool DeviceBackend::upload(const char *which, const double *host)
+{
+    double *dst = array(which);
+    if (std::string(which) == "xcur") { dst = xcur_; cand_in_x_ = false; }
+    if (!dst) return fail(std::string("unknown array ") + which);
+    NB_CUDA(cudaMemcpyAsync(dst, host + geo_.j0, geo_.n_local * sizeof(double), cudaMemcpyHostToDevice, stream_));
+    NB_CUDA(cudaStreamSynchronize(stream_));
+    return true;
+}
+
+bool DeviceBackend::upload_grad_c(const double *host)
+{
+    if (!m_) return true;
+    NB_CUDA(cudaMemcpy2DAsync(G_, geo_.ld * sizeof(double), host + geo_.j0, (size_t) geo_.n * sizeof(double),
+                              geo_.n_local * sizeof(double), m_, cudaMemcpyHostToDevice, stream_));
+    NB_CUDA(cudaStreamSynchronize(stream_));
+    return true;
+}
+
+bool DeviceBackend::download(const char *which, double *host)
+{
+    const std::string w = which;
+    if (w == "grad_c") {
+        if (!m_) return true;
+        NB_CUDA(cudaMemcpy2DAsync(host + geo_.j0, (size_t) geo_.n * sizeof(double), G_, geo_.ld * sizeof(double),
+                                  geo_.n_local * sizeof(double), m_, cudaMemcpyDeviceToHost, stream_));
+        NB_CUDA(cudaStreamSynchronize(stream_));
+        return true;
+    }
+    double *src = array(which);
+    if (!src) return fail(std::string("unknown array ") + which);
+    NB_CUDA(cudaMemcpyAsync(host + geo_.j0, src, geo_.n_local * sizeof(double), cudaMemcpyDeviceToHost, stream_));
+    NB_CUDA(cudaStreamSynchronize(stream_));
+    return true;
+}
+
+bool DeviceBackend::fill_synthetic(unsigned long long seed)
+{
+    SynthArgs a;
+    a.x = x_; a.lb = lb_; a.ub = ub_; a.sigma = sigma_; a.g = g_; a.G = G_;
+    a.ld = geo_.ld; a.n_local = geo_.n_local; a.j0 = geo_.j0; a.seed = seed; a.m = (int) m_;
+    synth_fill_kernel<<<grid_for(geo_.n_local), kBlock, 0, stream_>>>(a);
+    NB_CUDA(cudaGetLastError());
+    NB_CUDA(cudaStreamSynchronize(stream_));
+    cand_in_x_ = true;
+    return true;
+}
+
+bool DeviceBackend::configure(const char *key, long long value)
+{
+    const std::string k = key;
+    if (k == "time_kernels") { time_kernels_ = value != 0; return true; }
+    if (k == "pmax" || k == "target_pairs") {
+        if (value < 1) return fail("bad value");
+        if (k == "pmax") pmax_ = (unsigned) value; else target_pairs_ = (unsigned) value;
+        if (pool_) {
+            Geometry g2 = Geometry::make(geo_.n, geo_.world, geo_.rank, target_pairs_, pmax_);
+            if (g2.ld != geo_.ld || g2.j0 != geo_.j0)
+                return fail("changing the segment geometry of a sharded, allocated problem is not supported");
+            geo_ = g2;
+            return alloc_workspace();
+        }
+        return true;
+    }
+    return fail(std::string("unknown key ") + key);
+}
+
+long long DeviceBackend::query(const char *key) const
+{
+    const std::string k = key;
+    if (k == "segments") return geo_.S;
+    if (k == "segments_local") return geo_.nseg_local;
+    if (k == "P") return geo_.P;
+    if (k == "n_local") return (long long) geo_.n_local;
+    if (k == "j0") return (long long) geo_.j0;
+    if (k == "ld") return (long long) geo_.ld;
+    if (k == "launches") return stats_->kernel_launches;
+    if (k == "maxm") return pick_maxm((int) m_);
+    return -1;
+}
+
+Backend *make_backend(const BackendConfig &cfg, std::string *err)
+{
+    DeviceBackend *be = new DeviceBackend();
+    if (!be->setup(cfg)) {
+        if (err) *err = be->error();
+        delete be;
+        return nullptr;
+    }
+    return be;
+}
+
+}  // namespace nb200
+
+// ================================================================================================
+// C ABI: kernel-level access (include/nlopt_b200.h).  A handle is a DeviceBackend without user
+// callbacks; the functions below are what the reference's static dual_func (mma.c:59,
+// ccsa_quadratic.c:79) and the O(n) loops around it (mma.c:202-210, :264-265, :418-442) would
+// bind to.
+// ================================================================================================
+
+struct nlopt_b200_dual_s {
+    nb200::DeviceBackend be;
+    std::vector<double> c0, rhoc, gc;
+    double f0 = 0, rho = 1;
+    std::string err;
+};
+
+namespace {
+int ok(nlopt_b200_dual h, bool good)
+{
+    if (!good) h->err = h->be.error();
+    return good ? 0 : -1;
+}
+}  // namespace
+
+extern "C" {
+
+nlopt_b200_dual nlopt_b200_dual_create(int variant, unsigned n, unsigned m)
+{
+    nlopt_b200_dual h = new nlopt_b200_dual_s;
+    h->c0.assign(m, 0.0);
+    h->rhoc.assign(m, 1.0);
+    h->gc.assign(m > 0 ? m : 1, 0.0);
+    if (!h->be.setup_raw(variant == NLOPT_B200_MMA ? nb200::kMMA : nb200::kCCSAQ, n, m)) {
+        std::fprintf(stderr, "nlopt_b200_dual_create: %s\n", h->be.error().c_str());
+        delete h;
+        return nullptr;
+    }
+    return h;
+}
+
+void nlopt_b200_dual_destroy(nlopt_b200_dual h) { delete h; }
+
+const char *nlopt_b200_dual_errmsg(nlopt_b200_dual h) { return h ? h->err.c_str() : "null handle"; }
+
+int nlopt_b200_dual_upload(nlopt_b200_dual h, const double *x, const double *lb, const double *ub,
+                           const double *sigma, const double *grad_f, const double *grad_c)
+{
+    bool good = true;
+    if (x) good = good && h->be.upload("x", x);
+    if (lb) good = good && h->be.upload("lb", lb);
+    if (ub) good = good && h->be.upload("ub", ub);
+    if (sigma) good = good && h->be.upload("sigma", sigma);
+    if (grad_f) good = good && h->be.upload("grad_f", grad_f);
+    if (grad_c) good = good && h->be.upload_grad_c(grad_c);
+    return ok(h, good);
+}
+
+int nlopt_b200_dual_fill_synthetic(nlopt_b200_dual h, unsigned long long seed) { return ok(h, h->be.fill_synthetic(seed)); }
+
+int nlopt_b200_dual_set_scalars(nlopt_b200_dual h, double f0, double rho, const double *c0, const double *rhoc)
+{
+    h->f0 = f0;
+    h->rho = rho;
+    for (size_t i = 0; i < h->c0.size(); ++i) {
+        h->c0[i] = c0[i];
+        h->rhoc[i] = rhoc[i];
+    }
+    return 0;
+}
+
+int nlopt_b200_dual_eval(nlopt_b200_dual h, const double *y, int want_xcur, double *out, double *grad)
+{
+    nb200::DualScalars sc;
+    sc.fval = h->f0;
+    sc.rho = h->rho;
+    sc.fcval = h->c0.data();
+    sc.rhoc = h->rhoc.data();
+    nb200::DualSums s;
+    s.gc = h->gc.data();
+    if (!h->be.dual_eval(y, sc, want_xcur != 0, &s)) return ok(h, false);
+    // add the O(m) constants exactly as the driver does (mma.c:75-78)
+    const unsigned m = h->be.m();
+    double val = h->f0;
+    for (unsigned i = 0; i < m; ++i) {
+        const double ci = (h->be.is_mma() && std::isnan(h->c0[i])) ? 0.0 : h->c0[i];
+        val += y[i] * ci;
+        out[3 + i] = ci + s.gc[i];
+        if (grad) grad[i] = -out[3 + i];
+    }
+    val += s.val;
+    out[0] = -val;
+    out[1] = h->f0 + s.gval;
+    out[2] = s.wval;
+    return 0;
+}
+
+int nlopt_b200_dual_download_xcur(nlopt_b200_dual h, double *xcur_host) { return ok(h, h->be.download("xcur", xcur_host)); }
+
+int nlopt_b200_dual_download(nlopt_b200_dual h, const char *which, double *host) { return ok(h, h->be.download(which, host)); }
+
+int nlopt_b200_dual_sigma_init(nlopt_b200_dual h, const double *sigma_init_host, double sigma_min)
+{
+    return ok(h, h->be.sigma_init_from(sigma_init_host, sigma_min));
+}
+
+int nlopt_b200_dual_set_prev(nlopt_b200_dual h, const double *xcur, const double *xprev, const double *xprevprev)
+{
+    bool good = true;
+    if (xcur) good = good && h->be.upload("xcur", xcur);
+    if (xprev) good = good && h->be.upload("xprev", xprev);
+    if (xprevprev) good = good && h->be.upload("xprevprev", xprevprev);
+    return ok(h, good);
+}
+
+int nlopt_b200_dual_end_outer(nlopt_b200_dual h, int k, double sigma_min, const double *x_weights_host,
+                              const double *xtol_abs_host, double *norms, int *all_below_xtol_abs)
+{
+    if (!h->be.set_norm_arrays(x_weights_host, xtol_abs_host)) return ok(h, false);
+    bool below = false;
+    if (!h->be.end_outer((unsigned) k, sigma_min, &norms[0], &norms[1], &below)) return ok(h, false);
+    *all_below_xtol_abs = below ? 1 : 0;
+    return 0;
+}
+
+int nlopt_b200_dual_time(nlopt_b200_dual h, const double *y, int want_xcur, int iters, double *ms_avg)
+{
+    nb200::DualScalars sc;
+    sc.fval = h->f0;
+    sc.rho = h->rho;
+    sc.fcval = h->c0.data();
+    sc.rhoc = h->rhoc.data();
+    return ok(h, h->be.time_dual(y, sc, want_xcur != 0, iters, ms_avg));
+}
+
+int nlopt_b200_dual_configure(nlopt_b200_dual h, const char *key, long long value) { return ok(h, h->be.configure(key, value)); }
+
+long long nlopt_b200_dual_query(nlopt_b200_dual h, const char *key) { return h->be.query(key); }
+
+void nlopt_b200_shard_range(unsigned long long n, int rank, int world, unsigned long long *j0, unsigned long long *count)
+{
+    nb200::Geometry g = nb200::Geometry::make(n, world, rank, nb200::kDefaultTargetPairs, nb200::kDefaultPmax);
+    *j0 = g.j0;
+    *count = g.n_local;
+}
+
+int nlopt_b200_device_count(void)
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) return 0;
+    return e == cudaSuccess ? n : -1;
+}
+
+const char *nlopt_b200_build_info(void)
+{
+    return "nlopt_b200: NLOPT_LD_MMA / NLOPT_LD_CCSAQ on CUDA sm_100a, fp64, exact-rounding (no FMA contraction); "
+           "built " __DATE__;
+}
+
+}  // extern "C"

@@ -1,0 +1,120 @@
+// device_backend.hpp -- HBM-resident state + kernel launches of the MMA/CCSAQ path.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <string>
+#include <vector>
+
+#include "backend_factory.hpp"
+#include "geometry.hpp"
+
+namespace nb200 {
+
+// Data layout in HBM (per rank): one cudaMalloc carved into (9 + 2m) arrays of `ld` doubles,
+//   x xcur xprev xprevprev lb ub sigma grad_f grad_f_cur | grad_c[m][ld] | grad_c_cur[m][ld]
+// ld = shard length rounded up to 32 doubles, so every array and every row is 256-byte aligned.
+// Padding lanes carry sigma = 0, which both dual formulas skip (mma.c:96-99).
+class DeviceBackend : public Backend {
+public:
+    DeviceBackend();
+    ~DeviceBackend() override;
+
+    bool setup(const BackendConfig &cfg);           // allocate + upload bounds/start point
+    bool setup_raw(Variant v, unsigned n, unsigned m);   // kernel-level handle: arrays only
+
+    // ---- Backend ----
+    unsigned n() const override { return (unsigned) geo_.n; }
+    unsigned m() const override { return m_; }
+    unsigned num_constraint_objects() const override { return (unsigned) cfg_.constraints.size(); }
+    unsigned constraint_dim(unsigned ic) const override { return cfg_.constraints[ic].m; }
+    bool init_sigma(double sigma_min) override;
+    bool eval_objective(Slot slot, bool want_grad, double *value) override;
+    bool eval_constraint(Slot slot, unsigned ic, unsigned row0, bool want_grad, double *values) override;
+    bool dual_eval(const double *y, const DualScalars &sc, bool materialize, DualSums *out) override;
+    void accept_candidate() override;
+    bool first_outer() override;
+    bool end_outer(unsigned k, double sigma_min, double *dnorm, double *xnorm, bool *all_below_abs) override;
+    bool fetch_x(double *x_out) override;
+    const std::string &error() const override { return err_; }
+    double seconds_in_callbacks() const override { return cb_seconds_; }
+
+    // ---- kernel-level access (nlopt_b200_dual_* C ABI) ----
+    bool upload(const char *which, const double *host);          // which: x lb ub sigma grad_f xcur xprev xprevprev
+    bool upload_grad_c(const double *host_rowmajor_m_by_n);
+    bool download(const char *which, double *host);
+    bool fill_synthetic(unsigned long long seed);
+    bool sigma_init_from(const double *sigma_init_host, double sigma_min);
+    bool set_norm_arrays(const double *x_weights_host, const double *xtol_abs_host);
+    bool time_dual(const double *y, const DualScalars &sc, bool materialize, int iters, double *ms_avg);
+    bool configure(const char *key, long long value);
+    long long query(const char *key) const;
+    const Geometry &geometry() const { return geo_; }
+    bool is_mma() const { return variant_ == kMMA; }
+
+private:
+    bool fail(const char *what, cudaError_t e);
+    bool fail(const std::string &what);
+    bool alloc_state();
+    void free_state();
+    bool alloc_workspace();
+    double *array(const char *which);
+    double *xcur_view() { return cand_in_x_ ? x_ : xcur_; }
+    bool launch_dual(const double *y, const DualScalars &sc, bool store, int chunk0, int chunk_n, bool wait);
+    bool wait_flag();
+    bool host_x_for(Slot slot);                      // bring the slot's x to pinned host memory (cached per epoch)
+    bool push_grad_rows(Slot slot, int row0, unsigned rows, bool is_objective, const double *host_grad);
+    double *staging(unsigned rows);
+
+    BackendConfig cfg_;
+    Variant variant_ = kMMA;
+    unsigned m_ = 0;
+    Geometry geo_;
+    unsigned target_pairs_ = kDefaultTargetPairs, pmax_ = kDefaultPmax;
+    int device_ = 0;
+
+    // device state
+    double *pool_ = nullptr;
+    double *x_ = nullptr, *xcur_ = nullptr, *xprev_ = nullptr, *xprevprev_ = nullptr, *lb_ = nullptr, *ub_ = nullptr,
+           *sigma_ = nullptr, *g_ = nullptr, *gcur_ = nullptr, *G_ = nullptr, *Gcur_ = nullptr;
+    double *w_dev_ = nullptr, *xtol_abs_dev_ = nullptr;
+    bool cand_in_x_ = true;       // the latest candidate's values live in x_ (start point / just accepted)
+    bool bounds_set_ = false;
+
+    // reduction workspace + result mailbox
+    double *partials_ = nullptr, *vsums_ = nullptr, *out_dev_ = nullptr;
+    unsigned *tickets_ = nullptr;
+    double *out_host_ = nullptr;                     // mapped pinned
+    unsigned long long *flag_host_ = nullptr;        // mapped pinned
+    unsigned long long seq_ = 0;
+    int nvp_ = 24;
+
+    // staging for host callbacks
+    double *h_x_ = nullptr;
+    double *h_grad_[2] = {nullptr, nullptr};
+    size_t h_grad_cap_ = 0;
+    int h_grad_next_ = 0;
+    cudaEvent_t h_grad_done_[2] = {nullptr, nullptr};
+    double *xfull_dev_ = nullptr;                    // multi-rank host callbacks: gathered x
+    double *scalar_dev_ = nullptr;                   // multi-rank device callbacks: value all-reduce
+    size_t shard_cap_ = 0;                           // largest padded shard length over all ranks
+    unsigned long long x_epoch_ = 1, h_x_epoch_ = 0; // which (slot, epoch) h_x_ currently mirrors
+    int h_x_slot_ = -1;
+
+    cudaStream_t stream_ = nullptr, copy_stream_ = nullptr;
+    cudaEvent_t copied_ = nullptr;
+
+    // optional per-launch timing of the dual kernel
+    bool time_kernels_ = false;
+    std::vector<cudaEvent_t> ev_pool_;
+    size_t ev_used_ = 0;
+    void drain_events();
+
+    std::string err_;
+    double cb_seconds_ = 0;
+    nlopt_b200_stats local_stats_{};
+    nlopt_b200_stats *stats_ = &local_stats_;
+    unsigned max_cdim_ = 1;
+};
+
+}  // namespace nb200

@@ -1,0 +1,859 @@
+// nlopt_api.cpp -- the NLopt object API (C ABI) of libnlopt_b200.so.
+//
+// Same names, arguments, return codes and side effects as the reference's
+// src/api/options.c, src/api/general.c and the MMA/CCSAQ slice of src/api/optimize.c
+// (cited per function).  The object is a C++ struct of our own; only two algorithms run.
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "backend_factory.hpp"
+#include "ccsa_driver.hpp"
+#include "dual_mma.hpp"
+#include "nlopt_object.hpp"
+
+using nb200::ConstraintRec;
+using nb200::NamedParam;
+
+namespace {
+
+const double kInf = HUGE_VAL;
+
+void set_err(nlopt_opt opt, const char *fmt, ...)
+{
+    if (!opt) return;
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    std::vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    opt->errmsg = buf;
+    opt->has_errmsg = true;
+}
+
+void clear_err(nlopt_opt opt)
+{
+    if (opt) { opt->errmsg.clear(); opt->has_errmsg = false; }
+}
+
+// nlopt_istiny (stop.c:230-245): zero or subnormal
+bool is_tiny(double x) { return x == 0.0 || std::fpclassify(x) == FP_SUBNORMAL; }
+
+// options.c:375-377 / :429-431: a subnormally thin interval is snapped shut
+void snap_lower(nlopt_opt o, unsigned i)
+{
+    if (o->lb[i] < o->ub[i] && is_tiny(o->ub[i] - o->lb[i])) o->lb[i] = o->ub[i];
+}
+void snap_upper(nlopt_opt o, unsigned i)
+{
+    if (o->lb[i] < o->ub[i] && is_tiny(o->ub[i] - o->lb[i])) o->ub[i] = o->lb[i];
+}
+
+bool is_auglag(nlopt_algorithm a)
+{
+    return a == NLOPT_AUGLAG || a == NLOPT_AUGLAG_EQ || a == NLOPT_LN_AUGLAG || a == NLOPT_LN_AUGLAG_EQ
+        || a == NLOPT_LD_AUGLAG || a == NLOPT_LD_AUGLAG_EQ;
+}
+// options.c:549-554
+bool inequality_ok(nlopt_algorithm a)
+{
+    return a == NLOPT_LD_MMA || a == NLOPT_LD_CCSAQ || a == NLOPT_LD_SLSQP || a == NLOPT_LN_COBYLA || is_auglag(a)
+        || a == NLOPT_GN_ISRES || a == NLOPT_GN_ORIG_DIRECT || a == NLOPT_GN_ORIG_DIRECT_L || a == NLOPT_GN_AGS;
+}
+// options.c:617-622
+bool equality_ok(nlopt_algorithm a)
+{
+    return is_auglag(a) || a == NLOPT_LD_SLSQP || a == NLOPT_GN_ISRES || a == NLOPT_LN_COBYLA;
+}
+
+void munge_all(nlopt_opt o, std::vector<ConstraintRec> &v)
+{
+    if (o->munge_on_destroy)
+        for (auto &c : v) o->munge_on_destroy(c.f_data);
+}
+
+// options.c:504-547
+nlopt_result add_constraint(nlopt_opt opt, std::vector<ConstraintRec> &list, unsigned fm, nlopt_func fc,
+                            nlopt_mfunc mfc, nlopt_b200_dfunc dfc, nlopt_precond pre, void *data, const double *tol)
+{
+    const int kinds = (fc != nullptr) + (mfc != nullptr) + (dfc != nullptr);
+    if (kinds != 1 || ((fc || dfc) && fm != 1)) return NLOPT_INVALID_ARGS;
+    if (tol)
+        for (unsigned i = 0; i < fm; ++i)
+            if (tol[i] < 0) { set_err(opt, "negative constraint tolerance"); return NLOPT_INVALID_ARGS; }
+    ConstraintRec r;
+    r.m = fm; r.f = fc; r.mf = mfc; r.df = dfc; r.pre = pre; r.f_data = data;
+    r.tol.assign(fm, 0.0);
+    if (tol) r.tol.assign(tol, tol + fm);
+    try { list.push_back(r); } catch (const std::bad_alloc &) { return NLOPT_OUT_OF_MEMORY; }
+    return NLOPT_SUCCESS;
+}
+
+struct AlgInfo { const char *id; const char *desc; };
+// general.c:39-98 (descriptions) and :112-160 (ids)
+const AlgInfo kAlgs[NLOPT_NUM_ALGORITHMS] = {
+    {"GN_DIRECT", "DIRECT (global, no-derivative)"},
+    {"GN_DIRECT_L", "DIRECT-L (global, no-derivative)"},
+    {"GN_DIRECT_L_RAND", "Randomized DIRECT-L (global, no-derivative)"},
+    {"GN_DIRECT_NOSCAL", "Unscaled DIRECT (global, no-derivative)"},
+    {"GN_DIRECT_L_NOSCAL", "Unscaled DIRECT-L (global, no-derivative)"},
+    {"GN_DIRECT_L_RAND_NOSCAL", "Unscaled Randomized DIRECT-L (global, no-derivative)"},
+    {"GN_ORIG_DIRECT", "Original DIRECT version (global, no-derivative)"},
+    {"GN_ORIG_DIRECT_L", "Original DIRECT-L version (global, no-derivative)"},
+    {"GD_STOGO", "StoGO (NOT COMPILED)"},
+    {"GD_STOGO_RAND", "StoGO randomized (NOT COMPILED)"},
+    {"NLOPT_LD_LBFGS_NOCEDAL", "original L-BFGS code by Nocedal et al. (NOT COMPILED)"},
+    {"LD_LBFGS", "Limited-memory BFGS (L-BFGS) (local, derivative-based)"},
+    {"LN_PRAXIS", "Principal-axis, praxis (local, no-derivative)"},
+    {"LD_VAR1", "Limited-memory variable-metric, rank 1 (local, derivative-based)"},
+    {"LD_VAR2", "Limited-memory variable-metric, rank 2 (local, derivative-based)"},
+    {"LD_TNEWTON", "Truncated Newton (local, derivative-based)"},
+    {"LD_TNEWTON_RESTART", "Truncated Newton with restarting (local, derivative-based)"},
+    {"LD_TNEWTON_PRECOND", "Preconditioned truncated Newton (local, derivative-based)"},
+    {"LD_TNEWTON_PRECOND_RESTART", "Preconditioned truncated Newton with restarting (local, derivative-based)"},
+    {"GN_CRS2_LM", "Controlled random search (CRS2) with local mutation (global, no-derivative)"},
+    {"GN_MLSL", "Multi-level single-linkage (MLSL), random (global, no-derivative)"},
+    {"GD_MLSL", "Multi-level single-linkage (MLSL), random (global, derivative)"},
+    {"GN_MLSL_LDS", "Multi-level single-linkage (MLSL), quasi-random (global, no-derivative)"},
+    {"GD_MLSL_LDS", "Multi-level single-linkage (MLSL), quasi-random (global, derivative)"},
+    {"LD_MMA", "Method of Moving Asymptotes (MMA) (local, derivative)"},
+    {"LN_COBYLA", "COBYLA (Constrained Optimization BY Linear Approximations) (local, no-derivative)"},
+    {"LN_NEWUOA", "NEWUOA unconstrained optimization via quadratic models (local, no-derivative)"},
+    {"LN_NEWUOA_BOUND", "Bound-constrained optimization via NEWUOA-based quadratic models (local, no-derivative)"},
+    {"LN_NELDERMEAD", "Nelder-Mead simplex algorithm (local, no-derivative)"},
+    {"LN_SBPLX", "Sbplx variant of Nelder-Mead (re-implementation of Rowan's Subplex) (local, no-derivative)"},
+    {"LN_AUGLAG", "Augmented Lagrangian method (local, no-derivative)"},
+    {"LD_AUGLAG", "Augmented Lagrangian method (local, derivative)"},
+    {"LN_AUGLAG_EQ", "Augmented Lagrangian method for equality constraints (local, no-derivative)"},
+    {"LD_AUGLAG_EQ", "Augmented Lagrangian method for equality constraints (local, derivative)"},
+    {"LN_BOBYQA", "BOBYQA bound-constrained optimization via quadratic models (local, no-derivative)"},
+    {"GN_ISRES", "ISRES evolutionary constrained optimization (global, no-derivative)"},
+    {"AUGLAG", "Augmented Lagrangian method (needs sub-algorithm)"},
+    {"AUGLAG_EQ", "Augmented Lagrangian method for equality constraints (needs sub-algorithm)"},
+    {"G_MLSL", "Multi-level single-linkage (MLSL), random (global, needs sub-algorithm)"},
+    {"G_MLSL_LDS", "Multi-level single-linkage (MLSL), quasi-random (global, needs sub-algorithm)"},
+    {"LD_SLSQP", "Sequential Quadratic Programming (SQP) (local, derivative)"},
+    {"LD_CCSAQ",
+     "CCSA (Conservative Convex Separable Approximations) with simple quadratic approximations (local, derivative)"},
+    {"GN_ESCH", "ESCH evolutionary strategy"},
+    {"GN_AGS", "AGS (NOT COMPILED)"},
+};
+
+struct ResName { int code; const char *name; };
+const ResName kResults[] = {   // general.c:180-196
+    {NLOPT_FAILURE, "FAILURE"}, {NLOPT_INVALID_ARGS, "INVALID_ARGS"}, {NLOPT_OUT_OF_MEMORY, "OUT_OF_MEMORY"},
+    {NLOPT_ROUNDOFF_LIMITED, "ROUNDOFF_LIMITED"}, {NLOPT_FORCED_STOP, "FORCED_STOP"}, {NLOPT_SUCCESS, "SUCCESS"},
+    {NLOPT_STOPVAL_REACHED, "STOPVAL_REACHED"}, {NLOPT_FTOL_REACHED, "FTOL_REACHED"},
+    {NLOPT_XTOL_REACHED, "XTOL_REACHED"}, {NLOPT_MAXEVAL_REACHED, "MAXEVAL_REACHED"},
+    {NLOPT_MAXTIME_REACHED, "MAXTIME_REACHED"},
+};
+
+// maximisation = minimisation of the negated function (optimize.c:969-989)
+struct FlipData { nlopt_func f; void *data; };
+double flipped(unsigned n, const double *x, double *grad, void *p)
+{
+    FlipData *d = static_cast<FlipData *>(p);
+    const double v = d->f(n, x, grad, d->data);
+    if (grad)
+        for (unsigned i = 0; i < n; ++i) grad[i] = -grad[i];
+    return -v;
+}
+
+nlopt_result run_ccsa(nlopt_opt opt, double *x_host, double *x_dev, double *minf);
+
+}  // namespace
+
+extern "C" {
+
+/* ------------------------------------------------------------------ names / version */
+
+const char *nlopt_algorithm_name(nlopt_algorithm a)
+{
+    if ((int) a < 0 || a >= NLOPT_NUM_ALGORITHMS) return "UNKNOWN";
+    return kAlgs[a].desc;
+}
+
+const char *nlopt_algorithm_to_string(nlopt_algorithm a)
+{
+    if ((int) a < 0 || a >= NLOPT_NUM_ALGORITHMS) return nullptr;
+    return kAlgs[a].id;
+}
+
+nlopt_algorithm nlopt_algorithm_from_string(const char *name)
+{
+    if (name)
+        for (int i = 0; i < NLOPT_NUM_ALGORITHMS; ++i)
+            if (!std::strcmp(name, kAlgs[i].id)) return (nlopt_algorithm) i;
+    return (nlopt_algorithm) -1;
+}
+
+const char *nlopt_result_to_string(nlopt_result r)
+{
+    for (const ResName &e : kResults)
+        if (e.code == (int) r) return e.name;
+    return nullptr;
+}
+
+nlopt_result nlopt_result_from_string(const char *name)
+{
+    if (name)
+        for (const ResName &e : kResults)
+            if (!std::strcmp(name, e.name)) return (nlopt_result) e.code;
+    return (nlopt_result) -1;
+}
+
+void nlopt_version(int *major, int *minor, int *bugfix)
+{
+    *major = 2; *minor = 11; *bugfix = 0;   /* ABI level of the reference this library mirrors */
+}
+
+void nlopt_srand(unsigned long) {}
+void nlopt_srand_time(void) {}
+
+/* ------------------------------------------------------------------ lifetime (options.c:36-265) */
+
+nlopt_opt nlopt_create(nlopt_algorithm algorithm, unsigned n)
+{
+    if ((int) algorithm < 0 || algorithm >= NLOPT_NUM_ALGORITHMS) return nullptr;
+    nlopt_opt o = new (std::nothrow) nlopt_opt_s;
+    if (!o) return nullptr;
+    o->algorithm = algorithm;
+    o->n = n;
+    o->stopval = -kInf;
+    try {
+        o->lb.assign(n, -kInf);
+        o->ub.assign(n, +kInf);
+    } catch (const std::bad_alloc &) {
+        delete o;
+        return nullptr;
+    }
+    return o;
+}
+
+void nlopt_destroy(nlopt_opt opt)
+{
+    if (!opt) return;
+    if (opt->munge_on_destroy) {
+        opt->munge_on_destroy(opt->f_data);
+        munge_all(opt, opt->fc);
+        munge_all(opt, opt->h);
+    }
+    for (NamedParam *p : opt->params) delete p;
+    nlopt_destroy(opt->local_opt);
+    delete opt;
+}
+
+nlopt_opt nlopt_copy(const nlopt_opt opt)
+{
+    if (!opt) return nullptr;
+    nlopt_opt c = new (std::nothrow) nlopt_opt_s(*opt);
+    if (!c) return nullptr;
+    c->params.clear();
+    c->local_opt = nullptr;
+    c->force_stop_child = nullptr;
+    c->errmsg.clear();
+    c->has_errmsg = false;
+    for (NamedParam *p : opt->params) c->params.push_back(new NamedParam(*p));
+    if (nlopt_munge mg = c->munge_on_copy) {
+        bool bad = false;
+        if (c->f_data && !(c->f_data = mg(c->f_data))) bad = true;
+        for (auto &r : c->fc) if (!bad && r.f_data && !(r.f_data = mg(r.f_data))) bad = true;
+        for (auto &r : c->h) if (!bad && r.f_data && !(r.f_data = mg(r.f_data))) bad = true;
+        if (bad) {                       /* options.c:261-263: better to leak than to crash */
+            c->munge_on_destroy = nullptr;
+            nlopt_destroy(c);
+            return nullptr;
+        }
+    }
+    if (opt->local_opt && !(c->local_opt = nlopt_copy(opt->local_opt))) {
+        c->munge_on_destroy = nullptr;
+        nlopt_destroy(c);
+        return nullptr;
+    }
+    return c;
+}
+
+/* ------------------------------------------------------------------ objective (options.c:322-364) */
+
+static nlopt_result set_objective(nlopt_opt opt, nlopt_func f, nlopt_b200_dfunc df, nlopt_precond pre, void *data,
+                                  int maximize)
+{
+    if (!opt) return NLOPT_INVALID_ARGS;
+    clear_err(opt);
+    if (opt->munge_on_destroy) opt->munge_on_destroy(opt->f_data);
+    opt->f = f;
+    opt->df = df;
+    opt->f_data = data;
+    opt->pre = pre;
+    opt->maximize = maximize;
+    if (nb200::nl_isinf(opt->stopval)) {
+        if (!maximize && opt->stopval > 0) opt->stopval = -kInf;
+        if (maximize && opt->stopval < 0) opt->stopval = +kInf;
+    }
+    return NLOPT_SUCCESS;
+}
+
+nlopt_result nlopt_set_precond_min_objective(nlopt_opt opt, nlopt_func f, nlopt_precond pre, void *d)
+{ return set_objective(opt, f, nullptr, pre, d, 0); }
+nlopt_result nlopt_set_min_objective(nlopt_opt opt, nlopt_func f, void *d)
+{ return set_objective(opt, f, nullptr, nullptr, d, 0); }
+nlopt_result nlopt_set_precond_max_objective(nlopt_opt opt, nlopt_func f, nlopt_precond pre, void *d)
+{ return set_objective(opt, f, nullptr, pre, d, 1); }
+nlopt_result nlopt_set_max_objective(nlopt_opt opt, nlopt_func f, void *d)
+{ return set_objective(opt, f, nullptr, nullptr, d, 1); }
+nlopt_result nlopt_b200_set_min_objective_device(nlopt_opt opt, nlopt_b200_dfunc f, void *d)
+{ return set_objective(opt, nullptr, f, nullptr, d, 0); }
+
+nlopt_algorithm nlopt_get_algorithm(const nlopt_opt opt) { return opt->algorithm; }
+unsigned nlopt_get_dimension(const nlopt_opt opt) { return opt->n; }
+const char *nlopt_get_errmsg(nlopt_opt opt) { return opt->has_errmsg ? opt->errmsg.c_str() : nullptr; }
+
+/* ------------------------------------------------------------------ named parameters (options.c:268-318) */
+
+nlopt_result nlopt_set_param(nlopt_opt opt, const char *name, double val)
+{
+    if (!opt) return NLOPT_INVALID_ARGS;
+    if (!name) { set_err(opt, "invalid NULL parameter name"); return NLOPT_INVALID_ARGS; }
+    if (strnlen(name, 1024) + 1 > 1024) { set_err(opt, "parameter name must be < 1024 bytes"); return NLOPT_INVALID_ARGS; }
+    for (NamedParam *p : opt->params)
+        if (p->name == name) { p->val = val; return NLOPT_SUCCESS; }
+    NamedParam *p = new (std::nothrow) NamedParam{name, val};
+    if (!p) return NLOPT_OUT_OF_MEMORY;
+    opt->params.push_back(p);
+    return NLOPT_SUCCESS;
+}
+
+double nlopt_get_param(const nlopt_opt opt, const char *name, double defaultval)
+{
+    if (!opt || !name || strnlen(name, 1024) == 1024) return defaultval;
+    for (NamedParam *p : opt->params)
+        if (p->name == name) return p->val;
+    return defaultval;
+}
+
+int nlopt_has_param(const nlopt_opt opt, const char *name)
+{
+    if (!opt || !name || strnlen(name, 1024) == 1024) return 0;
+    for (NamedParam *p : opt->params)
+        if (p->name == name) return 1;
+    return 0;
+}
+
+unsigned nlopt_num_params(const nlopt_opt opt) { return opt ? (unsigned) opt->params.size() : 0; }
+
+const char *nlopt_nth_param(const nlopt_opt opt, unsigned n)
+{
+    return opt && n < opt->params.size() ? opt->params[n]->name.c_str() : nullptr;
+}
+
+/* ------------------------------------------------------------------ bounds (options.c:368-474) */
+
+nlopt_result nlopt_set_lower_bounds(nlopt_opt opt, const double *lb)
+{
+    clear_err(opt);
+    if (!opt || (opt->n > 0 && !lb)) return NLOPT_INVALID_ARGS;
+    for (unsigned i = 0; i < opt->n; ++i) opt->lb[i] = lb[i];
+    for (unsigned i = 0; i < opt->n; ++i) snap_lower(opt, i);
+    return NLOPT_SUCCESS;
+}
+
+nlopt_result nlopt_set_lower_bounds1(nlopt_opt opt, double lb)
+{
+    clear_err(opt);
+    if (!opt) return NLOPT_INVALID_ARGS;
+    for (unsigned i = 0; i < opt->n; ++i) { opt->lb[i] = lb; snap_lower(opt, i); }
+    return NLOPT_SUCCESS;
+}
+
+nlopt_result nlopt_set_lower_bound(nlopt_opt opt, int i, double lb)
+{
+    clear_err(opt);
+    if (!opt) return NLOPT_INVALID_ARGS;
+    if (i < 0 || i >= (int) opt->n) { set_err(opt, "invalid bound index"); return NLOPT_INVALID_ARGS; }
+    opt->lb[i] = lb;
+    snap_lower(opt, i);
+    return NLOPT_SUCCESS;
+}
+
+nlopt_result nlopt_get_lower_bounds(const nlopt_opt opt, double *lb)
+{
+    clear_err(opt);
+    if (!opt || (opt->n > 0 && !lb)) return NLOPT_INVALID_ARGS;
+    for (unsigned i = 0; i < opt->n; ++i) lb[i] = opt->lb[i];
+    return NLOPT_SUCCESS;
+}
+
+nlopt_result nlopt_set_upper_bounds(nlopt_opt opt, const double *ub)
+{
+    clear_err(opt);
+    if (!opt || (opt->n > 0 && !ub)) return NLOPT_INVALID_ARGS;
+    for (unsigned i = 0; i < opt->n; ++i) opt->ub[i] = ub[i];
+    for (unsigned i = 0; i < opt->n; ++i) snap_upper(opt, i);
+    return NLOPT_SUCCESS;
+}
+
+nlopt_result nlopt_set_upper_bounds1(nlopt_opt opt, double ub)
+{
+    clear_err(opt);
+    if (!opt) return NLOPT_INVALID_ARGS;
+    for (unsigned i = 0; i < opt->n; ++i) { opt->ub[i] = ub; snap_upper(opt, i); }
+    return NLOPT_SUCCESS;
+}
+
+nlopt_result nlopt_set_upper_bound(nlopt_opt opt, int i, double ub)
+{
+    clear_err(opt);
+    if (!opt) return NLOPT_INVALID_ARGS;
+    if (i < 0 || i >= (int) opt->n) { set_err(opt, "invalid bound index"); return NLOPT_INVALID_ARGS; }
+    opt->ub[i] = ub;
+    snap_upper(opt, i);
+    return NLOPT_SUCCESS;
+}
+
+nlopt_result nlopt_get_upper_bounds(const nlopt_opt opt, double *ub)
+{
+    clear_err(opt);
+    if (!opt || (opt->n > 0 && !ub)) return NLOPT_INVALID_ARGS;
+    for (unsigned i = 0; i < opt->n; ++i) ub[i] = opt->ub[i];
+    return NLOPT_SUCCESS;
+}
+
+/* ------------------------------------------------------------------ constraints (options.c:476-659) */
+
+nlopt_result nlopt_remove_inequality_constraints(nlopt_opt opt)
+{
+    clear_err(opt);
+    if (!opt) return NLOPT_INVALID_ARGS;
+    munge_all(opt, opt->fc);
+    opt->fc.clear();
+    return NLOPT_SUCCESS;
+}
+
+nlopt_result nlopt_remove_equality_constraints(nlopt_opt opt)
+{
+    clear_err(opt);
+    if (!opt) return NLOPT_INVALID_ARGS;
+    munge_all(opt, opt->h);
+    opt->h.clear();
+    return NLOPT_SUCCESS;
+}
+
+static nlopt_result add_any(nlopt_opt opt, bool equality, bool vector_form, unsigned m, nlopt_func fc,
+                            nlopt_mfunc mfc, nlopt_b200_dfunc dfc, nlopt_precond pre, void *data, const double *tol)
+{
+    nlopt_result ret;
+    clear_err(opt);
+    if (vector_form && !m) {                 /* options.c:560-564: an empty vector constraint is fine */
+        if (opt && opt->munge_on_destroy) opt->munge_on_destroy(data);
+        return NLOPT_SUCCESS;
+    }
+    if (!opt) ret = NLOPT_INVALID_ARGS;
+    else if (!(equality ? equality_ok(opt->algorithm) : inequality_ok(opt->algorithm))) {
+        set_err(opt, "invalid algorithm for constraints");
+        ret = NLOPT_INVALID_ARGS;
+    } else
+        ret = add_constraint(opt, equality ? opt->h : opt->fc, m, fc, mfc, dfc, pre, data, tol);
+    if (ret < 0 && opt && opt->munge_on_destroy) opt->munge_on_destroy(data);
+    return ret;
+}
+
+nlopt_result nlopt_add_inequality_mconstraint(nlopt_opt opt, unsigned m, nlopt_mfunc fc, void *d, const double *tol)
+{ return add_any(opt, false, true, m, nullptr, fc, nullptr, nullptr, d, tol); }
+nlopt_result nlopt_add_precond_inequality_constraint(nlopt_opt opt, nlopt_func fc, nlopt_precond pre, void *d, double tol)
+{ return add_any(opt, false, false, 1, fc, nullptr, nullptr, pre, d, &tol); }
+nlopt_result nlopt_add_inequality_constraint(nlopt_opt opt, nlopt_func fc, void *d, double tol)
+{ return add_any(opt, false, false, 1, fc, nullptr, nullptr, nullptr, d, &tol); }
+nlopt_result nlopt_b200_add_inequality_constraint_device(nlopt_opt opt, nlopt_b200_dfunc fc, void *d, double tol)
+{ return add_any(opt, false, false, 1, nullptr, nullptr, fc, nullptr, d, &tol); }
+nlopt_result nlopt_add_equality_mconstraint(nlopt_opt opt, unsigned m, nlopt_mfunc h, void *d, const double *tol)
+{ return add_any(opt, true, true, m, nullptr, h, nullptr, nullptr, d, tol); }
+nlopt_result nlopt_add_precond_equality_constraint(nlopt_opt opt, nlopt_func h, nlopt_precond pre, void *d, double tol)
+{ return add_any(opt, true, false, 1, h, nullptr, nullptr, pre, d, &tol); }
+nlopt_result nlopt_add_equality_constraint(nlopt_opt opt, nlopt_func h, void *d, double tol)
+{ return add_any(opt, true, false, 1, h, nullptr, nullptr, nullptr, d, &tol); }
+
+/* ------------------------------------------------------------------ stopping criteria (options.c:661-816) */
+
+#define NB_SCALAR_ACCESSORS(name, T, field)                                                   \
+    T nlopt_get_##name(const nlopt_opt opt) { return opt->field; }                            \
+    nlopt_result nlopt_set_##name(nlopt_opt opt, T v)                                         \
+    {                                                                                         \
+        if (!opt) return NLOPT_INVALID_ARGS;                                                  \
+        clear_err(opt);                                                                       \
+        opt->field = v;                                                                       \
+        return NLOPT_SUCCESS;                                                                 \
+    }
+NB_SCALAR_ACCESSORS(stopval, double, stopval)
+NB_SCALAR_ACCESSORS(ftol_rel, double, ftol_rel)
+NB_SCALAR_ACCESSORS(ftol_abs, double, ftol_abs)
+NB_SCALAR_ACCESSORS(xtol_rel, double, xtol_rel)
+NB_SCALAR_ACCESSORS(maxeval, int, maxeval)
+NB_SCALAR_ACCESSORS(maxtime, double, maxtime)
+NB_SCALAR_ACCESSORS(population, unsigned, stochastic_population)
+NB_SCALAR_ACCESSORS(vector_storage, unsigned, vector_storage)
+#undef NB_SCALAR_ACCESSORS
+
+int nlopt_get_numevals(const nlopt_opt opt) { return opt->numevals; }
+
+nlopt_result nlopt_set_xtol_abs(nlopt_opt opt, const double *v)
+{
+    if (!opt) return NLOPT_INVALID_ARGS;
+    clear_err(opt);
+    if (!v) { opt->xtol_abs.clear(); opt->has_xtol_abs = false; return NLOPT_SUCCESS; }
+    opt->xtol_abs.assign(v, v + opt->n);
+    opt->has_xtol_abs = opt->n > 0;
+    return NLOPT_SUCCESS;
+}
+
+nlopt_result nlopt_set_xtol_abs1(nlopt_opt opt, double v)
+{
+    if (!opt) return NLOPT_INVALID_ARGS;
+    clear_err(opt);
+    opt->xtol_abs.assign(opt->n, v);
+    opt->has_xtol_abs = opt->n > 0;
+    return NLOPT_SUCCESS;
+}
+
+nlopt_result nlopt_get_xtol_abs(const nlopt_opt opt, double *v)
+{
+    clear_err(opt);
+    if (!opt || (opt->n > 0 && !v)) return NLOPT_INVALID_ARGS;
+    for (unsigned i = 0; i < opt->n; ++i) v[i] = opt->has_xtol_abs ? opt->xtol_abs[i] : 0.0;
+    return NLOPT_SUCCESS;
+}
+
+nlopt_result nlopt_set_x_weights(nlopt_opt opt, const double *w)
+{
+    if (!opt) return NLOPT_INVALID_ARGS;
+    clear_err(opt);
+    if (!w) { opt->x_weights.clear(); opt->has_x_weights = false; return NLOPT_SUCCESS; }
+    for (unsigned i = 0; i < opt->n; ++i)
+        if (w[i] < 0) { set_err(opt, "invalid negative weight"); return NLOPT_INVALID_ARGS; }
+    opt->x_weights.assign(w, w + opt->n);
+    opt->has_x_weights = opt->n > 0;
+    return NLOPT_SUCCESS;
+}
+
+nlopt_result nlopt_set_x_weights1(nlopt_opt opt, double w)
+{
+    if (!opt) return NLOPT_INVALID_ARGS;
+    if (w < 0) { set_err(opt, "invalid negative weight"); return NLOPT_INVALID_ARGS; }
+    clear_err(opt);
+    opt->x_weights.assign(opt->n, w);
+    opt->has_x_weights = opt->n > 0;
+    return NLOPT_SUCCESS;
+}
+
+nlopt_result nlopt_get_x_weights(const nlopt_opt opt, double *w)
+{
+    if (!opt) return NLOPT_INVALID_ARGS;
+    if (opt->n > 0 && !w) { set_err(opt, "invalid NULL weights"); return NLOPT_INVALID_ARGS; }
+    clear_err(opt);
+    for (unsigned i = 0; i < opt->n; ++i) w[i] = opt->has_x_weights ? opt->x_weights[i] : 1.0;
+    return NLOPT_SUCCESS;
+}
+
+nlopt_result nlopt_set_force_stop(nlopt_opt opt, int val)
+{
+    if (!opt) return NLOPT_INVALID_ARGS;
+    clear_err(opt);
+    opt->force_stop = val;
+    if (opt->force_stop_child) return nlopt_set_force_stop(opt->force_stop_child, val);
+    return NLOPT_SUCCESS;
+}
+int nlopt_get_force_stop(const nlopt_opt opt) { return opt->force_stop; }
+nlopt_result nlopt_force_stop(nlopt_opt opt) { return nlopt_set_force_stop(opt, 1); }
+
+/* ------------------------------------------------------------------ algorithm-specific (options.c:818-957) */
+
+nlopt_result nlopt_set_local_optimizer(nlopt_opt opt, const nlopt_opt local_opt)
+{
+    if (!opt) return NLOPT_INVALID_ARGS;
+    clear_err(opt);
+    if (local_opt && local_opt->n != opt->n) {
+        set_err(opt, "dimension mismatch in local optimizer");
+        return NLOPT_INVALID_ARGS;
+    }
+    nlopt_destroy(opt->local_opt);
+    opt->local_opt = nlopt_copy(local_opt);
+    if (local_opt) {
+        if (!opt->local_opt) return NLOPT_OUT_OF_MEMORY;
+        nlopt_opt lo = opt->local_opt;
+        nlopt_set_lower_bounds(lo, opt->lb.data());
+        nlopt_set_upper_bounds(lo, opt->ub.data());
+        nlopt_remove_inequality_constraints(lo);
+        nlopt_remove_equality_constraints(lo);
+        nlopt_set_min_objective(lo, nullptr, nullptr);
+        nlopt_set_munge(lo, nullptr, nullptr);
+        lo->force_stop = 0;
+    }
+    return NLOPT_SUCCESS;
+}
+
+nlopt_result nlopt_set_initial_step1(nlopt_opt opt, double dx)
+{
+    if (!opt) return NLOPT_INVALID_ARGS;
+    clear_err(opt);
+    if (dx == 0) { set_err(opt, "zero step size"); return NLOPT_INVALID_ARGS; }
+    opt->dx.assign(opt->n, dx);
+    opt->has_dx = opt->n > 0;
+    return NLOPT_SUCCESS;
+}
+
+nlopt_result nlopt_set_initial_step(nlopt_opt opt, const double *dx)
+{
+    if (!opt) return NLOPT_INVALID_ARGS;
+    clear_err(opt);
+    if (!dx) { opt->dx.clear(); opt->has_dx = false; return NLOPT_SUCCESS; }
+    for (unsigned i = 0; i < opt->n; ++i)
+        if (dx[i] == 0) { set_err(opt, "zero step size"); return NLOPT_INVALID_ARGS; }
+    opt->dx.assign(dx, dx + opt->n);
+    opt->has_dx = opt->n > 0;
+    return NLOPT_SUCCESS;
+}
+
+/* heuristic step of options.c:903-957 (used by derivative-free algorithms; kept for ABI completeness) */
+nlopt_result nlopt_set_default_initial_step(nlopt_opt opt, const double *x)
+{
+    clear_err(opt);
+    if (!opt || !x) return NLOPT_INVALID_ARGS;
+    opt->dx.assign(opt->n, 1.0);
+    opt->has_dx = opt->n > 0;
+    for (unsigned i = 0; i < opt->n; ++i) {
+        const double lo = opt->lb[i], hi = opt->ub[i];
+        const bool flo = !nb200::nl_isinf(lo), fhi = !nb200::nl_isinf(hi);
+        double step = kInf;
+        if (fhi && flo && (hi - lo) * 0.25 < step && hi > lo) step = (hi - lo) * 0.25;
+        if (fhi && hi - x[i] < step && hi > x[i]) step = (hi - x[i]) * 0.75;
+        if (flo && x[i] - lo < step && x[i] > lo) step = (x[i] - lo) * 0.75;
+        if (nb200::nl_isinf(step)) {
+            if (fhi && std::fabs(hi - x[i]) < std::fabs(step)) step = (hi - x[i]) * 1.1;
+            if (flo && std::fabs(x[i] - lo) < std::fabs(step)) step = (x[i] - lo) * 1.1;
+        }
+        if (nb200::nl_isinf(step) || is_tiny(step)) step = x[i];
+        if (nb200::nl_isinf(step) || step == 0.0) step = 1;
+        opt->dx[i] = step;
+    }
+    return NLOPT_SUCCESS;
+}
+
+nlopt_result nlopt_get_initial_step(const nlopt_opt opt, const double *x, double *dx)
+{
+    if (!opt) return NLOPT_INVALID_ARGS;
+    clear_err(opt);
+    if (!opt->n) return NLOPT_SUCCESS;
+    if (!opt->has_dx) {
+        nlopt_result r = nlopt_set_default_initial_step(opt, x);
+        if (r != NLOPT_SUCCESS) return r;
+        for (unsigned i = 0; i < opt->n; ++i) dx[i] = opt->dx[i];
+        opt->dx.clear();                 /* x-dependent: not remembered (options.c:896-898) */
+        opt->has_dx = false;
+    } else
+        for (unsigned i = 0; i < opt->n; ++i) dx[i] = opt->dx[i];
+    return NLOPT_SUCCESS;
+}
+
+void nlopt_set_munge(nlopt_opt opt, nlopt_munge on_destroy, nlopt_munge on_copy)
+{
+    if (opt) { opt->munge_on_destroy = on_destroy; opt->munge_on_copy = on_copy; }
+}
+
+void nlopt_munge_data(nlopt_opt opt, nlopt_munge2 munge, void *data)
+{
+    if (!opt || !munge) return;
+    opt->f_data = munge(opt->f_data, data);
+    for (auto &c : opt->fc) c.f_data = munge(c.f_data, data);
+    for (auto &c : opt->h) c.f_data = munge(c.f_data, data);
+}
+
+nlopt_result nlopt_b200_get_stats(const nlopt_opt opt, nlopt_b200_stats *out)
+{
+    if (!opt || !out) return NLOPT_INVALID_ARGS;
+    *out = opt->stats;
+    return NLOPT_SUCCESS;
+}
+
+/* ------------------------------------------------------------------ run (optimize.c:991-1083) */
+
+static nlopt_result optimize_common(nlopt_opt opt, double *x_host, double *x_dev, double *opt_f)
+{
+    clear_err(opt);
+    if (!opt || !opt_f || (!opt->f && !opt->df)) {
+        set_err(opt, "NULL args to nlopt_optimize");
+        return NLOPT_INVALID_ARGS;
+    }
+    nlopt_set_force_stop(opt, 0);
+    opt->force_stop_child = nullptr;
+
+    /* maximisation: minimise the sign-flipped objective, then restore (optimize.c:1014-1024, :1070-1077) */
+    nlopt_func f0 = opt->f;
+    void *d0 = opt->f_data;
+    FlipData flip{f0, d0};
+    const int maximize = opt->maximize;
+    if (maximize) {
+        if (!opt->f) { set_err(opt, "maximisation needs a host objective"); return NLOPT_INVALID_ARGS; }
+        opt->f = flipped;
+        opt->f_data = &flip;
+        opt->stopval = -opt->stopval;
+        opt->maximize = 0;
+    }
+    nlopt_result ret = run_ccsa(opt, x_host, x_dev, opt_f);
+    if (maximize) {
+        opt->maximize = maximize;
+        opt->stopval = -opt->stopval;
+        opt->f = f0;
+        opt->f_data = d0;
+        *opt_f = -*opt_f;
+    }
+    return ret;
+}
+
+nlopt_result nlopt_optimize(nlopt_opt opt, double *x, double *opt_f)
+{
+    return optimize_common(opt, x, nullptr, opt_f);
+}
+
+nlopt_result nlopt_b200_optimize_device(nlopt_opt opt, double *x_dev, double *opt_f)
+{
+    return optimize_common(opt, nullptr, x_dev, opt_f);
+}
+
+}  // extern "C"
+
+namespace {
+
+// nlopt_optimize_ (optimize.c:514-566) + the MMA/CCSAQ case (optimize.c:795-834)
+nlopt_result run_ccsa(nlopt_opt opt, double *x_host, double *x_dev, double *minf)
+{
+    const unsigned n = opt->n;
+    if ((!x_host && !x_dev) || opt->maximize) {
+        set_err(opt, "NULL args to nlopt_optimize_");
+        return NLOPT_INVALID_ARGS;
+    }
+    if (n == 0) {                                    /* optimize.c:536-539 */
+        if (!opt->f) { set_err(opt, "n == 0 needs a host objective"); return NLOPT_INVALID_ARGS; }
+        *minf = opt->f(0, x_host, nullptr, opt->f_data);
+        return NLOPT_SUCCESS;
+    }
+    *minf = HUGE_VAL;
+
+    if (opt->algorithm != NLOPT_LD_MMA && opt->algorithm != NLOPT_LD_CCSAQ) {
+        set_err(opt, "algorithm %s is not part of this library (only LD_MMA and LD_CCSAQ are built)",
+                nlopt_algorithm_to_string(opt->algorithm));
+        return NLOPT_INVALID_ARGS;
+    }
+    if (x_host)                                      /* optimize.c:547-551 */
+        for (unsigned i = 0; i < n; ++i)
+            if (opt->lb[i] > opt->ub[i] || x_host[i] < opt->lb[i] || x_host[i] > opt->ub[i]) {
+                set_err(opt, "bounds %d fail %g <= %g <= %g", (int) i, opt->lb[i], x_host[i], opt->ub[i]);
+                return NLOPT_INVALID_ARGS;
+            }
+
+    /* parameters, optimize.c:798-815 */
+    nb200::CcsaParams prm;
+    prm.inner_maxeval = (int) nlopt_get_param(opt, "inner_maxeval", 0);
+    prm.verbosity = (int) nlopt_get_param(opt, "verbosity", 0);
+    prm.rho_init = nlopt_get_param(opt, "rho_init", 1.0);
+    prm.inner_gradients = (int) nlopt_get_param(opt, "inner_gradients", 1);
+    prm.always_improve = (int) nlopt_get_param(opt, "always_improve", 1);
+    prm.sigma_min = nlopt_get_param(opt, "sigma_min", 0.0);
+    if (!(prm.rho_init > 0) && !nb200::nl_isinf(prm.rho_init)) {
+        set_err(opt, "rho_init must be positive and finite");
+        return NLOPT_INVALID_ARGS;
+    }
+    if (prm.inner_gradients != 0 && prm.inner_gradients != 1) {
+        set_err(opt, "inner_gradients must be 0 or 1");
+        return NLOPT_INVALID_ARGS;
+    }
+    if (prm.always_improve != 0 && prm.always_improve != 1) {
+        set_err(opt, "always_improve must be 0 or 1");
+        return NLOPT_INVALID_ARGS;
+    }
+    if (prm.sigma_min < 0.0) { set_err(opt, "sigma_min must be non-negative"); return NLOPT_INVALID_ARGS; }
+    if (prm.verbosity < 0) prm.verbosity = 0;
+
+    /* the dual optimiser's configuration, optimize.c:817-826.  Precedence: named parameter >
+       local optimiser (if one was set) > library default; only MMA exists here for the dual. */
+    const nlopt_opt lo = opt->local_opt;
+    const int dual_alg = (int) nlopt_get_param(opt, "dual_algorithm", lo ? (double) lo->algorithm : (double) NLOPT_LD_MMA);
+    if (dual_alg != NLOPT_LD_MMA) {
+        set_err(opt, "dual_algorithm %d is not part of this library (the dual problem is solved by LD_MMA)", dual_alg);
+        return NLOPT_INVALID_ARGS;
+    }
+    prm.dual_ftol_rel = nlopt_get_param(opt, "dual_ftol_rel", lo ? lo->ftol_rel : 1e-14);
+    prm.dual_ftol_abs = nlopt_get_param(opt, "dual_ftol_abs", lo ? lo->ftol_abs : 0.0);
+    prm.dual_xtol_rel = nlopt_get_param(opt, "dual_xtol_rel", 0.0);
+    prm.dual_xtol_abs = nlopt_get_param(opt, "dual_xtol_abs", 0.0);
+    prm.dual_maxeval = (int) nlopt_get_param(opt, "dual_maxeval", lo ? (double) lo->maxeval : 100000.0);
+
+    bool any_pre = opt->pre != nullptr;
+    for (const auto &c : opt->fc) any_pre = any_pre || c.pre != nullptr;
+    if (any_pre && opt->algorithm == NLOPT_LD_CCSAQ) {
+        set_err(opt, "preconditioned CCSAQ (ccsa_quadratic.c:299-324) is not built into this library");
+        return NLOPT_INVALID_ARGS;
+    }
+
+    /* hand the O(n) state to the device */
+    nb200::BackendConfig cfg;
+    cfg.variant = opt->algorithm == NLOPT_LD_MMA ? nb200::kMMA : nb200::kCCSAQ;
+    cfg.n = n;
+    cfg.objective.f = opt->f;
+    cfg.objective.df = opt->df;
+    cfg.objective.data = opt->f_data;
+    std::vector<double> tol;
+    for (const auto &c : opt->fc) {
+        nb200::FuncSpec s;
+        s.m = c.m; s.f = c.f; s.mf = c.mf; s.df = c.df; s.data = c.f_data;
+        cfg.constraints.push_back(s);
+        tol.insert(tol.end(), c.tol.begin(), c.tol.end());
+    }
+    cfg.lb = opt->lb.data();
+    cfg.ub = opt->ub.data();
+    cfg.x0_host = x_host;
+    cfg.x_dev = x_dev;
+    cfg.sigma_init = opt->has_dx ? opt->dx.data() : nullptr;
+    cfg.x_weights = opt->has_x_weights ? opt->x_weights.data() : nullptr;
+    cfg.xtol_abs = opt->has_xtol_abs ? opt->xtol_abs.data() : nullptr;
+    opt->stats = nlopt_b200_stats{};
+    cfg.stats = &opt->stats;
+
+    const double t0 = nb200::wall_seconds();
+    std::string err;
+    nb200::Backend *be = nb200::make_backend(cfg, &err);
+    if (!be) {
+        set_err(opt, "%s", err.c_str());
+        return NLOPT_FAILURE;
+    }
+
+    nb200::StopCriteria st;                          /* optimize.c:553-566 */
+    st.minf_max = opt->stopval;
+    st.ftol_rel = opt->ftol_rel;
+    st.ftol_abs = opt->ftol_abs;
+    st.xtol_rel = opt->xtol_rel;
+    st.has_xtol_abs = opt->has_xtol_abs;
+    opt->numevals = 0;
+    st.nevals_p = &opt->numevals;
+    st.maxeval = opt->maxeval;
+    st.maxtime = opt->maxtime;
+    st.force_stop = &opt->force_stop;
+
+    nb200::DriverStats ds;
+    int ret = nb200::ccsa_minimize(cfg.variant, *be, tol, minf, st, prm, &ds, &err);
+    if (ret == NLOPT_FAILURE && !err.empty()) set_err(opt, "%s", err.c_str());
+    if (ret == NLOPT_INVALID_ARGS && !err.empty()) set_err(opt, "%s", err.c_str());
+    if (!be->fetch_x(x_host ? x_host : x_dev) && ret > 0) {
+        set_err(opt, "copying the result back failed: %s", be->error().c_str());
+        ret = NLOPT_FAILURE;
+    }
+    opt->stats.dual_evals = ds.dual_evals;
+    opt->stats.dual_solves = ds.dual_solves;
+    opt->stats.outer_iters = ds.outer_iters;
+    opt->stats.seconds_callbacks = be->seconds_in_callbacks();
+    delete be;
+    opt->stats.seconds_total = nb200::wall_seconds() - t0;
+    return (nlopt_result) ret;
+}
+
+}  // namespace

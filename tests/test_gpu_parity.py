@@ -1,0 +1,281 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the oracle on identical inputs.
+
+Tolerances (stated once, used everywhere):
+  * x*(y), sigma, xprev...: BIT-EXACT (the kernels evaluate the reference's expressions with
+    un-fused IEEE operations; reference is built with -ffp-contract=off).
+  * the m+3 sums: the GPU adds the same per-variable terms in a fixed tree instead of
+    sequentially, so |delta| <= 4 * n * 2^-53 * sum|terms| is guaranteed; we assert the much
+    tighter 1e-12 * (|value| + sum-scale) that the tree actually achieves.
+  * end-to-end optimisation: same return code class, |f* - f*_ref| <= 1e-6 max(1,|f*_ref|),
+    x* within 1e-5 (rounding-level differences are amplified by the flat dual optimum).
+"""
+import numpy as np
+import pytest
+
+import nlopt_b200 as nl
+import oracle_bindings as ob
+import problems as P
+import synth
+from gpu_dual import DualHandle
+
+pytestmark = pytest.mark.gpu
+
+REL = 1e-12
+
+
+def close(a, b, scale):
+    return abs(a - b) <= REL * (abs(b) + scale)
+
+
+def check_dual(variant, inst, y=None, pmax=None):
+    h = DualHandle(variant, inst)
+    if pmax:
+        h.configure("pmax", pmax)
+    got = h.eval(inst["y"] if y is None else y, want_xcur=True)
+    want = ob.port_dual(variant, inst, y)
+    assert np.array_equal(got["xcur"], want["xcur"], equal_nan=True), "x*(y) not bit-identical"
+    n = inst["n"]
+    scale = float(n)    # terms are O(1) each in the synthetic instance
+    assert close(got["ret"], want["ret"], scale), (got["ret"], want["ret"])
+    assert close(got["g0"], want["g0"], scale)
+    assert close(got["w"], want["w"], scale)
+    for i in range(inst["m"]):
+        assert close(got["gc"][i], want["gc"][i], scale), i
+        assert got["grad"][i] == -got["gc"][i]
+    # a second evaluation without materialising x* gives the same bits (deterministic reduction)
+    again = h.eval(inst["y"] if y is None else y, want_xcur=False)
+    assert again["ret"] == got["ret"] and np.array_equal(again["gc"], got["gc"])
+    return got
+
+
+@pytest.mark.parametrize("variant", [ob.MMA, ob.CCSAQ])
+@pytest.mark.parametrize("n,m", [(1, 0), (2, 2), (3, 1), (5, 2), (255, 3), (4097, 4), (100001, 1), (100000, 4),
+                                 (250000, 8), (60000, 16), (30000, 5), (20000, 12), (9999, 20), (5000, 32)])
+def test_dual_kernel_vs_oracle(built, variant, n, m):
+    check_dual(variant, synth.kernel_instance(n, m))
+
+
+@pytest.mark.parametrize("variant", [ob.MMA, ob.CCSAQ])
+def test_dual_kernel_known_answer(built, variant):
+    from test_oracle_port import KA, KA_EXPECT
+    got = DualHandle(variant, KA).eval(KA["y"], want_xcur=True)
+    e = KA_EXPECT[variant]
+    assert list(got["xcur"]) == e["xcur"]
+    assert abs(got["ret"] - e["ret"]) < 1e-15 and abs(got["g0"] - e["g0"]) < 1e-15 and abs(got["w"] - e["w"]) < 1e-16
+    assert np.allclose(got["gc"], e["gc"], rtol=0, atol=1e-15)
+
+
+@pytest.mark.parametrize("variant", [ob.MMA, ob.CCSAQ])
+def test_dual_kernel_multipliers_zero_and_huge(built, variant):
+    inst = synth.kernel_instance(50000, 4)
+    for y in ([0, 0, 0, 0], [1e40, 0, 0, 0], [1e40, 1e40, 1e40, 1e40], [1e-300, 3.0, 0.0, 7e5]):
+        h = DualHandle(variant, inst)
+        got = h.eval(np.array(y, dtype=float), want_xcur=True)
+        want = ob.port_dual(variant, inst, np.array(y, dtype=float))
+        assert np.array_equal(got["xcur"], want["xcur"], equal_nan=True)
+        for k in ("ret", "g0", "w"):
+            assert np.isclose(got[k], want[k], rtol=1e-11, atol=1e-300, equal_nan=True), (y, k, got[k], want[k])
+
+
+def test_dual_kernel_nan_constraint_mma(built):
+    inst = synth.kernel_instance(40000, 3)
+    inst["c0"] = np.array([-0.1, np.nan, 0.2])
+    got = check_dual(ob.MMA, inst)
+    assert got["gc"][1] == 0.0
+
+
+def test_dual_kernel_special_lanes(built):
+    """fixed variables (sigma = 0, lb == ub) and unbounded variables in the same launch; n odd."""
+    n = 30001
+    inst = synth.kernel_instance(n, 2)
+    inst["sigma"][::7] = 0.0
+    inst["lb"][::7] = inst["x"][::7]; inst["ub"][::7] = inst["x"][::7]
+    inst["lb"][3::11] = -np.inf
+    inst["ub"][5::13] = np.inf
+    for v in (ob.MMA, ob.CCSAQ):
+        check_dual(v, inst)
+
+
+@pytest.mark.parametrize("variant", [ob.MMA, ob.CCSAQ])
+def test_segment_geometry_does_not_change_x_and_barely_changes_sums(built, variant):
+    inst = synth.kernel_instance(300000, 4)
+    base = check_dual(variant, inst)
+    for pmax in (1, 7, 74, 148, 592):
+        got = check_dual(variant, inst, pmax=pmax)
+        assert abs(got["ret"] - base["ret"]) <= 1e-12 * (abs(base["ret"]) + inst["n"])
+
+
+def test_synthetic_fill_matches_host_generator(built):
+    n, m = 70001, 3
+    inst = synth.kernel_instance(n, m)
+    h = DualHandle(ob.CCSAQ, n=n, m=m, synthetic_seed=synth.SEED0)
+    for k in ("x", "lb", "ub", "sigma", "grad_f"):
+        assert np.array_equal(h.download(k), inst[k]), k
+    assert np.array_equal(h.download("grad_c"), inst["grad_c"])
+
+
+@pytest.mark.parametrize("variant", [ob.MMA, ob.CCSAQ])
+def test_sigma_init_and_end_outer_vs_oracle(built, variant):
+    L = ob.port()
+    n = 123457
+    rng = np.random.default_rng(7)
+    inst = synth.kernel_instance(n, 1)
+    lb, ub = inst["lb"].copy(), inst["ub"].copy()
+    h = DualHandle(variant, inst)
+    # sigma init: with and without an initial step, with a floor
+    for si, smin in ((None, 0.0), (np.where(rng.random(n) < 0.5, 0.3, -1.0), 0.25)):
+        want = np.zeros(n)
+        L.port_sigma_init(n, ob._p(lb), ob._p(ub), ob._p(si) if si is not None else None, smin, ob._p(want))
+        h.sigma_init(si, smin)
+        assert np.array_equal(h.download("sigma"), want)
+    # end of an outer iteration: norms, sigma update, rotation
+    xcur = inst["x"] + 0.01 * rng.standard_normal(n)
+    xprev = inst["x"] + 0.01 * rng.standard_normal(n)
+    xprevprev = inst["x"] + 0.01 * rng.standard_normal(n)
+    xprev[::5] = xcur[::5]                          # zero oscillation product on some lanes
+    w = rng.random(n)
+    xtol_abs = np.full(n, 0.05)
+    sig0 = h.download("sigma")
+    for k, weights, tol in ((1, None, None), (2, None, None), (3, w, xtol_abs)):
+        h.upload(dict(inst, sigma=sig0))
+        h.set_prev(xcur, xprev, xprevprev)
+        dn, xn, below = h.end_outer(k, 0.0, weights, tol)
+        ww = weights if weights is not None else np.ones(n)
+        assert np.isclose(dn, np.sum(ww * np.abs(xcur - xprev)), rtol=1e-12)
+        assert np.isclose(xn, np.sum(ww * np.abs(xcur)), rtol=1e-12)
+        if tol is not None:
+            assert below == bool(np.all(np.abs(xcur - xprev) < tol))
+        want = sig0.copy()
+        if k > 1:
+            L.port_sigma_update(variant, n, ob._p(xcur), ob._p(xprev), ob._p(xprevprev), ob._p(lb), ob._p(ub), 0.0,
+                                ob._p(want))
+        assert np.array_equal(h.download("sigma"), want)
+        assert np.array_equal(h.download("xprev"), xcur) and np.array_equal(h.download("xprevprev"), xprev)
+
+
+# ---- end to end through nlopt_optimize --------------------------------------------------------------------
+
+def _run(alg, n, f, cons, tols, lb, ub, x0, lib=None, **kw):
+    o = nl.opt(alg, n, library=lib)
+    o.set_lower_bounds(lb); o.set_upper_bounds(ub)
+    o.set_min_objective(f)
+    for c, t in zip(cons, tols):
+        o.add_inequality_constraint(c, t)
+    for k, v in kw.items():
+        if k in ("xtol_rel", "ftol_rel", "maxeval", "stopval"):
+            getattr(o, "set_" + k)(v)
+        elif k == "initial_step":
+            o.set_initial_step(v)
+        else:
+            o.set_param(k, v)
+    x = o.optimize(x0)
+    return dict(ret=o.last_optimize_result(), x=x, minf=o.last_optimum_value(), numevals=o.get_numevals(), opt=o)
+
+
+@pytest.mark.parametrize("variant,setting,ret,evals,x0,x1,f", __import__("test_oracle_port").GOLD)
+def test_tutorial_goldens_on_gpu(built, variant, setting, ret, evals, x0, x1, f):
+    """BASELINE config 1 (t_tutorial / doc tutorial settings) against the reference's measured optimum."""
+    from test_oracle_port import SETTINGS
+    s = dict(SETTINGS[setting])
+    lb, ub = s.pop("lb"), s.pop("ub")
+    if "sigma_init" in s:
+        s["initial_step"] = s.pop("sigma_init")
+    alg = nl.LD_MMA if variant == ob.MMA else nl.LD_CCSAQ
+    r = _run(alg, 2, P.tut_f, [P.tut_c(2, 0), P.tut_c(-1, 1)], [1e-8, 1e-8], lb, ub, P.TUT_X0, **s)
+    assert r["ret"] == ret
+    assert abs(r["numevals"] - evals) <= 2
+    assert abs(r["minf"] - f) <= 1e-6 and abs(r["x"][0] - x0) <= 1e-5 and abs(r["x"][1] - x1) <= 1e-5
+    st = r["opt"].get_stats()
+    assert st["dual_evals"] > 0 and st["kernel_launches"] >= st["dual_evals"]
+
+
+@pytest.mark.parametrize("variant", [ob.MMA, ob.CCSAQ])
+def test_rosenbrock_vs_oracle_short_run(built, variant):
+    """config-3 instance at n=20000, m=4, fixed maxeval: compare with the port after 30 evaluations."""
+    n, m = 20000, 4
+    cons = [P.lin_constraint(k, n) for k in range(m)]
+    lb, ub = np.full(n, -2.0), np.full(n, 2.0)
+    alg = nl.LD_MMA if variant == ob.MMA else nl.LD_CCSAQ
+    a = _run(alg, n, P.rosen_f, cons, [1e-8] * m, lb, ub, P.rosen_x0(n), maxeval=30)
+    b = ob.port_minimize(variant, P.rosen_f, cons, [1e-8] * m, lb, ub, P.rosen_x0(n), maxeval=30)
+    assert a["ret"] == b["ret"] == 5 and a["numevals"] == b["numevals"]
+    assert abs(a["minf"] - b["minf"]) <= 1e-5 * abs(b["minf"])
+    assert np.max(np.abs(a["x"] - b["x"])) <= 1e-4
+
+
+@pytest.mark.parametrize("variant", [ob.MMA, ob.CCSAQ])
+@pytest.mark.parametrize("x0v", [-0.5, 0.5])
+def test_quadratic_converged_vs_oracle(built, variant, x0v):
+    """config-2 shape: separable quadratic + mean constraint, converged to xtol_rel=1e-6."""
+    if variant == ob.CCSAQ and x0v > 0:
+        pytest.skip("reference CCSAQ stalls from an infeasible start on this instance (SURVEY.md 8(d))")
+    n = 100000
+    f, c = P.quad_problem(n)
+    lb, ub = np.full(n, -1.0), np.full(n, 1.0)
+    alg = nl.LD_MMA if variant == ob.MMA else nl.LD_CCSAQ
+    a = _run(alg, n, f, [c], [0.0], lb, ub, np.full(n, x0v), xtol_rel=1e-6, maxeval=300)
+    b = ob.port_minimize(variant, f, [c], [0.0], lb, ub, np.full(n, x0v), xtol_rel=1e-6, maxeval=300)
+    assert a["ret"] == b["ret"] == 4
+    assert abs(a["minf"] - b["minf"]) <= 1e-6 * max(1.0, abs(b["minf"]))
+    assert np.max(np.abs(a["x"] - b["x"])) <= 1e-5
+
+
+def test_simp_mma_converged_vs_oracle(built):
+    """config-4 shape (host callback): synthetic SIMP compliance + volume constraint."""
+    n = 100000
+    f, c = P.simp_problem(n)
+    lb, ub = np.zeros(n), np.ones(n)
+    a = _run(nl.LD_MMA, n, f, [c], [0.0], lb, ub, np.full(n, 0.4), xtol_rel=1e-6, maxeval=300)
+    b = ob.port_minimize(ob.MMA, f, [c], [0.0], lb, ub, np.full(n, 0.4), xtol_rel=1e-6, maxeval=300)
+    assert a["ret"] == b["ret"]
+    assert abs(a["minf"] - b["minf"]) <= 1e-6 * abs(b["minf"])
+    assert np.max(np.abs(a["x"] - b["x"])) <= 1e-5
+
+
+def test_unconstrained_m0_and_options(built):
+    """m = 0 (reference test/cpp_functor.cxx shape): bound-free quadratic form, sigma0 = 1."""
+    A = np.array([[4.0, 1, 0], [1, 3, 1], [0, 1, 2]])
+    b = np.array([1.0, -2.0, 0.5])
+
+    def f(x, g):
+        if g.size:
+            g[:] = A @ x - b
+        return 0.5 * x @ A @ x - b @ x
+    r = _run(nl.LD_MMA, 3, f, [], [], np.full(3, -np.inf), np.full(3, np.inf), np.zeros(3), xtol_rel=1e-8, maxeval=500)
+    ref = ob.port_minimize(ob.MMA, f, [], [], np.full(3, -np.inf), np.full(3, np.inf), np.zeros(3), xtol_rel=1e-8,
+                           maxeval=500)
+    assert r["ret"] == ref["ret"] and abs(r["minf"] - ref["minf"]) < 1e-10
+    assert np.allclose(r["x"], np.linalg.solve(A, b), atol=1e-5)
+
+
+def test_device_path_has_no_cpu_fallback_symbols(built):
+    """the product library must not contain or import anything from the oracle"""
+    import subprocess, nlopt_b200._capi as capi
+    syms = subprocess.run(["nm", "-D", capi.DEFAULT_LIB], capture_output=True, text=True).stdout
+    assert "port_dual" not in syms and "port_ccsa" not in syms
+
+
+@pytest.mark.parametrize("variant", [ob.MMA, ob.CCSAQ])
+def test_full_size_properties(built, variant):
+    """BASELINE full size n = 1e7, m = 4 on device-generated arrays: properties that need no oracle run.
+      (1) val == g0 + sum_i y_i g_i  (A.5 #5: only the rounding differs);
+      (2) the returned gradient is the derivative of the dual function (finite differences in y);
+      (3) bitwise reproducibility across launches and across segment geometries for x*(y)."""
+    n, m = 10_000_000, 4
+    h = DualHandle(variant, n=n, m=m, synthetic_seed=synth.SEED0)
+    i = np.arange(m, dtype=float)
+    h.set_scalars(1.0, 1.0, -0.1 * (i + 1), 1.0 + 0.1 * i)
+    y = 0.5 * (i + 1)
+    a = h.eval(y, want_xcur=False)
+    assert abs(-a["ret"] - (a["g0"] + float(np.dot(y, a["gc"])))) <= 1e-11 * n
+    b = h.eval(y, want_xcur=False)
+    assert a["ret"] == b["ret"] and np.array_equal(a["gc"], b["gc"])
+    for k in range(m):
+        e = np.zeros(m); e[k] = 1e-6
+        fd = (h.eval(y + e)["ret"] - h.eval(y - e)["ret"]) / 2e-6
+        assert abs(fd - a["grad"][k]) <= 1e-5 * (abs(a["grad"][k]) + 1.0) * 10
+    # oracle on a prefix-sized instance with the same generator: x* agrees bit for bit on the sample
+    small = synth.kernel_instance(200000, m)
+    hs = DualHandle(variant, small)
+    want = ob.port_dual(variant, small)
+    assert np.array_equal(hs.eval(small["y"], want_xcur=True)["xcur"], want["xcur"])
