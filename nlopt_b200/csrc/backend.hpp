@@ -73,6 +73,9 @@ public:
     // copy the accepted point to host memory (or a device pointer in device mode)
     virtual bool fetch_x(double *x_out) = 0;
 
+    // implementation knobs (e.g. "time_kernels"); unknown keys return false
+    virtual bool configure(const char *key, long long value) { (void) key; (void) value; return false; }
+
     virtual const std::string &error() const = 0;
     virtual double seconds_in_callbacks() const = 0;
 };

@@ -47,7 +47,7 @@ public:
     bool sigma_init_from(const double *sigma_init_host, double sigma_min);
     bool set_norm_arrays(const double *x_weights_host, const double *xtol_abs_host);
     bool time_dual(const double *y, const DualScalars &sc, bool materialize, int iters, double *ms_avg);
-    bool configure(const char *key, long long value);
+    bool configure(const char *key, long long value) override;
     long long query(const char *key) const;
     const Geometry &geometry() const { return geo_; }
     bool is_mma() const { return variant_ == kMMA; }

@@ -827,6 +827,12 @@ nlopt_result run_ccsa(nlopt_opt opt, double *x_host, double *x_dev, double *minf
         return NLOPT_FAILURE;
     }
 
+    /* library-specific knobs ride on the named-parameter mechanism (no ABI change) */
+    if (nlopt_get_param(opt, "b200_time_kernels", 0.0) != 0.0) be->configure("time_kernels", 1);
+    if (nlopt_has_param(opt, "b200_pmax")) be->configure("pmax", (long long) nlopt_get_param(opt, "b200_pmax", 0.0));
+    if (nlopt_has_param(opt, "b200_target_pairs"))
+        be->configure("target_pairs", (long long) nlopt_get_param(opt, "b200_target_pairs", 0.0));
+
     nb200::StopCriteria st;                          /* optimize.c:553-566 */
     st.minf_max = opt->stopval;
     st.ftol_rel = opt->ftol_rel;
