@@ -252,6 +252,10 @@ int nlopt_b200_comm_world(void);
 void nlopt_b200_shard_range(unsigned long long n, int rank, int world,
                             unsigned long long *j0, unsigned long long *count);
 
+/* nlopt_optimize parks its large device / pinned blocks in a process-wide cache for the next call;
+ * this frees them. */
+void nlopt_b200_release_cached_memory(void);
+
 /* library / device probe: returns number of visible CUDA devices, <0 on CUDA error */
 int nlopt_b200_device_count(void);
 const char *nlopt_b200_build_info(void);

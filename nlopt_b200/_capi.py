@@ -144,6 +144,7 @@ _EXT = {
     "nlopt_b200_comm_world": (C.c_int, []),
     "nlopt_b200_shard_range": (None, [C.c_ulonglong, C.c_int, C.c_int,
                                       C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong)]),
+    "nlopt_b200_release_cached_memory": (None, []),
     "nlopt_b200_device_count": (C.c_int, []),
     "nlopt_b200_build_info": (C.c_char_p, []),
 }

@@ -85,9 +85,10 @@ struct DualArgs {
 };
 
 // ---- block-level reduction with a fixed tree --------------------------------------------------
-template <int NV>
-__device__ __forceinline__ void block_reduce_to(double (&acc)[NV], double *smem /* [kWarps*NV] */, double *out)
+template <int NV, int BLOCK = kBlock>
+__device__ __forceinline__ void block_reduce_to(double (&acc)[NV], double *smem /* [(BLOCK/32)*NV] */, double *out)
 {
+    constexpr int kWarpsB = BLOCK / 32;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
     for (int k = 0; k < NV; ++k) {
@@ -100,7 +101,7 @@ __device__ __forceinline__ void block_reduce_to(double (&acc)[NV], double *smem 
     if (threadIdx.x < NV) {
         double s = smem[threadIdx.x];
 #pragma unroll
-        for (int w = 1; w < kWarps; ++w) s = addx(s, smem[w * NV + threadIdx.x]);
+        for (int w = 1; w < kWarpsB; ++w) s = addx(s, smem[w * NV + threadIdx.x]);
         out[threadIdx.x] = s;
     }
     __syncthreads();
@@ -208,13 +209,14 @@ __device__ __forceinline__ double ccsaq_point(const DualArgs &a, double x, doubl
 }
 
 // ---- the dual evaluation kernel -----------------------------------------------------------------
-// grid = number of local segments; CTA b owns global segment seg0 + b.
-template <int VARIANT, int MAXM, bool STORE>
-__global__ void __launch_bounds__(kBlock) dual_eval_kernel(const __grid_constant__ DualArgs a)
+// grid = number of local segments; CTA b owns global segment seg0 + b.  BLOCK threads; each thread
+// takes UNROLL double2 pairs per trip (all loads of a trip are issued before any arithmetic).
+template <int VARIANT, int MAXM, bool STORE, int BLOCK, int UNROLL, int MINB>
+__global__ void __launch_bounds__(BLOCK, MINB) dual_eval_kernel(const __grid_constant__ DualArgs a)
 {
     constexpr int MR = MAXM > 0 ? MAXM : 1;
     constexpr int NV = 3 + MR;
-    __shared__ double s_red[kWarps * NV];
+    __shared__ double s_red[(BLOCK / 32) * NV];
     __shared__ int s_flag;
 
     const unsigned seg = a.seg0 + blockIdx.x;
@@ -233,34 +235,49 @@ __global__ void __launch_bounds__(kBlock) dual_eval_kernel(const __grid_constant
     const double2 *g2 = reinterpret_cast<const double2 *>(a.g);
     const bool in_regs = a.m <= MAXM;
 
-    for (unsigned long long p = p_lo + threadIdx.x; p < p_hi; p += kBlock) {
-        const double2 vx = ld_stream(x2 + p), vlb = ld_stream(lb2 + p), vub = ld_stream(ub2 + p),
-                      vs = ld_stream(s2v + p), vg = ld_stream(g2 + p);
-        double Ga[MR], Gb[MR];
+    for (unsigned long long p0 = p_lo + threadIdx.x; p0 < p_hi; p0 += (unsigned long long) BLOCK * UNROLL) {
+        double2 vx[UNROLL], vlb[UNROLL], vub[UNROLL], vs[UNROLL], vg[UNROLL];
+        double Ga[UNROLL][MR], Gb[UNROLL][MR];
 #pragma unroll
-        for (int i = 0; i < MR; ++i) {
-            Ga[i] = 0.0;
-            Gb[i] = 0.0;
-            if (MAXM > 0 && in_regs && i < a.m) {
-                const double2 t = ld_stream(reinterpret_cast<const double2 *>(a.G + (unsigned long long) i * a.ld) + p);
-                Ga[i] = t.x;
-                Gb[i] = t.y;
+        for (int u = 0; u < UNROLL; ++u) {
+            const unsigned long long p = p0 + (unsigned long long) u * BLOCK;
+            const bool live = UNROLL == 1 || p < p_hi;
+            vs[u] = make_double2(0.0, 0.0);          // sigma = 0 lanes are skipped by both formulas
+            vx[u] = vlb[u] = vub[u] = vg[u] = make_double2(0.0, 0.0);
+            if (live) {
+                vx[u] = ld_stream(x2 + p); vlb[u] = ld_stream(lb2 + p); vub[u] = ld_stream(ub2 + p);
+                vs[u] = ld_stream(s2v + p); vg[u] = ld_stream(g2 + p);
+            }
+#pragma unroll
+            for (int i = 0; i < MR; ++i) {
+                Ga[u][i] = 0.0;
+                Gb[u][i] = 0.0;
+                if (MAXM > 0 && in_regs && i < a.m && live) {
+                    const double2 t = ld_stream(reinterpret_cast<const double2 *>(a.G + (unsigned long long) i * a.ld) + p);
+                    Ga[u][i] = t.x;
+                    Gb[u][i] = t.y;
+                }
             }
         }
-        const double *col = a.G + 2 * p;
-        double2 xc;
-        if (VARIANT == 0) {
-            xc.x = mma_point<MAXM>(a, vx.x, vlb.x, vub.x, vs.x, vg.x, Ga, col, a.ld, acc);
-            xc.y = mma_point<MAXM>(a, vx.y, vlb.y, vub.y, vs.y, vg.y, Gb, col + 1, a.ld, acc);
-        } else {
-            xc.x = ccsaq_point<MAXM>(a, vx.x, vlb.x, vub.x, vs.x, vg.x, Ga, col, a.ld, acc);
-            xc.y = ccsaq_point<MAXM>(a, vx.y, vlb.y, vub.y, vs.y, vg.y, Gb, col + 1, a.ld, acc);
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            const unsigned long long p = p0 + (unsigned long long) u * BLOCK;
+            const bool live = UNROLL == 1 || p < p_hi;
+            const double *col = a.G + 2 * p;
+            double2 xc;
+            if (VARIANT == 0) {
+                xc.x = mma_point<MAXM>(a, vx[u].x, vlb[u].x, vub[u].x, vs[u].x, vg[u].x, Ga[u], col, a.ld, acc);
+                xc.y = mma_point<MAXM>(a, vx[u].y, vlb[u].y, vub[u].y, vs[u].y, vg[u].y, Gb[u], col + 1, a.ld, acc);
+            } else {
+                xc.x = ccsaq_point<MAXM>(a, vx[u].x, vlb[u].x, vub[u].x, vs[u].x, vg[u].x, Ga[u], col, a.ld, acc);
+                xc.y = ccsaq_point<MAXM>(a, vx[u].y, vlb[u].y, vub[u].y, vs[u].y, vg[u].y, Gb[u], col + 1, a.ld, acc);
+            }
+            if (STORE && live) st_stream(reinterpret_cast<double2 *>(a.xcur) + p, xc);
         }
-        if (STORE) st_stream(reinterpret_cast<double2 *>(a.xcur) + p, xc);
     }
 
     // segment partial
-    block_reduce_to<NV>(acc, s_red, a.partials + (unsigned long long) blockIdx.x * a.nvp);
+    block_reduce_to<NV, BLOCK>(acc, s_red, a.partials + (unsigned long long) blockIdx.x * a.nvp);
 
     // virtual-shard fold by the last CTA of the shard
     const unsigned vs_local = blockIdx.x / a.segs_per_vshard;
@@ -269,11 +286,11 @@ __global__ void __launch_bounds__(kBlock) dual_eval_kernel(const __grid_constant
     for (int k = 0; k < NV; ++k) acc[k] = 0.0;
     {
         const double *base = a.partials + (unsigned long long) vs_local * a.segs_per_vshard * a.nvp;
-        for (unsigned sgi = threadIdx.x; sgi < a.segs_per_vshard; sgi += kBlock)
+        for (unsigned sgi = threadIdx.x; sgi < a.segs_per_vshard; sgi += BLOCK)
 #pragma unroll
             for (int k = 0; k < NV; ++k) acc[k] = addx(acc[k], __ldcg(base + (unsigned long long) sgi * a.nvp + k));
     }
-    block_reduce_to<NV>(acc, s_red, a.vsums + (unsigned long long) vs_local * a.nvp);
+    block_reduce_to<NV, BLOCK>(acc, s_red, a.vsums + (unsigned long long) vs_local * a.nvp);
 
     // rank fold by the last virtual shard
     if (!is_last_arrival(a.tickets + a.local_vshards, a.local_vshards, &s_flag)) return;

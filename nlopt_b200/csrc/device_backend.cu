@@ -7,6 +7,8 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <map>
+#include <mutex>
 
 #include "ccsa_kernels.cuh"
 #include "comm.hpp"
@@ -25,24 +27,107 @@ namespace {
 
 int grid_for(unsigned long long n) { unsigned long long g = (n + kBlock - 1) / kBlock; return (int) (g < 1 ? 1 : (g > 148ull * 16 ? 148ull * 16 : g)); }
 
-template <int VARIANT, int MAXM>
-void launch_variant(bool store, int grid, cudaStream_t s, const DualArgs &a)
+// launch-geometry variants of the dual kernel: {threads per CTA, pairs per thread per trip, min CTAs/SM}
+struct KernelCfg { int block, unroll, minb; };
+constexpr KernelCfg kCfgs[] = {{256, 1, 1}, {256, 2, 1}, {512, 1, 1}, {256, 1, 3}, {256, 1, 4}, {128, 2, 1}, {512, 2, 1},
+                               {128, 4, 1}, {256, 2, 2}, {1024, 1, 1}};
+constexpr int kNumCfgs = (int) (sizeof(kCfgs) / sizeof(kCfgs[0]));
+
+typedef void (*DualKernel)(const DualArgs);
+
+template <int VARIANT, int MAXM, int CFG>
+DualKernel kernel_for(bool store)
 {
-    if (store) dual_eval_kernel<VARIANT, MAXM, true><<<grid, kBlock, 0, s>>>(a);
-    else dual_eval_kernel<VARIANT, MAXM, false><<<grid, kBlock, 0, s>>>(a);
+    constexpr KernelCfg c = kCfgs[CFG];
+    return store ? (DualKernel) dual_eval_kernel<VARIANT, MAXM, true, c.block, c.unroll, c.minb>
+                 : (DualKernel) dual_eval_kernel<VARIANT, MAXM, false, c.block, c.unroll, c.minb>;
 }
 
+template <int VARIANT, int MAXM>
+DualKernel kernel_by_cfg(int cfg, bool store)
+{
+    switch (cfg) {
+    case 1: return kernel_for<VARIANT, MAXM, 1>(store);
+    case 2: return kernel_for<VARIANT, MAXM, 2>(store);
+    case 3: return kernel_for<VARIANT, MAXM, 3>(store);
+    case 4: return kernel_for<VARIANT, MAXM, 4>(store);
+    case 5: return kernel_for<VARIANT, MAXM, 5>(store);
+    case 6: return kernel_for<VARIANT, MAXM, 6>(store);
+    case 7: return kernel_for<VARIANT, MAXM, 7>(store);
+    case 8: return kernel_for<VARIANT, MAXM, 8>(store);
+    case 9: return kernel_for<VARIANT, MAXM, 9>(store);
+    default: return kernel_for<VARIANT, MAXM, 0>(store);
+    }
+}
+
+// every m has the default geometry; the tuning variants are built for the headline m <= 4 and m <= 16 kernels
 template <int VARIANT>
-void launch_by_m(int maxm, bool store, int grid, cudaStream_t s, const DualArgs &a)
+DualKernel pick_kernel(int maxm, int cfg, bool store)
 {
     switch (maxm) {
-    case 0: launch_variant<VARIANT, 0>(store, grid, s, a); break;
-    case 1: launch_variant<VARIANT, 1>(store, grid, s, a); break;
-    case 2: launch_variant<VARIANT, 2>(store, grid, s, a); break;
-    case 4: launch_variant<VARIANT, 4>(store, grid, s, a); break;
-    case 8: launch_variant<VARIANT, 8>(store, grid, s, a); break;
-    default: launch_variant<VARIANT, 16>(store, grid, s, a); break;
+    case 0: return kernel_for<VARIANT, 0, 0>(store);
+    case 1: return kernel_by_cfg<VARIANT, 1>(cfg == 1 || cfg == 2 ? cfg : 0, store);
+    case 2: return kernel_for<VARIANT, 2, 0>(store);
+    case 4: return kernel_by_cfg<VARIANT, 4>(cfg, store);
+    case 8: return kernel_for<VARIANT, 8, 0>(store);
+    default: return kernel_by_cfg<VARIANT, 16>(cfg == 2 || cfg == 5 || cfg == 9 ? cfg : 0, store);
     }
+}
+
+// Process-wide cache of the big allocations (device state pool, pinned staging).  nlopt_optimize
+// creates and destroys its state per call like the reference (mma.c:173, :450); cudaMalloc /
+// cudaHostAlloc of gigabytes costs tens to hundreds of milliseconds, so freed blocks are parked here
+// and handed back to the next call of a similar size.  nlopt_b200_release_cached_memory() empties it.
+class BlockCache {
+public:
+    void *take(bool pinned, size_t bytes)
+    {
+        std::lock_guard<std::mutex> g(mu_);
+        auto &pool = pinned ? pinned_ : device_;
+        auto it = pool.lower_bound(bytes);
+        if (it != pool.end() && it->first <= bytes + bytes / 4 + 4096) {
+            void *p = it->second;
+            pool.erase(it);
+            return p;
+        }
+        return nullptr;
+    }
+    void give(bool pinned, size_t bytes, void *p)
+    {
+        std::lock_guard<std::mutex> g(mu_);
+        auto &pool = pinned ? pinned_ : device_;
+        pool.emplace(bytes, p);
+        while (pool.size() > 4) {                 // keep the cache small: drop the smallest block
+            auto it = pool.begin();
+            if (pinned) cudaFreeHost(it->second); else cudaFree(it->second);
+            pool.erase(it);
+        }
+    }
+    void clear()
+    {
+        std::lock_guard<std::mutex> g(mu_);
+        for (auto &e : device_) cudaFree(e.second);
+        for (auto &e : pinned_) cudaFreeHost(e.second);
+        device_.clear();
+        pinned_.clear();
+    }
+    static BlockCache &get() { static BlockCache c; return c; }
+
+private:
+    std::mutex mu_;
+    std::multimap<size_t, void *> device_, pinned_;
+};
+
+cudaError_t cached_malloc(double **p, size_t bytes)
+{
+    if (void *q = BlockCache::get().take(false, bytes)) { *p = (double *) q; return cudaSuccess; }
+    return cudaMalloc(p, bytes);
+}
+
+cudaError_t cached_host_alloc(double **p, size_t bytes)
+{
+    if (void *q = BlockCache::get().take(true, bytes)) { *p = (double *) q; return cudaSuccess; }
+    return cudaHostAlloc(p, bytes, cudaHostAllocDefault);
 }
 
 int pick_maxm(int m) { return m == 0 ? 0 : m <= 1 ? 1 : m <= 2 ? 2 : m <= 4 ? 4 : m <= 8 ? 8 : 16; }
@@ -72,7 +157,9 @@ bool DeviceBackend::fail(const std::string &what)
 
 void DeviceBackend::free_state()
 {
-    if (pool_) cudaFree(pool_);
+    if (stream_) cudaStreamSynchronize(stream_);
+    if (copy_stream_) cudaStreamSynchronize(copy_stream_);
+    if (pool_) BlockCache::get().give(false, pool_bytes_, pool_);
     if (w_dev_) cudaFree(w_dev_);
     if (xtol_abs_dev_) cudaFree(xtol_abs_dev_);
     if (partials_) cudaFree(partials_);
@@ -83,9 +170,9 @@ void DeviceBackend::free_state()
     if (scalar_dev_) cudaFree(scalar_dev_);
     if (out_host_) cudaFreeHost(out_host_);
     if (flag_host_) cudaFreeHost(flag_host_);
-    if (h_x_) cudaFreeHost(h_x_);
+    if (h_x_) BlockCache::get().give(true, (size_t) geo_.n * sizeof(double), h_x_);
     for (int b = 0; b < 2; ++b) {
-        if (h_grad_[b]) cudaFreeHost(h_grad_[b]);
+        if (h_grad_[b]) BlockCache::get().give(true, h_grad_cap_ * sizeof(double), h_grad_[b]);
         if (h_grad_done_[b]) cudaEventDestroy(h_grad_done_[b]);
     }
     if (copied_) cudaEventDestroy(copied_);
@@ -131,7 +218,8 @@ bool DeviceBackend::alloc_state()
 
     const size_t ld = geo_.ld;
     const size_t total = (9 + 2 * (size_t) m_) * ld;
-    NB_CUDA(cudaMalloc(&pool_, total * sizeof(double)));
+    pool_bytes_ = total * sizeof(double);
+    NB_CUDA(cached_malloc(&pool_, pool_bytes_));
     NB_CUDA(cudaMemsetAsync(pool_, 0, total * sizeof(double), stream_));
     double *p = pool_;
     x_ = p; p += ld;  xcur_ = p; p += ld;  xprev_ = p; p += ld;  xprevprev_ = p; p += ld;
@@ -195,10 +283,10 @@ bool DeviceBackend::setup(const BackendConfig &cfg)
     bool any_host_cb = cfg.objective.f != nullptr;
     for (const FuncSpec &c : cfg.constraints) any_host_cb = any_host_cb || c.f || c.mf;
     if (any_host_cb) {
-        NB_CUDA(cudaHostAlloc(&h_x_, (size_t) geo_.n * sizeof(double), cudaHostAllocDefault));
+        NB_CUDA(cached_host_alloc(&h_x_, (size_t) geo_.n * sizeof(double)));
         h_grad_cap_ = (size_t) max_cdim_ * geo_.n;
         for (int b = 0; b < 2; ++b) {
-            NB_CUDA(cudaHostAlloc(&h_grad_[b], h_grad_cap_ * sizeof(double), cudaHostAllocDefault));
+            NB_CUDA(cached_host_alloc(&h_grad_[b], h_grad_cap_ * sizeof(double)));
             NB_CUDA(cudaEventCreateWithFlags(&h_grad_done_[b], cudaEventDisableTiming));
         }
         if (Comm::instance().active())
@@ -430,8 +518,11 @@ bool DeviceBackend::launch_dual(const double *y, const DualScalars &sc, bool sto
         e1 = ev_pool_[ev_used_++];
         cudaEventRecord(e0, stream_);
     }
-    if (variant_ == kMMA) launch_by_m<0>(maxm, store, grid, stream_, a);
-    else launch_by_m<1>(maxm, store, grid, stream_, a);
+    const int cfg = kernel_cfg_ >= 0 && kernel_cfg_ < kNumCfgs ? kernel_cfg_ : 0;
+    DualKernel fn = variant_ == kMMA ? pick_kernel<0>(maxm, cfg, store) : pick_kernel<1>(maxm, cfg, store);
+    const int block = (maxm == 4 || (maxm == 1 && (cfg == 1 || cfg == 2)) || (maxm == 16 && (cfg == 2 || cfg == 5 || cfg == 9)))
+                          ? kCfgs[cfg].block : kCfgs[0].block;
+    fn<<<grid, block, 0, stream_>>>(a);
     if (time_kernels_) cudaEventRecord(e1, stream_);
     ++stats_->kernel_launches;
     NB_CUDA(cudaGetLastError());
@@ -565,7 +656,7 @@ bool DeviceBackend::fetch_x(double *x_out)
         stats_->d2h_bytes += geo_.n_local * sizeof(double);
         return true;
     }
-    if (!h_x_) NB_CUDA(cudaHostAlloc(&h_x_, (size_t) geo_.n * sizeof(double), cudaHostAllocDefault));
+    if (!h_x_) NB_CUDA(cached_host_alloc(&h_x_, (size_t) geo_.n * sizeof(double)));
     if (!xfull_dev_) NB_CUDA(cudaMalloc(&xfull_dev_, (size_t) comm.world * shard_cap_ * sizeof(double)));
     h_x_slot_ = -1;
     if (!host_x_for(kBase)) return false;
@@ -643,6 +734,7 @@ bool DeviceBackend::configure(const char *key, long long value)
 {
     const std::string k = key;
     if (k == "time_kernels") { time_kernels_ = value != 0; return true; }
+    if (k == "kernel_cfg") { kernel_cfg_ = (int) value; return true; }
     if (k == "pmax" || k == "target_pairs") {
         if (value < 1) return fail("bad value");
         if (k == "pmax") pmax_ = (unsigned) value; else target_pairs_ = (unsigned) value;
@@ -661,6 +753,10 @@ bool DeviceBackend::configure(const char *key, long long value)
 long long DeviceBackend::query(const char *key) const
 {
     const std::string k = key;
+    if (k == "kernel_ns") {            // accumulated device time of timed dual launches, nanoseconds
+        const_cast<DeviceBackend *>(this)->drain_events();
+        return (long long) (stats_->seconds_dual_kernel * 1e9);
+    }
     if (k == "segments") return geo_.S;
     if (k == "segments_local") return geo_.nseg_local;
     if (k == "P") return geo_.P;
@@ -671,6 +767,8 @@ long long DeviceBackend::query(const char *key) const
     if (k == "maxm") return pick_maxm((int) m_);
     return -1;
 }
+
+void release_cached_blocks() { BlockCache::get().clear(); }
 
 Backend *make_backend(const BackendConfig &cfg, std::string *err)
 {
@@ -835,6 +933,8 @@ int nlopt_b200_device_count(void)
     if (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) return 0;
     return e == cudaSuccess ? n : -1;
 }
+
+void nlopt_b200_release_cached_memory(void) { nb200::release_cached_blocks(); }
 
 const char *nlopt_b200_build_info(void)
 {

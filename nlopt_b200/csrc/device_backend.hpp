@@ -72,9 +72,11 @@ private:
     Geometry geo_;
     unsigned target_pairs_ = kDefaultTargetPairs, pmax_ = kDefaultPmax;
     int device_ = 0;
+    int kernel_cfg_ = 0;          // index into the launch-geometry table of device_backend.cu
 
     // device state
     double *pool_ = nullptr;
+    size_t pool_bytes_ = 0;
     double *x_ = nullptr, *xcur_ = nullptr, *xprev_ = nullptr, *xprevprev_ = nullptr, *lb_ = nullptr, *ub_ = nullptr,
            *sigma_ = nullptr, *g_ = nullptr, *gcur_ = nullptr, *G_ = nullptr, *Gcur_ = nullptr;
     double *w_dev_ = nullptr, *xtol_abs_dev_ = nullptr;
@@ -116,5 +118,7 @@ private:
     nlopt_b200_stats *stats_ = &local_stats_;
     unsigned max_cdim_ = 1;
 };
+
+void release_cached_blocks();
 
 }  // namespace nb200

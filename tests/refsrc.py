@@ -1,0 +1,47 @@
+"""Helpers that use the reference tree IN PLACE (this container only; never copied into the repo):
+generate nlopt.hpp the way cmake/generate-cpp.cmake does and compile the reference's own C++ tests
+against a library of ours.  Everything is skipped when /root/reference is absent (GPU box)."""
+import os
+import re
+import subprocess
+
+REF = os.environ.get("NLOPT_REFERENCE_DIR", "/root/reference")
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def available():
+    return os.path.isfile(os.path.join(REF, "src", "api", "nlopt-in.hpp"))
+
+
+def generate_hpp(outdir):
+    """nlopt-in.hpp + the enum block derived from nlopt.h (cmake/generate-cpp.cmake:39-52)."""
+    os.makedirs(outdir, exist_ok=True)
+    src = open(os.path.join(REF, "src", "api", "nlopt-in.hpp")).read().splitlines()
+    hdr = open(os.path.join(REF, "src", "api", "nlopt.h")).read().splitlines()
+    out = []
+    for line in src:
+        out.append(line)
+        if "GEN_ENUMS_HERE" in line:
+            out.append("  enum algorithm {")
+            for h in hdr:
+                if re.search(r"    NLOPT_[A-Z0-9_]+", h):
+                    out.append(h.replace("NLOPT_", ""))
+                    if "NLOPT_NUM_ALGORITHMS" in h:
+                        out += ["  };", "  enum result {"]
+                    elif "NLOPT_NUM_RESULTS" in h:
+                        out.append("  };")
+    path = os.path.join(outdir, "nlopt.hpp")
+    open(path, "w").write("\n".join(out) + "\n")
+    return path
+
+
+def compile_reference_test(name, libpath, outdir, use_our_header):
+    """g++ <ref>/test/<name> against `libpath`; returns the executable path."""
+    generate_hpp(outdir)
+    exe = os.path.join(outdir, os.path.splitext(name)[0] + ("_ourhdr" if use_our_header else "_refhdr"))
+    inc = os.path.join(ROOT, "include") if use_our_header else os.path.join(REF, "src", "api")
+    libdir, libfile = os.path.split(libpath)
+    cmd = ["g++", "-O1", "-std=c++11", f"-I{outdir}", f"-I{inc}", os.path.join(REF, "test", name), "-o", exe,
+           f"-L{libdir}", f"-l:{libfile}", f"-Wl,-rpath,{libdir}"]
+    subprocess.check_call(cmd)
+    return exe

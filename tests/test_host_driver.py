@@ -1,0 +1,244 @@
+"""Host-side logic of the product (nlopt_api.cpp, ccsa_driver.cpp, dual_mma.hpp) on a machine without
+a GPU: the same sources are linked against the oracle-backed CPU backend (tests/cpp/oracle_backend.cpp)
+and driven through the C ABI.  The O(n) kernels are NOT exercised here -- test_gpu_parity.py does that.
+
+Tolerance: the driver adds the O(m) constants after the n-term sums (like the GPU path), so results
+differ from the reference by rounding that the flat dual optimum amplifies:
+|f - f_ref| <= 1e-6, |x - x_ref| <= 1e-5, evaluation counts within a few."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import nlopt_b200 as nl
+import oracle_bindings as ob
+import problems as P
+import refsrc
+from test_oracle_port import GOLD, SETTINGS
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def run(lib, alg, n, f, cons, tols, lb, ub, x0, maximize=False, **kw):
+    o = nl.opt(alg, n, library=lib)
+    o.set_lower_bounds(lb); o.set_upper_bounds(ub)
+    (o.set_max_objective if maximize else o.set_min_objective)(f)
+    for c, t in zip(cons, tols):
+        o.add_inequality_constraint(c, t)
+    for k, v in kw.items():
+        if k in ("xtol_rel", "ftol_rel", "ftol_abs", "maxeval", "stopval", "maxtime"):
+            getattr(o, "set_" + k)(v)
+        elif k == "initial_step":
+            o.set_initial_step(v)
+        elif k == "xtol_abs":
+            o.set_xtol_abs(v)
+        else:
+            o.set_param(k, v)
+    x = o.optimize(x0)
+    return dict(ret=o.last_optimize_result(), x=x, minf=o.last_optimum_value(), numevals=o.get_numevals(), opt=o)
+
+
+@pytest.mark.parametrize("variant,setting,ret,evals,x0,x1,f", GOLD)
+def test_tutorial_goldens(hosttest_lib, variant, setting, ret, evals, x0, x1, f):
+    s = dict(SETTINGS[setting])
+    lb, ub = s.pop("lb"), s.pop("ub")
+    if "sigma_init" in s:
+        s["initial_step"] = s.pop("sigma_init")
+    alg = nl.LD_MMA if variant == ob.MMA else nl.LD_CCSAQ
+    r = run(hosttest_lib, alg, 2, P.tut_f, [P.tut_c(2, 0), P.tut_c(-1, 1)], [1e-8, 1e-8], lb, ub, P.TUT_X0, **s)
+    assert r["ret"] == ret
+    assert abs(r["numevals"] - evals) <= 2
+    assert abs(r["minf"] - f) <= 1e-6 and abs(r["x"][0] - x0) <= 1e-5 and abs(r["x"][1] - x1) <= 1e-5
+    st_ok = hosttest_lib.nlopt_get_numevals(r["opt"]._h) == r["numevals"]
+    assert st_ok
+
+
+@pytest.mark.parametrize("alg", [nl.LD_MMA, nl.LD_CCSAQ])
+def test_rosenbrock_vs_reference(hosttest_lib, reflib, alg):
+    n, m = 400, 4
+    cons = [P.lin_constraint(k, n) for k in range(m)]
+    lb, ub = np.full(n, -2.0), np.full(n, 2.0)
+    a = run(hosttest_lib, alg, n, P.rosen_f, cons, [1e-8] * m, lb, ub, P.rosen_x0(n), maxeval=25)
+    b = run(reflib, alg, n, P.rosen_f, cons, [1e-8] * m, lb, ub, P.rosen_x0(n), maxeval=25)
+    assert a["ret"] == b["ret"] == nl.MAXEVAL_REACHED and a["numevals"] == b["numevals"] == 25
+    assert abs(a["minf"] - b["minf"]) <= 1e-6 * abs(b["minf"])
+    assert np.max(np.abs(a["x"] - b["x"])) <= 1e-5
+
+
+@pytest.mark.parametrize("alg", [nl.LD_MMA, nl.LD_CCSAQ])
+@pytest.mark.parametrize("opts", [dict(), dict(inner_gradients=0), dict(always_improve=0), dict(sigma_min=0.05),
+                                  dict(inner_maxeval=2), dict(rho_init=10.0)])
+def test_algorithm_parameters_vs_reference(hosttest_lib, reflib, alg, opts):
+    """Every MMA/CCSAQ parameter of optimize.c:798-803 against the reference: (a) the first 20
+    evaluations must track the reference to rounding (same counts, f to 1e-8, x to 1e-7); (b) run to
+    convergence the result class and optimum must agree (rounding differences are amplified by the
+    flat dual optimum, so the paths -- and evaluation counts -- may legitimately differ late in the run)."""
+    n = 300
+    f, c = P.quad_problem(n)
+    lb, ub = np.full(n, -1.0), np.full(n, 1.0)
+    kw = dict(xtol_rel=1e-7, dual_ftol_rel=1e-8, **opts)
+    a = run(hosttest_lib, alg, n, f, [c], [0.0], lb, ub, np.full(n, -0.5), maxeval=20, **kw)
+    b = run(reflib, alg, n, f, [c], [0.0], lb, ub, np.full(n, -0.5), maxeval=20, **kw)
+    assert a["ret"] == b["ret"] and a["numevals"] == b["numevals"] == 20
+    assert abs(a["minf"] - b["minf"]) <= 1e-8 * max(1.0, abs(b["minf"]))
+    assert np.max(np.abs(a["x"] - b["x"])) <= 1e-7
+    a = run(hosttest_lib, alg, n, f, [c], [0.0], lb, ub, np.full(n, -0.5), maxeval=150, **kw)
+    b = run(reflib, alg, n, f, [c], [0.0], lb, ub, np.full(n, -0.5), maxeval=150, **kw)
+    assert a["ret"] == b["ret"]
+    assert abs(a["minf"] - b["minf"]) <= 1e-5 * max(1.0, abs(b["minf"]))
+
+
+@pytest.mark.parametrize("alg", [nl.LD_MMA, nl.LD_CCSAQ])
+def test_default_dual_tolerance_agrees_loosely(hosttest_lib, reflib, alg):
+    n = 300
+    f, c = P.quad_problem(n)
+    lb, ub = np.full(n, -1.0), np.full(n, 1.0)
+    a = run(hosttest_lib, alg, n, f, [c], [0.0], lb, ub, np.full(n, -0.5), xtol_rel=1e-7, maxeval=150)
+    b = run(reflib, alg, n, f, [c], [0.0], lb, ub, np.full(n, -0.5), xtol_rel=1e-7, maxeval=150)
+    assert a["ret"] == b["ret"] == nl.XTOL_REACHED
+    assert abs(a["minf"] - b["minf"]) <= 5e-6 * max(1.0, abs(b["minf"]))
+    assert np.max(np.abs(a["x"] - b["x"])) <= 2e-4
+
+
+def test_infeasible_start_uses_capped_multipliers(hosttest_lib, reflib):
+    """x0 violates the constraint: dual_ub = 1e40 until a feasible point is accepted (mma.c:245-246, :384-388)."""
+    n = 300
+    f, c = P.quad_problem(n)
+    lb, ub = np.full(n, -1.0), np.full(n, 1.0)
+    a = run(hosttest_lib, nl.LD_MMA, n, f, [c], [0.0], lb, ub, np.full(n, 0.5), xtol_rel=1e-7, maxeval=200)
+    b = run(reflib, nl.LD_MMA, n, f, [c], [0.0], lb, ub, np.full(n, 0.5), xtol_rel=1e-7, maxeval=200)
+    assert a["ret"] == b["ret"] == nl.XTOL_REACHED
+    assert abs(a["minf"] - b["minf"]) <= 1e-6 * abs(b["minf"])
+
+
+def test_unconstrained_m0(hosttest_lib, reflib):
+    """reference test/cpp_functor.cxx shape: LD_MMA, no constraints, no bounds (sigma0 = 1)."""
+    A = np.array([[4.0, 1, 0], [1, 3, 1], [0, 1, 2]]); b = np.array([1.0, -2.0, 0.5])
+
+    def f(x, g):
+        if g.size:
+            g[:] = A @ x - b
+        return float(0.5 * x @ A @ x - b @ x)
+    inf = np.full(3, np.inf)
+    a = run(hosttest_lib, nl.LD_MMA, 3, f, [], [], -inf, inf, np.zeros(3), xtol_rel=1e-4, maxeval=1000)
+    r = run(reflib, nl.LD_MMA, 3, f, [], [], -inf, inf, np.zeros(3), xtol_rel=1e-4, maxeval=1000)
+    assert a["ret"] == r["ret"] and a["numevals"] == r["numevals"]
+    assert abs(a["minf"] - r["minf"]) <= 1e-12 and np.max(np.abs(a["x"] - r["x"])) <= 1e-10
+
+
+def test_vector_constraint_equals_scalar_constraints(hosttest_lib):
+    lb, ub = [-np.inf, 0.0], [np.inf, np.inf]
+    a = run(hosttest_lib, nl.LD_MMA, 2, P.tut_f, [P.tut_c(2, 0), P.tut_c(-1, 1)], [1e-8, 1e-8], lb, ub, P.TUT_X0,
+            xtol_rel=1e-4)
+    o = nl.opt(nl.LD_MMA, 2, library=hosttest_lib)
+    o.set_lower_bounds(lb); o.set_min_objective(P.tut_f); o.set_xtol_rel(1e-4)
+    c0, c1 = P.tut_c(2, 0), P.tut_c(-1, 1)
+
+    def both(result, x, grad):
+        result[0] = c0(x, grad[0] if grad.size else grad)
+        result[1] = c1(x, grad[1] if grad.size else grad)
+    o.add_inequality_mconstraint(both, [1e-8, 1e-8])
+    x = o.optimize(P.TUT_X0)
+    assert o.last_optimize_result() == a["ret"] and o.get_numevals() == a["numevals"]
+    assert np.array_equal(x, a["x"]) and o.last_optimum_value() == a["minf"]
+
+
+def test_maximize_flips_sign(hosttest_lib):
+    lb, ub = [-np.inf, 0.0], [np.inf, np.inf]
+    a = run(hosttest_lib, nl.LD_CCSAQ, 2, P.tut_f, [P.tut_c(2, 0), P.tut_c(-1, 1)], [1e-8, 1e-8], lb, ub, P.TUT_X0,
+            xtol_rel=1e-4)
+
+    def negf(x, g):
+        v = P.tut_f(x, g)
+        if g.size:
+            g[:] = -g
+        return -v
+    b = run(hosttest_lib, nl.LD_CCSAQ, 2, negf, [P.tut_c(2, 0), P.tut_c(-1, 1)], [1e-8, 1e-8], lb, ub, P.TUT_X0,
+            maximize=True, xtol_rel=1e-4)
+    assert b["ret"] == a["ret"] and np.array_equal(a["x"], b["x"]) and b["minf"] == -a["minf"]
+
+
+def test_stopping_and_forced_stop(hosttest_lib):
+    lb, ub = [-np.inf, 0.0], [np.inf, np.inf]
+    cons, tols = [P.tut_c(2, 0), P.tut_c(-1, 1)], [1e-8, 1e-8]
+    r = run(hosttest_lib, nl.LD_MMA, 2, P.tut_f, cons, tols, lb, ub, P.TUT_X0, maxeval=5)
+    assert r["ret"] == nl.MAXEVAL_REACHED and r["numevals"] == 5
+    r = run(hosttest_lib, nl.LD_MMA, 2, P.tut_f, cons, tols, lb, ub, P.TUT_X0, ftol_rel=1e-3)
+    assert r["ret"] == nl.FTOL_REACHED
+    r = run(hosttest_lib, nl.LD_MMA, 2, P.tut_f, cons, tols, lb, ub, P.TUT_X0, xtol_abs=1e-3)
+    assert r["ret"] == nl.XTOL_REACHED
+    # an exception inside the objective becomes a forced stop and is re-raised (nlopt.hpp:149-166)
+    calls = [0]
+
+    def boom(x, g):
+        calls[0] += 1
+        if calls[0] == 3:
+            raise KeyError("stop here")
+        return P.tut_f(x, g)
+    o = nl.opt(nl.LD_MMA, 2, library=hosttest_lib)
+    o.set_lower_bounds(lb); o.set_min_objective(boom)
+    for c in cons:
+        o.add_inequality_constraint(c, 1e-8)
+    with pytest.raises(KeyError):
+        o.optimize(P.TUT_X0)
+    assert o.last_optimize_result() == nl.FORCED_STOP
+
+
+def test_nan_constraint_is_ignored_by_mma(hosttest_lib, reflib):
+    """mma.c:141-143 hidden feature: a constraint that returns NaN is inactive."""
+    def nanc(x, g):
+        if g.size:
+            g[:] = 0.0
+        return float("nan")
+    lb, ub = [-np.inf, 0.0], [np.inf, np.inf]
+    cons, tols = [P.tut_c(2, 0), nanc, P.tut_c(-1, 1)], [1e-8, 0.0, 1e-8]
+    a = run(hosttest_lib, nl.LD_MMA, 2, P.tut_f, cons, tols, lb, ub, P.TUT_X0, xtol_rel=1e-4)
+    b = run(reflib, nl.LD_MMA, 2, P.tut_f, cons, tols, lb, ub, P.TUT_X0, xtol_rel=1e-4)
+    assert a["ret"] == b["ret"] and abs(a["minf"] - b["minf"]) <= 1e-6
+
+
+def test_local_optimizer_supplies_dual_tolerances(hosttest_lib, reflib):
+    """optimize.c:817-826: ftol/maxeval of a local optimiser configure the dual solve (same outcome as
+    the reference, including its premature stop with these loose settings)."""
+    out = []
+    for lib in (hosttest_lib, reflib):
+        o = nl.opt(nl.LD_MMA, 2, library=lib)
+        lo = nl.opt(nl.LD_MMA, 2, library=lib)
+        lo.set_ftol_rel(1e-6); lo.set_maxeval(50)
+        o.set_local_optimizer(lo)
+        o.set_lower_bounds([-np.inf, 1e-6]); o.set_min_objective(P.tut_f); o.set_xtol_rel(1e-4)
+        o.add_inequality_constraint(P.tut_c(2, 0), 1e-8); o.add_inequality_constraint(P.tut_c(-1, 1), 1e-8)
+        x = o.optimize(P.TUT_X0)
+        out.append((o.last_optimize_result(), o.get_numevals(), x, o.last_optimum_value()))
+    assert out[0][0] == out[1][0] and out[0][1] == out[1][1]
+    assert np.allclose(out[0][2], out[1][2], atol=1e-9) and abs(out[0][3] - out[1][3]) <= 1e-9
+    bad = nl.opt(nl.LD_SLSQP, 2, library=hosttest_lib)
+    o.set_local_optimizer(bad) if False else None
+    o2 = nl.opt(nl.LD_MMA, 2, library=hosttest_lib)
+    o2.set_local_optimizer(bad)
+    o2.set_min_objective(P.tut_f)
+    with pytest.raises(ValueError):
+        o2.optimize([1.0, 1.0])
+    assert "dual_algorithm" in o2.get_errmsg()
+
+
+@pytest.mark.skipif(not refsrc.available(), reason="/root/reference not mounted")
+@pytest.mark.parametrize("use_our_header", [False, True])
+@pytest.mark.parametrize("arg", [None, "24", "41"])
+def test_reference_t_tutorial_links_and_passes(hosttest_lib, use_our_header, arg):
+    """BASELINE config 1: the reference's own test/t_tutorial.cxx, unmodified, compiled against the
+    reference-generated nlopt.hpp and linked with OUR object API + CCSA driver."""
+    out = os.path.join(ROOT, "tests", "_build", "refinc")
+    exe = refsrc.compile_reference_test("t_tutorial.cxx", hosttest_lib.path, out, use_our_header)
+    r = subprocess.run([exe] + ([arg] if arg else []), capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "found minimum" in r.stdout
+
+
+@pytest.mark.skipif(not refsrc.available(), reason="/root/reference not mounted")
+def test_reference_cpp_functor_links_and_runs(hosttest_lib):
+    out = os.path.join(ROOT, "tests", "_build", "refinc")
+    exe = refsrc.compile_reference_test("cpp_functor.cxx", hosttest_lib.path, out, False)
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
