@@ -317,6 +317,150 @@ __global__ void __launch_bounds__(BLOCK, MINB) dual_eval_kernel(const __grid_con
     }
 }
 
+// ---- the dual evaluation kernel, warp-granular persistent form ---------------------------------------
+// The reduction unit ("segment") is owned by ONE WARP: lanes stride over its double2 pairs, the m+3
+// lane accumulators are folded with a fixed xor-butterfly, lane 0 stores the record.  No shared
+// memory, no block barrier; the grid is sized to the machine (persistent CTAs) and warps walk the
+// rank's segments round-robin, so neighbouring warps stream neighbouring 16 KB windows of each array.
+// Because a record depends only on the segment (never on which warp or how many CTAs ran), the sums
+// are bit-identical for every grid size and every number of ranks.
+template <int NV>
+__device__ __forceinline__ void warp_fold(double (&acc)[NV])
+{
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) acc[k] = addx(acc[k], __shfl_xor_sync(0xffffffffu, acc[k], off));
+    }
+}
+
+__device__ __forceinline__ bool warp_is_last(unsigned *ticket, unsigned total, int lane)
+{
+    unsigned t = 0;
+    __threadfence();
+    if (lane == 0) t = atomicAdd(ticket, 1u);
+    t = __shfl_sync(0xffffffffu, t, 0);
+    return t == total - 1u;
+}
+
+template <int VARIANT, int MAXM, bool STORE, int BLOCK, int UNROLL, int MINB>
+__global__ void __launch_bounds__(BLOCK, MINB) dual_eval_warp_kernel(const __grid_constant__ DualArgs a)
+{
+    constexpr int MR = MAXM > 0 ? MAXM : 1;
+    constexpr int NV = 3 + MR;
+    constexpr int WARPS = BLOCK / 32;
+    const int lane = threadIdx.x & 31;
+    const unsigned warp_global = blockIdx.x * WARPS + (threadIdx.x >> 5);
+    const unsigned total_warps = gridDim.x * WARPS;
+    const unsigned nseg_local = a.segs_per_vshard * a.local_vshards;
+
+    const double2 *x2 = reinterpret_cast<const double2 *>(a.x);
+    const double2 *lb2 = reinterpret_cast<const double2 *>(a.lb);
+    const double2 *ub2 = reinterpret_cast<const double2 *>(a.ub);
+    const double2 *s2v = reinterpret_cast<const double2 *>(a.sigma);
+    const double2 *g2 = reinterpret_cast<const double2 *>(a.g);
+    const bool in_regs = a.m <= MAXM;
+
+    for (unsigned sl = warp_global; sl < nseg_local; sl += total_warps) {
+        const unsigned seg = a.seg0 + sl;
+        const unsigned long long p_lo = (unsigned long long) seg * a.npairs / a.nseg_total - a.pair0;
+        const unsigned long long p_hi = (unsigned long long) (seg + 1) * a.npairs / a.nseg_total - a.pair0;
+        double acc[NV];
+#pragma unroll
+        for (int k = 0; k < NV; ++k) acc[k] = 0.0;
+
+        for (unsigned long long p0 = p_lo + lane; p0 < p_hi; p0 += 32ull * UNROLL) {
+            double2 vx[UNROLL], vlb[UNROLL], vub[UNROLL], vs[UNROLL], vg[UNROLL];
+            double Ga[UNROLL][MR], Gb[UNROLL][MR];
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) {
+                const unsigned long long p = p0 + 32ull * u;
+                const bool live = u == 0 || p < p_hi;
+                vs[u] = make_double2(0.0, 0.0);      // sigma = 0 lanes are skipped by both formulas
+                vx[u] = vlb[u] = vub[u] = vg[u] = make_double2(0.0, 0.0);
+                if (live) {
+                    vx[u] = ld_stream(x2 + p); vlb[u] = ld_stream(lb2 + p); vub[u] = ld_stream(ub2 + p);
+                    vs[u] = ld_stream(s2v + p); vg[u] = ld_stream(g2 + p);
+                }
+#pragma unroll
+                for (int i = 0; i < MR; ++i) {
+                    Ga[u][i] = 0.0;
+                    Gb[u][i] = 0.0;
+                    if (MAXM > 0 && in_regs && i < a.m && live) {
+                        const double2 t = ld_stream(reinterpret_cast<const double2 *>(a.G + (unsigned long long) i * a.ld) + p);
+                        Ga[u][i] = t.x;
+                        Gb[u][i] = t.y;
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) {
+                const unsigned long long p = p0 + 32ull * u;
+                const bool live = u == 0 || p < p_hi;
+                const double *col = a.G + 2 * p;
+                double2 xc;
+                if (VARIANT == 0) {
+                    xc.x = mma_point<MAXM>(a, vx[u].x, vlb[u].x, vub[u].x, vs[u].x, vg[u].x, Ga[u], col, a.ld, acc);
+                    xc.y = mma_point<MAXM>(a, vx[u].y, vlb[u].y, vub[u].y, vs[u].y, vg[u].y, Gb[u], col + 1, a.ld, acc);
+                } else {
+                    xc.x = ccsaq_point<MAXM>(a, vx[u].x, vlb[u].x, vub[u].x, vs[u].x, vg[u].x, Ga[u], col, a.ld, acc);
+                    xc.y = ccsaq_point<MAXM>(a, vx[u].y, vlb[u].y, vub[u].y, vs[u].y, vg[u].y, Gb[u], col + 1, a.ld, acc);
+                }
+                if (STORE && live) st_stream(reinterpret_cast<double2 *>(a.xcur) + p, xc);
+            }
+        }
+
+        // segment record
+        warp_fold<NV>(acc);
+        if (lane == 0) {
+            double *rec = a.partials + (unsigned long long) sl * a.nvp;
+#pragma unroll
+            for (int k = 0; k < NV; ++k) rec[k] = acc[k];
+        }
+
+        // virtual-shard fold by the warp that completes the shard
+        const unsigned vs_local = sl / a.segs_per_vshard;
+        if (!warp_is_last(a.tickets + vs_local, a.segs_per_vshard, lane)) continue;
+#pragma unroll
+        for (int k = 0; k < NV; ++k) acc[k] = 0.0;
+        {
+            const double *base = a.partials + (unsigned long long) vs_local * a.segs_per_vshard * a.nvp;
+            for (unsigned r = lane; r < a.segs_per_vshard; r += 32)
+#pragma unroll
+                for (int k = 0; k < NV; ++k) acc[k] = addx(acc[k], __ldcg(base + (unsigned long long) r * a.nvp + k));
+        }
+        warp_fold<NV>(acc);
+        if (lane == 0) {
+            double *rec = a.vsums + (unsigned long long) vs_local * a.nvp;
+#pragma unroll
+            for (int k = 0; k < NV; ++k) rec[k] = acc[k];
+        }
+
+        // rank fold by the warp that completes the last virtual shard
+        if (!warp_is_last(a.tickets + a.local_vshards, a.local_vshards, lane)) continue;
+        if (lane < NV) {
+            if (a.publish_host) {
+                double s = __ldcg(a.vsums + lane);
+                for (unsigned v = 1; v < a.local_vshards; ++v) s = addx(s, __ldcg(a.vsums + (unsigned long long) v * a.nvp + lane));
+                a.out_host[lane] = s;
+                __threadfence_system();
+            } else {
+                const unsigned v0 = a.seg0 / a.segs_per_vshard;
+                for (unsigned v = 0; v < a.local_vshards; ++v)
+                    a.out_dev[(unsigned long long) (v0 + v) * a.nvp + lane] = __ldcg(a.vsums + (unsigned long long) v * a.nvp + lane);
+            }
+        }
+        __syncwarp();
+        if (lane == 0) {
+            for (unsigned v = 0; v <= a.local_vshards; ++v) a.tickets[v] = 0;    // ready for the next launch
+            if (a.publish_host) {
+                *a.flag_host = a.seq;
+                __threadfence_system();
+            }
+        }
+    }
+}
+
 // After the all-gather (several ranks): fold the 8 shard sums in index order and publish.
 __global__ void publish_kernel(const double *all_vsums /* [8][nvp] */, int nv, int nvp, volatile double *out_host,
                                volatile unsigned long long *flag_host, unsigned long long seq)

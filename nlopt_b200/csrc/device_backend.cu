@@ -60,6 +60,49 @@ DualKernel kernel_by_cfg(int cfg, bool store)
     }
 }
 
+// warp-granular persistent kernels: {threads per CTA, pairs per lane per trip, min CTAs/SM}; cfg id = 100 + index
+constexpr KernelCfg kWarpCfgs[] = {{256, 2, 2}, {256, 1, 3}, {256, 2, 3}, {512, 2, 1}, {256, 1, 4}, {128, 2, 4}, {256, 4, 1},
+                                   {512, 1, 1}, {256, 1, 2}, {128, 2, 6}};
+constexpr int kNumWarpCfgs = (int) (sizeof(kWarpCfgs) / sizeof(kWarpCfgs[0]));
+
+template <int VARIANT, int MAXM, int CFG>
+DualKernel warp_kernel_for(bool store)
+{
+    constexpr KernelCfg c = kWarpCfgs[CFG];
+    return store ? (DualKernel) dual_eval_warp_kernel<VARIANT, MAXM, true, c.block, c.unroll, c.minb>
+                 : (DualKernel) dual_eval_warp_kernel<VARIANT, MAXM, false, c.block, c.unroll, c.minb>;
+}
+
+template <int VARIANT, int MAXM>
+DualKernel warp_kernel_by_cfg(int cfg, bool store)
+{
+    switch (cfg) {
+    case 1: return warp_kernel_for<VARIANT, MAXM, 1>(store);
+    case 2: return warp_kernel_for<VARIANT, MAXM, 2>(store);
+    case 3: return warp_kernel_for<VARIANT, MAXM, 3>(store);
+    case 4: return warp_kernel_for<VARIANT, MAXM, 4>(store);
+    case 5: return warp_kernel_for<VARIANT, MAXM, 5>(store);
+    case 6: return warp_kernel_for<VARIANT, MAXM, 6>(store);
+    case 7: return warp_kernel_for<VARIANT, MAXM, 7>(store);
+    case 8: return warp_kernel_for<VARIANT, MAXM, 8>(store);
+    case 9: return warp_kernel_for<VARIANT, MAXM, 9>(store);
+    default: return warp_kernel_for<VARIANT, MAXM, 0>(store);
+    }
+}
+
+template <int VARIANT>
+DualKernel pick_warp_kernel(int maxm, int cfg, bool store)
+{
+    switch (maxm) {
+    case 0: return warp_kernel_by_cfg<VARIANT, 0>(cfg, store);
+    case 1: return warp_kernel_by_cfg<VARIANT, 1>(cfg, store);
+    case 2: return warp_kernel_by_cfg<VARIANT, 2>(cfg, store);
+    case 4: return warp_kernel_by_cfg<VARIANT, 4>(cfg, store);
+    case 8: return warp_kernel_by_cfg<VARIANT, 8>(cfg, store);
+    default: return warp_kernel_by_cfg<VARIANT, 16>(cfg, store);
+    }
+}
+
 // every m has the default geometry; the tuning variants are built for the headline m <= 4 and m <= 16 kernels
 template <int VARIANT>
 DualKernel pick_kernel(int maxm, int cfg, bool store)
@@ -212,6 +255,11 @@ bool DeviceBackend::alloc_state()
     if (m_ > (unsigned) kMaxParamM)
         return fail("more than 32 inequality constraints are not supported by this build of the dual kernel");
 
+    {
+        cudaDeviceProp prop;
+        NB_CUDA(cudaGetDeviceProperties(&prop, device_));
+        sm_count_ = prop.multiProcessorCount;
+    }
     NB_CUDA(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
     NB_CUDA(cudaStreamCreateWithFlags(&copy_stream_, cudaStreamNonBlocking));
     NB_CUDA(cudaEventCreateWithFlags(&copied_, cudaEventDisableTiming));
@@ -518,11 +566,23 @@ bool DeviceBackend::launch_dual(const double *y, const DualScalars &sc, bool sto
         e1 = ev_pool_[ev_used_++];
         cudaEventRecord(e0, stream_);
     }
-    const int cfg = kernel_cfg_ >= 0 && kernel_cfg_ < kNumCfgs ? kernel_cfg_ : 0;
-    DualKernel fn = variant_ == kMMA ? pick_kernel<0>(maxm, cfg, store) : pick_kernel<1>(maxm, cfg, store);
-    const int block = (maxm == 4 || (maxm == 1 && (cfg == 1 || cfg == 2)) || (maxm == 16 && (cfg == 2 || cfg == 5 || cfg == 9)))
-                          ? kCfgs[cfg].block : kCfgs[0].block;
-    fn<<<grid, block, 0, stream_>>>(a);
+    if (kernel_cfg_ >= 100) {
+        // persistent warp-granular kernel: grid sized to the machine, not to the problem
+        const int cfg = kernel_cfg_ - 100 < kNumWarpCfgs ? kernel_cfg_ - 100 : 0;
+        const KernelCfg c = kWarpCfgs[cfg];
+        DualKernel fn = variant_ == kMMA ? pick_warp_kernel<0>(maxm, cfg, store) : pick_warp_kernel<1>(maxm, cfg, store);
+        const int warps = c.block / 32;
+        long long want = ((long long) geo_.nseg_local + warps - 1) / warps;
+        long long cap = (long long) sm_count_ * (ctas_per_sm_ > 0 ? ctas_per_sm_ : c.minb);
+        const int pgrid = (int) (want < cap ? want : cap);
+        fn<<<pgrid < 1 ? 1 : pgrid, c.block, 0, stream_>>>(a);
+    } else {
+        const int cfg = kernel_cfg_ >= 0 && kernel_cfg_ < kNumCfgs ? kernel_cfg_ : 0;
+        DualKernel fn = variant_ == kMMA ? pick_kernel<0>(maxm, cfg, store) : pick_kernel<1>(maxm, cfg, store);
+        const int block = (maxm == 4 || (maxm == 1 && (cfg == 1 || cfg == 2)) || (maxm == 16 && (cfg == 2 || cfg == 5 || cfg == 9)))
+                              ? kCfgs[cfg].block : kCfgs[0].block;
+        fn<<<grid, block, 0, stream_>>>(a);
+    }
     if (time_kernels_) cudaEventRecord(e1, stream_);
     ++stats_->kernel_launches;
     NB_CUDA(cudaGetLastError());
@@ -735,6 +795,7 @@ bool DeviceBackend::configure(const char *key, long long value)
     const std::string k = key;
     if (k == "time_kernels") { time_kernels_ = value != 0; return true; }
     if (k == "kernel_cfg") { kernel_cfg_ = (int) value; return true; }
+    if (k == "ctas_per_sm") { ctas_per_sm_ = (int) value; return true; }
     if (k == "pmax" || k == "target_pairs") {
         if (value < 1) return fail("bad value");
         if (k == "pmax") pmax_ = (unsigned) value; else target_pairs_ = (unsigned) value;

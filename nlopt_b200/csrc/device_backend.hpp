@@ -72,6 +72,7 @@ private:
     Geometry geo_;
     unsigned target_pairs_ = kDefaultTargetPairs, pmax_ = kDefaultPmax;
     int device_ = 0;
+    int sm_count_ = 148, ctas_per_sm_ = 0;
     int kernel_cfg_ = 0;          // index into the launch-geometry table of device_backend.cu
 
     // device state

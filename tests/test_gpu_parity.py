@@ -56,6 +56,30 @@ def test_dual_kernel_vs_oracle(built, variant, n, m):
 
 
 @pytest.mark.parametrize("variant", [ob.MMA, ob.CCSAQ])
+@pytest.mark.parametrize("n,m", [(3, 1), (4097, 4), (300001, 4), (70000, 16), (9999, 20), (50000, 0)])
+def test_warp_kernel_vs_oracle_and_grid_independence(built, variant, n, m):
+    """The warp-granular persistent kernel: x* bit-exact, sums to rounding, and -- because a segment
+    record never depends on which warp produced it -- bit-identical sums for every launch geometry."""
+    inst = synth.kernel_instance(n, m)
+    want = ob.port_dual(variant, inst)
+    seen = []
+    for cfg, cps in ((100, 0), (101, 1), (103, 2), (105, 8), (107, 1), (100, 3)):
+        h = DualHandle(variant, inst)
+        h.configure("pmax", 1 << 20)
+        h.configure("kernel_cfg", cfg)
+        h.configure("ctas_per_sm", cps)
+        got = h.eval(inst["y"], want_xcur=True)
+        assert np.array_equal(got["xcur"], want["xcur"], equal_nan=True)
+        scale = float(n)
+        for k in ("ret", "g0", "w"):
+            assert close(got[k], want[k], scale), (cfg, k)
+        for i in range(m):
+            assert close(got["gc"][i], want["gc"][i], scale)
+        seen.append((got["ret"], got["g0"], got["w"], tuple(got["gc"])))
+    assert all(s == seen[0] for s in seen), "sums must not depend on the launch geometry"
+
+
+@pytest.mark.parametrize("variant", [ob.MMA, ob.CCSAQ])
 def test_dual_kernel_known_answer(built, variant):
     from test_oracle_port import KA, KA_EXPECT
     got = DualHandle(variant, KA).eval(KA["y"], want_xcur=True)
