@@ -27,6 +27,7 @@ struct BackendConfig {
     FuncSpec objective;
     std::vector<FuncSpec> constraints;       // inequality constraint objects, in registration order
     const double *lb = nullptr, *ub = nullptr;   // host, n entries
+    bool lb_uniform = false, ub_uniform = false; // all entries equal lb[0] / ub[0]: fill on the device, no H2D
     const double *x0_host = nullptr;         // host start point (n entries) ...
     double *x_dev = nullptr;                 // ... or this rank's device shard (device mode, in/out)
     const double *sigma_init = nullptr;      // nlopt initial step (host) or null

@@ -53,38 +53,51 @@ __device__ __forceinline__ void st_stream(double2 *p, double2 v)
 }
 
 // ---- arguments of one dual evaluation -------------------------------------------------------
+constexpr int kGroupWarps = 8;           // warps that sweep one group together (fixed: part of the reduction order)
+constexpr int kChunkPairs = 32 * kGroupWarps;   // 256 double2 pairs = 512 variables = 4 KB per array per sweep step
+
 struct DualArgs {
     // shard-local arrays (16-byte aligned, padded with sigma = 0 lanes)
     const double *x, *lb, *ub, *sigma, *g;
     const double *G;              // m rows of ld doubles
     double *xcur;                 // written iff STORE
     unsigned long long ld;        // row stride of G in doubles
-    // segment geometry (global, depends on n only)
-    unsigned long long npairs;    // ceil(n / 2) over ALL ranks
-    unsigned long long pair0;     // first global pair of this rank
+    // group geometry (global, depends on n only): group s covers chunks [s*nchunks/S, (s+1)*nchunks/S)
+    unsigned long long nchunks;   // ceil(ceil(n/2) / 256) over ALL ranks
+    unsigned long long chunk0;    // first global chunk of this rank
     unsigned nseg_total;          // S = 8 * P
-    unsigned seg0;                // first global segment of this rank
+    unsigned seg0;                // first global group of this rank
     unsigned segs_per_vshard;     // P
     unsigned local_vshards;       // 8 / world
     // reduction workspace
-    double *partials;             // [local segments][nvp]
+    double *partials;             // [local groups * 8][nvp]   warp records
+    double *grouprecs;            // [local groups][nvp]       group records
     double *vsums;                // [local_vshards][nvp]
+    unsigned *group_tickets;      // [local groups], zero between launches
     unsigned *tickets;            // [local_vshards + 1], zero between launches
     double *out_dev;              // [8][nvp] all-rank exchange buffer (this rank's slots filled)
     volatile double *out_host;    // mapped pinned [nvp]; written when publish_host
     volatile unsigned long long *flag_host;
     unsigned long long seq;
     int publish_host;             // 1: single rank, results + flag go straight to the host
-    int nvp;                      // stride of one partial record (>= 3 + chunk size)
+    int nvp;                      // stride of one record (>= 3 + chunk size)
     // the multipliers and penalties
     int m;                        // total number of constraints (rows of G)
-    int chunk0, chunk_n;          // this launch accumulates g_i for i in [chunk0, chunk0 + chunk_n)
+    int cons0, cons_n;            // this launch accumulates g_i for i in [cons0, cons0 + cons_n)
     unsigned active;              // bit i clear: constraint i switched off (MMA, NaN value)
     double rho, half_rho, u_ccsaq;    // u_ccsaq = rho + sum_i rhoc_i y_i (ccsa_quadratic.c:116-120)
     double y[kMaxParamM], rhoc[kMaxParamM], half_rhoc[kMaxParamM];
 };
 
-// ---- block-level reduction with a fixed tree --------------------------------------------------
+// pair range [p_lo, p_hi) of global group `seg`, relative to the start of this rank's shard
+__device__ __forceinline__ void group_pairs(unsigned long long nchunks, unsigned nseg_total, unsigned long long chunk0,
+                                            unsigned seg, unsigned long long *p_lo, unsigned long long *p_hi)
+{
+    *p_lo = ((unsigned long long) seg * nchunks / nseg_total - chunk0) * kChunkPairs;
+    *p_hi = ((unsigned long long) (seg + 1) * nchunks / nseg_total - chunk0) * kChunkPairs;
+}
+
+// ---- block-level reduction with a fixed tree (end_outer_kernel) ----------------------------------
 template <int NV, int BLOCK = kBlock>
 __device__ __forceinline__ void block_reduce_to(double (&acc)[NV], double *smem /* [(BLOCK/32)*NV] */, double *out)
 {
@@ -118,8 +131,10 @@ __device__ __forceinline__ bool is_last_arrival(unsigned *ticket, unsigned total
 }
 
 // ---- per-variable closed forms ------------------------------------------------------------------
-// MMA: mma.c:96-129.  G[i] holds d c_i / d x_j for the rows kept in registers.
-template <int MAXM>
+// MAXM rows of grad_c are kept in registers; FULL means m == MAXM with every constraint active, which
+// strips the per-row predicates from the unrolled loops (the common case m in {1,2,4,8,16}).
+// MMA: mma.c:96-129.
+template <int MAXM, bool FULL>
 __device__ __forceinline__ double mma_point(const DualArgs &a, double x, double lb, double ub, double s, double g,
                                             const double (&Gr)[MAXM > 0 ? MAXM : 1], const double *Gcol,
                                             unsigned long long ld, double (&acc)[3 + (MAXM > 0 ? MAXM : 1)])
@@ -128,10 +143,10 @@ __device__ __forceinline__ double mma_point(const DualArgs &a, double x, double 
     const double ag_s = mulx(fabs(g), s);
     double u = g;
     double v = addx(ag_s, a.half_rho);
-    if (a.m <= MAXM) {
+    if (FULL || a.m <= MAXM) {
 #pragma unroll
         for (int i = 0; i < MAXM; ++i)
-            if (i < a.m && ((a.active >> i) & 1u)) {
+            if (FULL || (i < a.m && ((a.active >> i) & 1u))) {
                 u = addx(u, mulx(Gr[i], a.y[i]));
                 v = addx(v, mulx(addx(mulx(fabs(Gr[i]), s), a.half_rhoc[i]), a.y[i]));
             }
@@ -160,9 +175,9 @@ __device__ __forceinline__ double mma_point(const DualArgs &a, double x, double 
     acc[2] = addx(acc[2], mulx(mulx(0.5, dx2), dinv));                                  // mma.c:125
 #pragma unroll
     for (int k = 0; k < MAXM; ++k) {
-        const int i = a.chunk0 + k;
-        if (k < a.chunk_n && ((a.active >> i) & 1u)) {
-            const double gi = (a.m <= MAXM) ? Gr[k] : Gcol[(unsigned long long) i * ld];
+        const int i = FULL ? k : a.cons0 + k;
+        if (FULL || (k < a.cons_n && ((a.active >> i) & 1u))) {
+            const double gi = (FULL || a.m <= MAXM) ? Gr[k] : Gcol[(unsigned long long) i * ld];
             acc[3 + k] = addx(acc[3 + k],
                               mulx(addx(mulx(gi, c), mulx(addx(mulx(fabs(gi), s), a.half_rhoc[i]), dx2)), dinv));   // mma.c:127
         }
@@ -171,17 +186,17 @@ __device__ __forceinline__ double mma_point(const DualArgs &a, double x, double 
 }
 
 // CCSAQ: ccsa_quadratic.c:111-140
-template <int MAXM>
+template <int MAXM, bool FULL>
 __device__ __forceinline__ double ccsaq_point(const DualArgs &a, double x, double lb, double ub, double s, double g,
                                               const double (&Gr)[MAXM > 0 ? MAXM : 1], const double *Gcol,
                                               unsigned long long ld, double (&acc)[3 + (MAXM > 0 ? MAXM : 1)])
 {
     if (s == 0) return x;                                    // ccsa_quadratic.c:111-114
     double v = g;
-    if (a.m <= MAXM) {
+    if (FULL || a.m <= MAXM) {
 #pragma unroll
         for (int i = 0; i < MAXM; ++i)
-            if (i < a.m) v = addx(v, mulx(Gr[i], a.y[i]));
+            if (FULL || i < a.m) v = addx(v, mulx(Gr[i], a.y[i]));
     } else {
         for (int i = 0; i < a.m; ++i) v = addx(v, mulx(Gcol[(unsigned long long) i * ld], a.y[i]));
     }
@@ -199,131 +214,26 @@ __device__ __forceinline__ double ccsaq_point(const DualArgs &a, double x, doubl
     acc[2] = addx(acc[2], q);                                                            // :138
 #pragma unroll
     for (int k = 0; k < MAXM; ++k) {
-        const int i = a.chunk0 + k;
-        if (k < a.chunk_n) {
-            const double gi = (a.m <= MAXM) ? Gr[k] : Gcol[(unsigned long long) i * ld];
+        const int i = FULL ? k : a.cons0 + k;
+        if (FULL || k < a.cons_n) {
+            const double gi = (FULL || a.m <= MAXM) ? Gr[k] : Gcol[(unsigned long long) i * ld];
             acc[3 + k] = addx(acc[3 + k], addx(mulx(gi, dx), mulx(a.rhoc[i], q)));       // :139-140
         }
     }
     return xc;
 }
 
-// ---- the dual evaluation kernel -----------------------------------------------------------------
-// grid = number of local segments; CTA b owns global segment seg0 + b.  BLOCK threads; each thread
-// takes UNROLL double2 pairs per trip (all loads of a trip are issued before any arithmetic).
-template <int VARIANT, int MAXM, bool STORE, int BLOCK, int UNROLL, int MINB>
-__global__ void __launch_bounds__(BLOCK, MINB) dual_eval_kernel(const __grid_constant__ DualArgs a)
-{
-    constexpr int MR = MAXM > 0 ? MAXM : 1;
-    constexpr int NV = 3 + MR;
-    __shared__ double s_red[(BLOCK / 32) * NV];
-    __shared__ int s_flag;
-
-    const unsigned seg = a.seg0 + blockIdx.x;
-    // pair range of this segment, relative to the shard start
-    const unsigned long long p_lo = (unsigned long long) seg * a.npairs / a.nseg_total - a.pair0;
-    const unsigned long long p_hi = (unsigned long long) (seg + 1) * a.npairs / a.nseg_total - a.pair0;
-
-    double acc[NV];
-#pragma unroll
-    for (int k = 0; k < NV; ++k) acc[k] = 0.0;
-
-    const double2 *x2 = reinterpret_cast<const double2 *>(a.x);
-    const double2 *lb2 = reinterpret_cast<const double2 *>(a.lb);
-    const double2 *ub2 = reinterpret_cast<const double2 *>(a.ub);
-    const double2 *s2v = reinterpret_cast<const double2 *>(a.sigma);
-    const double2 *g2 = reinterpret_cast<const double2 *>(a.g);
-    const bool in_regs = a.m <= MAXM;
-
-    for (unsigned long long p0 = p_lo + threadIdx.x; p0 < p_hi; p0 += (unsigned long long) BLOCK * UNROLL) {
-        double2 vx[UNROLL], vlb[UNROLL], vub[UNROLL], vs[UNROLL], vg[UNROLL];
-        double Ga[UNROLL][MR], Gb[UNROLL][MR];
-#pragma unroll
-        for (int u = 0; u < UNROLL; ++u) {
-            const unsigned long long p = p0 + (unsigned long long) u * BLOCK;
-            const bool live = UNROLL == 1 || p < p_hi;
-            vs[u] = make_double2(0.0, 0.0);          // sigma = 0 lanes are skipped by both formulas
-            vx[u] = vlb[u] = vub[u] = vg[u] = make_double2(0.0, 0.0);
-            if (live) {
-                vx[u] = ld_stream(x2 + p); vlb[u] = ld_stream(lb2 + p); vub[u] = ld_stream(ub2 + p);
-                vs[u] = ld_stream(s2v + p); vg[u] = ld_stream(g2 + p);
-            }
-#pragma unroll
-            for (int i = 0; i < MR; ++i) {
-                Ga[u][i] = 0.0;
-                Gb[u][i] = 0.0;
-                if (MAXM > 0 && in_regs && i < a.m && live) {
-                    const double2 t = ld_stream(reinterpret_cast<const double2 *>(a.G + (unsigned long long) i * a.ld) + p);
-                    Ga[u][i] = t.x;
-                    Gb[u][i] = t.y;
-                }
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < UNROLL; ++u) {
-            const unsigned long long p = p0 + (unsigned long long) u * BLOCK;
-            const bool live = UNROLL == 1 || p < p_hi;
-            const double *col = a.G + 2 * p;
-            double2 xc;
-            if (VARIANT == 0) {
-                xc.x = mma_point<MAXM>(a, vx[u].x, vlb[u].x, vub[u].x, vs[u].x, vg[u].x, Ga[u], col, a.ld, acc);
-                xc.y = mma_point<MAXM>(a, vx[u].y, vlb[u].y, vub[u].y, vs[u].y, vg[u].y, Gb[u], col + 1, a.ld, acc);
-            } else {
-                xc.x = ccsaq_point<MAXM>(a, vx[u].x, vlb[u].x, vub[u].x, vs[u].x, vg[u].x, Ga[u], col, a.ld, acc);
-                xc.y = ccsaq_point<MAXM>(a, vx[u].y, vlb[u].y, vub[u].y, vs[u].y, vg[u].y, Gb[u], col + 1, a.ld, acc);
-            }
-            if (STORE && live) st_stream(reinterpret_cast<double2 *>(a.xcur) + p, xc);
-        }
-    }
-
-    // segment partial
-    block_reduce_to<NV, BLOCK>(acc, s_red, a.partials + (unsigned long long) blockIdx.x * a.nvp);
-
-    // virtual-shard fold by the last CTA of the shard
-    const unsigned vs_local = blockIdx.x / a.segs_per_vshard;
-    if (!is_last_arrival(a.tickets + vs_local, a.segs_per_vshard, &s_flag)) return;
-#pragma unroll
-    for (int k = 0; k < NV; ++k) acc[k] = 0.0;
-    {
-        const double *base = a.partials + (unsigned long long) vs_local * a.segs_per_vshard * a.nvp;
-        for (unsigned sgi = threadIdx.x; sgi < a.segs_per_vshard; sgi += BLOCK)
-#pragma unroll
-            for (int k = 0; k < NV; ++k) acc[k] = addx(acc[k], __ldcg(base + (unsigned long long) sgi * a.nvp + k));
-    }
-    block_reduce_to<NV, BLOCK>(acc, s_red, a.vsums + (unsigned long long) vs_local * a.nvp);
-
-    // rank fold by the last virtual shard
-    if (!is_last_arrival(a.tickets + a.local_vshards, a.local_vshards, &s_flag)) return;
-    if (threadIdx.x < NV) {
-        if (a.publish_host) {
-            double s = __ldcg(a.vsums + threadIdx.x);
-            for (unsigned v = 1; v < a.local_vshards; ++v) s = addx(s, __ldcg(a.vsums + (unsigned long long) v * a.nvp + threadIdx.x));
-            a.out_host[threadIdx.x] = s;
-            __threadfence_system();
-        } else {
-            // several ranks: hand this rank's shard sums to the exchange buffer, untouched
-            const unsigned v0 = a.seg0 / a.segs_per_vshard;
-            for (unsigned v = 0; v < a.local_vshards; ++v)
-                a.out_dev[(unsigned long long) (v0 + v) * a.nvp + threadIdx.x] = __ldcg(a.vsums + (unsigned long long) v * a.nvp + threadIdx.x);
-        }
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        for (unsigned v = 0; v <= a.local_vshards; ++v) a.tickets[v] = 0;    // ready for the next launch
-        if (a.publish_host) {
-            *a.flag_host = a.seq;
-            __threadfence_system();
-        }
-    }
-}
-
-// ---- the dual evaluation kernel, warp-granular persistent form ---------------------------------------
-// The reduction unit ("segment") is owned by ONE WARP: lanes stride over its double2 pairs, the m+3
-// lane accumulators are folded with a fixed xor-butterfly, lane 0 stores the record.  No shared
-// memory, no block barrier; the grid is sized to the machine (persistent CTAs) and warps walk the
-// rank's segments round-robin, so neighbouring warps stream neighbouring 16 KB windows of each array.
-// Because a record depends only on the segment (never on which warp or how many CTAs ran), the sums
-// are bit-identical for every grid size and every number of ranks.
+// ---- the dual evaluation kernel ---------------------------------------------------------------------
+// Persistent CTAs (grid sized to the machine).  A *group* is a contiguous run of 512-variable chunks;
+// the 8 warps of a group slot sweep it together -- sweep step t reads one 4 KB-contiguous chunk per array,
+// warp w taking lanes [32w, 32w+32) of it -- but every warp keeps its OWN m+3 accumulators over the group
+// and folds them with a fixed xor-butterfly into a warp record.  No shared memory and no block barrier
+// on the streaming path.  Fold tree (all in fixed order, all un-fused adds):
+//   warp record -> group record (8 warp records, by the warp that completes the group)
+//               -> virtual-shard sum (P group records, by the warp that completes the shard)
+//               -> rank sum / exchange buffer (8/world shard sums, by the warp that completes the rank).
+// A record depends only on n (the cuts) -- never on the grid size, on which CTA swept the group or on the
+// number of ranks -- so the m+3 sums are bit-identical for every launch geometry and every world size.
 template <int NV>
 __device__ __forceinline__ void warp_fold(double (&acc)[NV])
 {
@@ -340,41 +250,43 @@ __device__ __forceinline__ bool warp_is_last(unsigned *ticket, unsigned total, i
     __threadfence();
     if (lane == 0) t = atomicAdd(ticket, 1u);
     t = __shfl_sync(0xffffffffu, t, 0);
+    __threadfence();
     return t == total - 1u;
 }
 
-template <int VARIANT, int MAXM, bool STORE, int BLOCK, int UNROLL, int MINB>
-__global__ void __launch_bounds__(BLOCK, MINB) dual_eval_warp_kernel(const __grid_constant__ DualArgs a)
+template <int VARIANT, int MAXM, bool FULL, bool STORE, int BLOCK, int UNROLL, int MINB>
+__global__ void __launch_bounds__(BLOCK, MINB) dual_eval_kernel(const __grid_constant__ DualArgs a)
 {
     constexpr int MR = MAXM > 0 ? MAXM : 1;
     constexpr int NV = 3 + MR;
-    constexpr int WARPS = BLOCK / 32;
+    constexpr int SLOTS = BLOCK / (32 * kGroupWarps);        // groups a CTA sweeps at a time
+    static_assert(BLOCK % (32 * kGroupWarps) == 0, "a CTA holds whole group slots");
     const int lane = threadIdx.x & 31;
-    const unsigned warp_global = blockIdx.x * WARPS + (threadIdx.x >> 5);
-    const unsigned total_warps = gridDim.x * WARPS;
-    const unsigned nseg_local = a.segs_per_vshard * a.local_vshards;
+    const int sub = (threadIdx.x >> 5) % kGroupWarps;        // which eighth of every chunk this warp owns
+    const unsigned slot = blockIdx.x * SLOTS + (threadIdx.x >> 5) / kGroupWarps;
+    const unsigned nslots = gridDim.x * SLOTS;
+    const unsigned ngroups = a.segs_per_vshard * a.local_vshards;
 
     const double2 *x2 = reinterpret_cast<const double2 *>(a.x);
     const double2 *lb2 = reinterpret_cast<const double2 *>(a.lb);
     const double2 *ub2 = reinterpret_cast<const double2 *>(a.ub);
     const double2 *s2v = reinterpret_cast<const double2 *>(a.sigma);
     const double2 *g2 = reinterpret_cast<const double2 *>(a.g);
-    const bool in_regs = a.m <= MAXM;
+    const bool in_regs = FULL || a.m <= MAXM;
 
-    for (unsigned sl = warp_global; sl < nseg_local; sl += total_warps) {
-        const unsigned seg = a.seg0 + sl;
-        const unsigned long long p_lo = (unsigned long long) seg * a.npairs / a.nseg_total - a.pair0;
-        const unsigned long long p_hi = (unsigned long long) (seg + 1) * a.npairs / a.nseg_total - a.pair0;
+    for (unsigned gl = slot; gl < ngroups; gl += nslots) {
+        unsigned long long p_lo, p_hi;
+        group_pairs(a.nchunks, a.nseg_total, a.chunk0, a.seg0 + gl, &p_lo, &p_hi);
         double acc[NV];
 #pragma unroll
         for (int k = 0; k < NV; ++k) acc[k] = 0.0;
 
-        for (unsigned long long p0 = p_lo + lane; p0 < p_hi; p0 += 32ull * UNROLL) {
+        for (unsigned long long p0 = p_lo + sub * 32 + lane; p0 < p_hi; p0 += (unsigned long long) kChunkPairs * UNROLL) {
             double2 vx[UNROLL], vlb[UNROLL], vub[UNROLL], vs[UNROLL], vg[UNROLL];
             double Ga[UNROLL][MR], Gb[UNROLL][MR];
 #pragma unroll
             for (int u = 0; u < UNROLL; ++u) {
-                const unsigned long long p = p0 + 32ull * u;
+                const unsigned long long p = p0 + (unsigned long long) kChunkPairs * u;
                 const bool live = u == 0 || p < p_hi;
                 vs[u] = make_double2(0.0, 0.0);      // sigma = 0 lanes are skipped by both formulas
                 vx[u] = vlb[u] = vub[u] = vg[u] = make_double2(0.0, 0.0);
@@ -386,7 +298,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) dual_eval_warp_kernel(const __gri
                 for (int i = 0; i < MR; ++i) {
                     Ga[u][i] = 0.0;
                     Gb[u][i] = 0.0;
-                    if (MAXM > 0 && in_regs && i < a.m && live) {
+                    if (MAXM > 0 && in_regs && (FULL || i < a.m) && live) {
                         const double2 t = ld_stream(reinterpret_cast<const double2 *>(a.G + (unsigned long long) i * a.ld) + p);
                         Ga[u][i] = t.x;
                         Gb[u][i] = t.y;
@@ -395,36 +307,47 @@ __global__ void __launch_bounds__(BLOCK, MINB) dual_eval_warp_kernel(const __gri
             }
 #pragma unroll
             for (int u = 0; u < UNROLL; ++u) {
-                const unsigned long long p = p0 + 32ull * u;
+                const unsigned long long p = p0 + (unsigned long long) kChunkPairs * u;
                 const bool live = u == 0 || p < p_hi;
                 const double *col = a.G + 2 * p;
                 double2 xc;
                 if (VARIANT == 0) {
-                    xc.x = mma_point<MAXM>(a, vx[u].x, vlb[u].x, vub[u].x, vs[u].x, vg[u].x, Ga[u], col, a.ld, acc);
-                    xc.y = mma_point<MAXM>(a, vx[u].y, vlb[u].y, vub[u].y, vs[u].y, vg[u].y, Gb[u], col + 1, a.ld, acc);
+                    xc.x = mma_point<MAXM, FULL>(a, vx[u].x, vlb[u].x, vub[u].x, vs[u].x, vg[u].x, Ga[u], col, a.ld, acc);
+                    xc.y = mma_point<MAXM, FULL>(a, vx[u].y, vlb[u].y, vub[u].y, vs[u].y, vg[u].y, Gb[u], col + 1, a.ld, acc);
                 } else {
-                    xc.x = ccsaq_point<MAXM>(a, vx[u].x, vlb[u].x, vub[u].x, vs[u].x, vg[u].x, Ga[u], col, a.ld, acc);
-                    xc.y = ccsaq_point<MAXM>(a, vx[u].y, vlb[u].y, vub[u].y, vs[u].y, vg[u].y, Gb[u], col + 1, a.ld, acc);
+                    xc.x = ccsaq_point<MAXM, FULL>(a, vx[u].x, vlb[u].x, vub[u].x, vs[u].x, vg[u].x, Ga[u], col, a.ld, acc);
+                    xc.y = ccsaq_point<MAXM, FULL>(a, vx[u].y, vlb[u].y, vub[u].y, vs[u].y, vg[u].y, Gb[u], col + 1, a.ld, acc);
                 }
                 if (STORE && live) st_stream(reinterpret_cast<double2 *>(a.xcur) + p, xc);
             }
         }
 
-        // segment record
+        // warp record
         warp_fold<NV>(acc);
         if (lane == 0) {
-            double *rec = a.partials + (unsigned long long) sl * a.nvp;
+            double *rec = a.partials + ((unsigned long long) gl * kGroupWarps + sub) * a.nvp;
 #pragma unroll
             for (int k = 0; k < NV; ++k) rec[k] = acc[k];
         }
+        // group record, by the warp that completes the group
+        if (!warp_is_last(a.group_tickets + gl, kGroupWarps, lane)) continue;
+        if (lane < NV) {
+            const double *rec = a.partials + (unsigned long long) gl * kGroupWarps * a.nvp + lane;
+            double s = __ldcg(rec);
+#pragma unroll
+            for (int w = 1; w < kGroupWarps; ++w) s = addx(s, __ldcg(rec + (unsigned long long) w * a.nvp));
+            a.grouprecs[(unsigned long long) gl * a.nvp + lane] = s;
+        }
+        if (lane == 0) a.group_tickets[gl] = 0;
+        __syncwarp();
 
-        // virtual-shard fold by the warp that completes the shard
-        const unsigned vs_local = sl / a.segs_per_vshard;
+        // virtual-shard sum, by the warp that completes the shard
+        const unsigned vs_local = gl / a.segs_per_vshard;
         if (!warp_is_last(a.tickets + vs_local, a.segs_per_vshard, lane)) continue;
 #pragma unroll
         for (int k = 0; k < NV; ++k) acc[k] = 0.0;
         {
-            const double *base = a.partials + (unsigned long long) vs_local * a.segs_per_vshard * a.nvp;
+            const double *base = a.grouprecs + (unsigned long long) vs_local * a.segs_per_vshard * a.nvp;
             for (unsigned r = lane; r < a.segs_per_vshard; r += 32)
 #pragma unroll
                 for (int k = 0; k < NV; ++k) acc[k] = addx(acc[k], __ldcg(base + (unsigned long long) r * a.nvp + k));
@@ -436,7 +359,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) dual_eval_warp_kernel(const __gri
             for (int k = 0; k < NV; ++k) rec[k] = acc[k];
         }
 
-        // rank fold by the warp that completes the last virtual shard
+        // rank sum, by the warp that completes the last virtual shard
         if (!warp_is_last(a.tickets + a.local_vshards, a.local_vshards, lane)) continue;
         if (lane < NV) {
             if (a.publish_host) {
@@ -478,6 +401,13 @@ __global__ void publish_kernel(const double *all_vsums /* [8][nvp] */, int nv, i
     }
 }
 
+__global__ void fill_kernel(double *dst, double value, unsigned long long n_local)
+{
+    for (unsigned long long j = blockIdx.x * (unsigned long long) blockDim.x + threadIdx.x; j < n_local;
+         j += (unsigned long long) gridDim.x * blockDim.x)
+        dst[j] = value;
+}
+
 // ---- sigma initialisation, mma.c:202-210 ---------------------------------------------------------
 __device__ __forceinline__ bool dev_isinf(double v) { return fabs(v) >= HUGE_VAL * 0.99 || isinf(v); }
 
@@ -501,7 +431,7 @@ struct EndOuterArgs {
     const double *lb, *ub;
     const double *w;          // x weights or null (stop.c:37-79)
     const double *xtol_abs;   // or null
-    unsigned long long n_local, npairs, pair0;
+    unsigned long long n_local, nchunks, chunk0;
     unsigned nseg_total, seg0, segs_per_vshard, local_vshards;
     double *partials, *vsums;
     unsigned *tickets;
@@ -521,8 +451,8 @@ __global__ void __launch_bounds__(kBlock) end_outer_kernel(const __grid_constant
     __shared__ double s_red[kWarps * NV];
     __shared__ int s_flag;
     const unsigned seg = a.seg0 + blockIdx.x;
-    const unsigned long long p_lo = (unsigned long long) seg * a.npairs / a.nseg_total - a.pair0;
-    const unsigned long long p_hi = (unsigned long long) (seg + 1) * a.npairs / a.nseg_total - a.pair0;
+    unsigned long long p_lo, p_hi;
+    group_pairs(a.nchunks, a.nseg_total, a.chunk0, seg, &p_lo, &p_hi);
     double acc[NV] = {0.0, 0.0, 0.0};
     for (unsigned long long p = p_lo + threadIdx.x; p < p_hi; p += kBlock) {
 #pragma unroll

@@ -27,94 +27,55 @@ namespace {
 
 int grid_for(unsigned long long n) { unsigned long long g = (n + kBlock - 1) / kBlock; return (int) (g < 1 ? 1 : (g > 148ull * 16 ? 148ull * 16 : g)); }
 
-// launch-geometry variants of the dual kernel: {threads per CTA, pairs per thread per trip, min CTAs/SM}
+// launch-geometry variants of the dual kernel: {threads per CTA, chunks per sweep step, min CTAs/SM}.
+// Tuned on B200 at n = 1e7 (profiles/r01_tune_group_kernel.jsonl): occupancy matters most; the grid is
+// 4x the resident CTAs (the hardware scheduler evens out the tail better than a strictly persistent grid).
 struct KernelCfg { int block, unroll, minb; };
-constexpr KernelCfg kCfgs[] = {{256, 1, 1}, {256, 2, 1}, {512, 1, 1}, {256, 1, 3}, {256, 1, 4}, {128, 2, 1}, {512, 2, 1},
-                               {128, 4, 1}, {256, 2, 2}, {1024, 1, 1}};
+constexpr KernelCfg kCfgs[] = {{256, 1, 3}, {256, 1, 4}, {256, 2, 3}, {256, 1, 2}};
 constexpr int kNumCfgs = (int) (sizeof(kCfgs) / sizeof(kCfgs[0]));
 
 typedef void (*DualKernel)(const DualArgs);
 
-template <int VARIANT, int MAXM, int CFG>
+template <int VARIANT, int MAXM, bool FULL, int CFG>
 DualKernel kernel_for(bool store)
 {
     constexpr KernelCfg c = kCfgs[CFG];
-    return store ? (DualKernel) dual_eval_kernel<VARIANT, MAXM, true, c.block, c.unroll, c.minb>
-                 : (DualKernel) dual_eval_kernel<VARIANT, MAXM, false, c.block, c.unroll, c.minb>;
+    return store ? (DualKernel) dual_eval_kernel<VARIANT, MAXM, FULL, true, c.block, c.unroll, c.minb>
+                 : (DualKernel) dual_eval_kernel<VARIANT, MAXM, FULL, false, c.block, c.unroll, c.minb>;
 }
 
-template <int VARIANT, int MAXM>
+// rows kept in registers <= 4: every geometry is built (tuning); 8 or 16 rows need the 128-register budget
+template <int VARIANT, int MAXM, bool FULL>
 DualKernel kernel_by_cfg(int cfg, bool store)
 {
+    if (MAXM >= 8) return kernel_for<VARIANT, MAXM, FULL, 3>(store);
     switch (cfg) {
-    case 1: return kernel_for<VARIANT, MAXM, 1>(store);
-    case 2: return kernel_for<VARIANT, MAXM, 2>(store);
-    case 3: return kernel_for<VARIANT, MAXM, 3>(store);
-    case 4: return kernel_for<VARIANT, MAXM, 4>(store);
-    case 5: return kernel_for<VARIANT, MAXM, 5>(store);
-    case 6: return kernel_for<VARIANT, MAXM, 6>(store);
-    case 7: return kernel_for<VARIANT, MAXM, 7>(store);
-    case 8: return kernel_for<VARIANT, MAXM, 8>(store);
-    case 9: return kernel_for<VARIANT, MAXM, 9>(store);
-    default: return kernel_for<VARIANT, MAXM, 0>(store);
+    case 1: return kernel_for<VARIANT, (MAXM >= 8 ? 0 : MAXM), FULL, 1>(store);
+    case 2: return kernel_for<VARIANT, (MAXM >= 8 ? 0 : MAXM), FULL, 2>(store);
+    case 3: return kernel_for<VARIANT, (MAXM >= 8 ? 0 : MAXM), FULL, 3>(store);
+    default: return kernel_for<VARIANT, (MAXM >= 8 ? 0 : MAXM), FULL, 0>(store);
     }
 }
 
-// warp-granular persistent kernels: {threads per CTA, pairs per lane per trip, min CTAs/SM}; cfg id = 100 + index
-constexpr KernelCfg kWarpCfgs[] = {{256, 2, 2}, {256, 1, 3}, {256, 2, 3}, {512, 2, 1}, {256, 1, 4}, {128, 2, 4}, {256, 4, 1},
-                                   {512, 1, 1}, {256, 1, 2}, {128, 2, 6}};
-constexpr int kNumWarpCfgs = (int) (sizeof(kWarpCfgs) / sizeof(kWarpCfgs[0]));
-
-template <int VARIANT, int MAXM, int CFG>
-DualKernel warp_kernel_for(bool store)
-{
-    constexpr KernelCfg c = kWarpCfgs[CFG];
-    return store ? (DualKernel) dual_eval_warp_kernel<VARIANT, MAXM, true, c.block, c.unroll, c.minb>
-                 : (DualKernel) dual_eval_warp_kernel<VARIANT, MAXM, false, c.block, c.unroll, c.minb>;
-}
-
-template <int VARIANT, int MAXM>
-DualKernel warp_kernel_by_cfg(int cfg, bool store)
-{
-    switch (cfg) {
-    case 1: return warp_kernel_for<VARIANT, MAXM, 1>(store);
-    case 2: return warp_kernel_for<VARIANT, MAXM, 2>(store);
-    case 3: return warp_kernel_for<VARIANT, MAXM, 3>(store);
-    case 4: return warp_kernel_for<VARIANT, MAXM, 4>(store);
-    case 5: return warp_kernel_for<VARIANT, MAXM, 5>(store);
-    case 6: return warp_kernel_for<VARIANT, MAXM, 6>(store);
-    case 7: return warp_kernel_for<VARIANT, MAXM, 7>(store);
-    case 8: return warp_kernel_for<VARIANT, MAXM, 8>(store);
-    case 9: return warp_kernel_for<VARIANT, MAXM, 9>(store);
-    default: return warp_kernel_for<VARIANT, MAXM, 0>(store);
-    }
-}
-
-template <int VARIANT>
-DualKernel pick_warp_kernel(int maxm, int cfg, bool store)
-{
-    switch (maxm) {
-    case 0: return warp_kernel_by_cfg<VARIANT, 0>(cfg, store);
-    case 1: return warp_kernel_by_cfg<VARIANT, 1>(cfg, store);
-    case 2: return warp_kernel_by_cfg<VARIANT, 2>(cfg, store);
-    case 4: return warp_kernel_by_cfg<VARIANT, 4>(cfg, store);
-    case 8: return warp_kernel_by_cfg<VARIANT, 8>(cfg, store);
-    default: return warp_kernel_by_cfg<VARIANT, 16>(cfg, store);
-    }
-}
-
-// every m has the default geometry; the tuning variants are built for the headline m <= 4 and m <= 16 kernels
-template <int VARIANT>
+template <int VARIANT, bool FULL>
 DualKernel pick_kernel(int maxm, int cfg, bool store)
 {
     switch (maxm) {
-    case 0: return kernel_for<VARIANT, 0, 0>(store);
-    case 1: return kernel_by_cfg<VARIANT, 1>(cfg == 1 || cfg == 2 ? cfg : 0, store);
-    case 2: return kernel_for<VARIANT, 2, 0>(store);
-    case 4: return kernel_by_cfg<VARIANT, 4>(cfg, store);
-    case 8: return kernel_for<VARIANT, 8, 0>(store);
-    default: return kernel_by_cfg<VARIANT, 16>(cfg == 2 || cfg == 5 || cfg == 9 ? cfg : 0, store);
+    case 0: return kernel_by_cfg<VARIANT, 0, FULL>(cfg, store);
+    case 1: return kernel_by_cfg<VARIANT, 1, FULL>(cfg, store);
+    case 2: return kernel_by_cfg<VARIANT, 2, FULL>(cfg, store);
+    case 4: return kernel_by_cfg<VARIANT, 4, FULL>(cfg, store);
+    case 8: return kernel_by_cfg<VARIANT, 8, FULL>(cfg, store);
+    default: return kernel_by_cfg<VARIANT, 16, FULL>(cfg, store);
     }
+}
+
+// measured best geometry per (variant, rows in registers)
+int default_cfg(Variant v, int maxm)
+{
+    if (maxm >= 8) return 3;
+    if (maxm == 4) return 0;
+    return v == kMMA ? 1 : 2;
 }
 
 // Process-wide cache of the big allocations (device state pool, pinned staging).  nlopt_optimize
@@ -206,6 +167,8 @@ void DeviceBackend::free_state()
     if (w_dev_) cudaFree(w_dev_);
     if (xtol_abs_dev_) cudaFree(xtol_abs_dev_);
     if (partials_) cudaFree(partials_);
+    if (grouprecs_) cudaFree(grouprecs_);
+    if (group_tickets_) cudaFree(group_tickets_);
     if (vsums_) cudaFree(vsums_);
     if (out_dev_) cudaFree(out_dev_);
     if (tickets_) cudaFree(tickets_);
@@ -222,7 +185,8 @@ void DeviceBackend::free_state()
     if (stream_) cudaStreamDestroy(stream_);
     if (copy_stream_) cudaStreamDestroy(copy_stream_);
     pool_ = w_dev_ = xtol_abs_dev_ = partials_ = vsums_ = out_dev_ = xfull_dev_ = scalar_dev_ = nullptr;
-    tickets_ = nullptr;
+    tickets_ = group_tickets_ = nullptr;
+    grouprecs_ = nullptr;
     out_host_ = nullptr;
     flag_host_ = nullptr;
     h_x_ = nullptr;
@@ -246,10 +210,10 @@ bool DeviceBackend::alloc_state()
     } else {
         NB_CUDA(cudaGetDevice(&device_));
     }
-    geo_ = Geometry::make(geo_.n, comm.world, comm.rank, target_pairs_, pmax_);
+    geo_ = Geometry::make(geo_.n, comm.world, comm.rank, target_chunks_, pmax_);
     shard_cap_ = 0;
     for (int r = 0; r < comm.world; ++r) {
-        Geometry gr = Geometry::make(geo_.n, comm.world, r, target_pairs_, pmax_);
+        Geometry gr = Geometry::make(geo_.n, comm.world, r, target_chunks_, pmax_);
         if (gr.ld > shard_cap_) shard_cap_ = gr.ld;
     }
     if (m_ > (unsigned) kMaxParamM)
@@ -281,17 +245,27 @@ bool DeviceBackend::alloc_state()
 bool DeviceBackend::alloc_workspace()
 {
     if (partials_) { cudaFree(partials_); partials_ = nullptr; }
+    if (grouprecs_) { cudaFree(grouprecs_); grouprecs_ = nullptr; }
+    if (group_tickets_) { cudaFree(group_tickets_); group_tickets_ = nullptr; }
     if (vsums_) { cudaFree(vsums_); vsums_ = nullptr; }
-    nvp_ = 24;   // >= kMaxNV, keeps records 64-byte aligned
-    NB_CUDA(cudaMalloc(&partials_, (size_t) geo_.nseg_local * nvp_ * sizeof(double)));
-    NB_CUDA(cudaMalloc(&vsums_, (size_t) kV * nvp_ * sizeof(double)));
-    if (!out_dev_) NB_CUDA(cudaMalloc(&out_dev_, (size_t) kV * nvp_ * sizeof(double)));
+    {
+        const int maxm = pick_maxm((int) m_);
+        const int nv = 3 + (maxm > 0 ? maxm : 1);
+        nvp_ = (nv + 3) / 4 * 4;                  // records are multiples of 32 bytes
+    }
+    const size_t ng = geo_.nseg_local;
+    NB_CUDA(cudaMalloc(&partials_, ng * kGroupWarps * nvp_ * sizeof(double)));
+    NB_CUDA(cudaMalloc(&grouprecs_, ng * nvp_ * sizeof(double)));
+    NB_CUDA(cudaMalloc(&group_tickets_, ng * sizeof(unsigned)));
+    NB_CUDA(cudaMemsetAsync(group_tickets_, 0, ng * sizeof(unsigned), stream_));
+    NB_CUDA(cudaMalloc(&vsums_, (size_t) kV * 24 * sizeof(double)));
+    if (!out_dev_) NB_CUDA(cudaMalloc(&out_dev_, (size_t) kV * 24 * sizeof(double)));
     if (!tickets_) {
         NB_CUDA(cudaMalloc(&tickets_, (kV + 1) * sizeof(unsigned)));
         NB_CUDA(cudaMemsetAsync(tickets_, 0, (kV + 1) * sizeof(unsigned), stream_));
     }
     if (!out_host_) {
-        NB_CUDA(cudaHostAlloc(&out_host_, nvp_ * sizeof(double), cudaHostAllocMapped));
+        NB_CUDA(cudaHostAlloc(&out_host_, 24 * sizeof(double), cudaHostAllocMapped));
         NB_CUDA(cudaHostAlloc(&flag_host_, 64, cudaHostAllocMapped));
         *flag_host_ = 0;
     }
@@ -325,9 +299,20 @@ bool DeviceBackend::setup(const BackendConfig &cfg)
     if (!alloc_state()) return false;
     const size_t nl = geo_.n_local, j0 = geo_.j0;
     // bounds and start point
-    NB_CUDA(cudaMemcpyAsync(lb_, cfg.lb + j0, nl * sizeof(double), cudaMemcpyHostToDevice, stream_));
-    NB_CUDA(cudaMemcpyAsync(ub_, cfg.ub + j0, nl * sizeof(double), cudaMemcpyHostToDevice, stream_));
-    stats_->h2d_bytes += 2 * nl * sizeof(double);
+    if (cfg.lb_uniform) {
+        fill_kernel<<<grid_for(nl), kBlock, 0, stream_>>>(lb_, cfg.lb[0], nl);
+        ++stats_->kernel_launches;
+    } else {
+        NB_CUDA(cudaMemcpyAsync(lb_, cfg.lb + j0, nl * sizeof(double), cudaMemcpyHostToDevice, stream_));
+        stats_->h2d_bytes += nl * sizeof(double);
+    }
+    if (cfg.ub_uniform) {
+        fill_kernel<<<grid_for(nl), kBlock, 0, stream_>>>(ub_, cfg.ub[0], nl);
+        ++stats_->kernel_launches;
+    } else {
+        NB_CUDA(cudaMemcpyAsync(ub_, cfg.ub + j0, nl * sizeof(double), cudaMemcpyHostToDevice, stream_));
+        stats_->h2d_bytes += nl * sizeof(double);
+    }
     bool any_host_cb = cfg.objective.f != nullptr;
     for (const FuncSpec &c : cfg.constraints) any_host_cb = any_host_cb || c.f || c.mf;
     if (any_host_cb) {
@@ -418,7 +403,7 @@ bool DeviceBackend::host_x_for(Slot slot)
                                 cudaMemcpyDeviceToDevice, stream_));
         if (comm.all_gather_inplace(xfull_dev_, shard_cap_, stream_, &err_)) return false;
         for (int r = 0; r < comm.world; ++r) {
-            Geometry gr = Geometry::make(geo_.n, comm.world, r, target_pairs_, pmax_);
+            Geometry gr = Geometry::make(geo_.n, comm.world, r, target_chunks_, pmax_);
             NB_CUDA(cudaMemcpyAsync(h_x_ + gr.j0, xfull_dev_ + (size_t) r * shard_cap_, gr.n_local * sizeof(double),
                                     cudaMemcpyDeviceToHost, stream_));
         }
@@ -531,15 +516,16 @@ bool DeviceBackend::launch_dual(const double *y, const DualScalars &sc, bool sto
     a.x = x_; a.lb = lb_; a.ub = ub_; a.sigma = sigma_; a.g = g_; a.G = G_;
     a.xcur = xcur_;
     a.ld = geo_.ld;
-    a.npairs = geo_.npairs; a.pair0 = geo_.pair0;
+    a.nchunks = geo_.nchunks; a.chunk0 = geo_.chunk0;
     a.nseg_total = geo_.S; a.seg0 = geo_.seg0; a.segs_per_vshard = geo_.P; a.local_vshards = geo_.local_vshards;
-    a.partials = partials_; a.vsums = vsums_; a.tickets = tickets_; a.out_dev = out_dev_;
+    a.partials = partials_; a.grouprecs = grouprecs_; a.vsums = vsums_; a.group_tickets = group_tickets_;
+    a.tickets = tickets_; a.out_dev = out_dev_;
     a.out_host = out_host_; a.flag_host = flag_host_;
     a.seq = ++seq_;
     a.publish_host = Comm::instance().active() ? 0 : 1;
     a.nvp = nvp_;
     a.m = (int) m_;
-    a.chunk0 = chunk0; a.chunk_n = chunk_n;
+    a.cons0 = chunk0; a.cons_n = chunk_n;
     a.rho = sc.rho;
     a.half_rho = 0.5 * sc.rho;
     a.active = 0;
@@ -554,7 +540,6 @@ bool DeviceBackend::launch_dual(const double *y, const DualScalars &sc, bool sto
     a.u_ccsaq = u;
 
     const int maxm = pick_maxm((int) m_);
-    const int grid = (int) geo_.nseg_local;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (time_kernels_) {
         if (ev_used_ + 2 > ev_pool_.size()) {
@@ -566,22 +551,19 @@ bool DeviceBackend::launch_dual(const double *y, const DualScalars &sc, bool sto
         e1 = ev_pool_[ev_used_++];
         cudaEventRecord(e0, stream_);
     }
-    if (kernel_cfg_ >= 100) {
-        // persistent warp-granular kernel: grid sized to the machine, not to the problem
-        const int cfg = kernel_cfg_ - 100 < kNumWarpCfgs ? kernel_cfg_ - 100 : 0;
-        const KernelCfg c = kWarpCfgs[cfg];
-        DualKernel fn = variant_ == kMMA ? pick_warp_kernel<0>(maxm, cfg, store) : pick_warp_kernel<1>(maxm, cfg, store);
-        const int warps = c.block / 32;
-        long long want = ((long long) geo_.nseg_local + warps - 1) / warps;
-        long long cap = (long long) sm_count_ * (ctas_per_sm_ > 0 ? ctas_per_sm_ : c.minb);
+    {
+        // persistent kernel: the grid is sized to the machine, not to the problem
+        int cfg = kernel_cfg_ >= 0 && kernel_cfg_ < kNumCfgs ? kernel_cfg_ : default_cfg(variant_, maxm);
+        if (maxm >= 8) cfg = 3;
+        const KernelCfg c = kCfgs[cfg];
+        const bool full = (int) m_ == maxm && (variant_ == kCCSAQ || a.active == (m_ >= 32 ? 0xffffffffu : ((1u << m_) - 1u)));
+        DualKernel fn = variant_ == kMMA ? (full ? pick_kernel<0, true>(maxm, cfg, store) : pick_kernel<0, false>(maxm, cfg, store))
+                                         : (full ? pick_kernel<1, true>(maxm, cfg, store) : pick_kernel<1, false>(maxm, cfg, store));
+        const int slots = c.block / (32 * kGroupWarps);
+        const long long want = ((long long) geo_.nseg_local + slots - 1) / slots;
+        const long long cap = (long long) sm_count_ * (ctas_per_sm_ > 0 ? ctas_per_sm_ : 4 * c.minb);
         const int pgrid = (int) (want < cap ? want : cap);
         fn<<<pgrid < 1 ? 1 : pgrid, c.block, 0, stream_>>>(a);
-    } else {
-        const int cfg = kernel_cfg_ >= 0 && kernel_cfg_ < kNumCfgs ? kernel_cfg_ : 0;
-        DualKernel fn = variant_ == kMMA ? pick_kernel<0>(maxm, cfg, store) : pick_kernel<1>(maxm, cfg, store);
-        const int block = (maxm == 4 || (maxm == 1 && (cfg == 1 || cfg == 2)) || (maxm == 16 && (cfg == 2 || cfg == 5 || cfg == 9)))
-                              ? kCfgs[cfg].block : kCfgs[0].block;
-        fn<<<grid, block, 0, stream_>>>(a);
     }
     if (time_kernels_) cudaEventRecord(e1, stream_);
     ++stats_->kernel_launches;
@@ -675,7 +657,7 @@ bool DeviceBackend::end_outer(unsigned k, double sigma_min, double *dnorm, doubl
     a.xcur = xcur_view();
     a.xprev = xprev_; a.xprevprev = xprevprev_; a.sigma = sigma_;
     a.lb = lb_; a.ub = ub_; a.w = w_dev_; a.xtol_abs = xtol_abs_dev_;
-    a.n_local = geo_.n_local; a.npairs = geo_.npairs; a.pair0 = geo_.pair0;
+    a.n_local = geo_.n_local; a.nchunks = geo_.nchunks; a.chunk0 = geo_.chunk0;
     a.nseg_total = geo_.S; a.seg0 = geo_.seg0; a.segs_per_vshard = geo_.P; a.local_vshards = geo_.local_vshards;
     a.partials = partials_; a.vsums = vsums_; a.tickets = tickets_; a.out_dev = out_dev_;
     a.out_host = out_host_; a.flag_host = flag_host_;
@@ -796,11 +778,11 @@ bool DeviceBackend::configure(const char *key, long long value)
     if (k == "time_kernels") { time_kernels_ = value != 0; return true; }
     if (k == "kernel_cfg") { kernel_cfg_ = (int) value; return true; }
     if (k == "ctas_per_sm") { ctas_per_sm_ = (int) value; return true; }
-    if (k == "pmax" || k == "target_pairs") {
+    if (k == "pmax" || k == "target_chunks") {
         if (value < 1) return fail("bad value");
-        if (k == "pmax") pmax_ = (unsigned) value; else target_pairs_ = (unsigned) value;
+        if (k == "pmax") pmax_ = (unsigned) value; else target_chunks_ = (unsigned) value;
         if (pool_) {
-            Geometry g2 = Geometry::make(geo_.n, geo_.world, geo_.rank, target_pairs_, pmax_);
+            Geometry g2 = Geometry::make(geo_.n, geo_.world, geo_.rank, target_chunks_, pmax_);
             if (g2.ld != geo_.ld || g2.j0 != geo_.j0)
                 return fail("changing the segment geometry of a sharded, allocated problem is not supported");
             geo_ = g2;
@@ -982,7 +964,7 @@ long long nlopt_b200_dual_query(nlopt_b200_dual h, const char *key) { return h->
 
 void nlopt_b200_shard_range(unsigned long long n, int rank, int world, unsigned long long *j0, unsigned long long *count)
 {
-    nb200::Geometry g = nb200::Geometry::make(n, world, rank, nb200::kDefaultTargetPairs, nb200::kDefaultPmax);
+    nb200::Geometry g = nb200::Geometry::make(n, world, rank, nb200::kDefaultTargetChunks, nb200::kDefaultPmax);
     *j0 = g.j0;
     *count = g.n_local;
 }

@@ -70,10 +70,10 @@ private:
     Variant variant_ = kMMA;
     unsigned m_ = 0;
     Geometry geo_;
-    unsigned target_pairs_ = kDefaultTargetPairs, pmax_ = kDefaultPmax;
+    unsigned target_chunks_ = kDefaultTargetChunks, pmax_ = kDefaultPmax;
     int device_ = 0;
     int sm_count_ = 148, ctas_per_sm_ = 0;
-    int kernel_cfg_ = 0;          // index into the launch-geometry table of device_backend.cu
+    int kernel_cfg_ = -1;         // -1: measured default for (variant, m)          // index into the launch-geometry table of device_backend.cu
 
     // device state
     double *pool_ = nullptr;
@@ -85,8 +85,8 @@ private:
     bool bounds_set_ = false;
 
     // reduction workspace + result mailbox
-    double *partials_ = nullptr, *vsums_ = nullptr, *out_dev_ = nullptr;
-    unsigned *tickets_ = nullptr;
+    double *partials_ = nullptr, *grouprecs_ = nullptr, *vsums_ = nullptr, *out_dev_ = nullptr;
+    unsigned *tickets_ = nullptr, *group_tickets_ = nullptr;
     double *out_host_ = nullptr;                     // mapped pinned
     unsigned long long *flag_host_ = nullptr;        // mapped pinned
     unsigned long long seq_ = 0;

@@ -356,6 +356,7 @@ nlopt_result nlopt_set_lower_bounds(nlopt_opt opt, const double *lb)
     if (!opt || (opt->n > 0 && !lb)) return NLOPT_INVALID_ARGS;
     for (unsigned i = 0; i < opt->n; ++i) opt->lb[i] = lb[i];
     for (unsigned i = 0; i < opt->n; ++i) snap_lower(opt, i);
+    opt->lb_uniform = false;
     return NLOPT_SUCCESS;
 }
 
@@ -364,6 +365,8 @@ nlopt_result nlopt_set_lower_bounds1(nlopt_opt opt, double lb)
     clear_err(opt);
     if (!opt) return NLOPT_INVALID_ARGS;
     for (unsigned i = 0; i < opt->n; ++i) { opt->lb[i] = lb; snap_lower(opt, i); }
+    opt->lb_uniform = true;
+    for (unsigned i = 1; i < opt->n && opt->lb_uniform; ++i) opt->lb_uniform = opt->lb[i] == opt->lb[0];   // snapping may differ
     return NLOPT_SUCCESS;
 }
 
@@ -374,6 +377,7 @@ nlopt_result nlopt_set_lower_bound(nlopt_opt opt, int i, double lb)
     if (i < 0 || i >= (int) opt->n) { set_err(opt, "invalid bound index"); return NLOPT_INVALID_ARGS; }
     opt->lb[i] = lb;
     snap_lower(opt, i);
+    opt->lb_uniform = false;
     return NLOPT_SUCCESS;
 }
 
@@ -391,6 +395,7 @@ nlopt_result nlopt_set_upper_bounds(nlopt_opt opt, const double *ub)
     if (!opt || (opt->n > 0 && !ub)) return NLOPT_INVALID_ARGS;
     for (unsigned i = 0; i < opt->n; ++i) opt->ub[i] = ub[i];
     for (unsigned i = 0; i < opt->n; ++i) snap_upper(opt, i);
+    opt->ub_uniform = false;
     return NLOPT_SUCCESS;
 }
 
@@ -399,6 +404,8 @@ nlopt_result nlopt_set_upper_bounds1(nlopt_opt opt, double ub)
     clear_err(opt);
     if (!opt) return NLOPT_INVALID_ARGS;
     for (unsigned i = 0; i < opt->n; ++i) { opt->ub[i] = ub; snap_upper(opt, i); }
+    opt->ub_uniform = true;
+    for (unsigned i = 1; i < opt->n && opt->ub_uniform; ++i) opt->ub_uniform = opt->ub[i] == opt->ub[0];
     return NLOPT_SUCCESS;
 }
 
@@ -409,6 +416,7 @@ nlopt_result nlopt_set_upper_bound(nlopt_opt opt, int i, double ub)
     if (i < 0 || i >= (int) opt->n) { set_err(opt, "invalid bound index"); return NLOPT_INVALID_ARGS; }
     opt->ub[i] = ub;
     snap_upper(opt, i);
+    opt->ub_uniform = false;
     return NLOPT_SUCCESS;
 }
 
@@ -811,6 +819,8 @@ nlopt_result run_ccsa(nlopt_opt opt, double *x_host, double *x_dev, double *minf
     }
     cfg.lb = opt->lb.data();
     cfg.ub = opt->ub.data();
+    cfg.lb_uniform = opt->lb_uniform && n > 0;
+    cfg.ub_uniform = opt->ub_uniform && n > 0;
     cfg.x0_host = x_host;
     cfg.x_dev = x_dev;
     cfg.sigma_init = opt->has_dx ? opt->dx.data() : nullptr;
@@ -830,8 +840,10 @@ nlopt_result run_ccsa(nlopt_opt opt, double *x_host, double *x_dev, double *minf
     /* library-specific knobs ride on the named-parameter mechanism (no ABI change) */
     if (nlopt_get_param(opt, "b200_time_kernels", 0.0) != 0.0) be->configure("time_kernels", 1);
     if (nlopt_has_param(opt, "b200_pmax")) be->configure("pmax", (long long) nlopt_get_param(opt, "b200_pmax", 0.0));
-    if (nlopt_has_param(opt, "b200_target_pairs"))
-        be->configure("target_pairs", (long long) nlopt_get_param(opt, "b200_target_pairs", 0.0));
+    if (nlopt_has_param(opt, "b200_target_chunks"))
+        be->configure("target_chunks", (long long) nlopt_get_param(opt, "b200_target_chunks", 0.0));
+    if (nlopt_has_param(opt, "b200_kernel_cfg")) be->configure("kernel_cfg", (long long) nlopt_get_param(opt, "b200_kernel_cfg", 0.0));
+    if (nlopt_has_param(opt, "b200_ctas_per_sm")) be->configure("ctas_per_sm", (long long) nlopt_get_param(opt, "b200_ctas_per_sm", 0.0));
 
     nb200::StopCriteria st;                          /* optimize.c:553-566 */
     st.minf_max = opt->stopval;

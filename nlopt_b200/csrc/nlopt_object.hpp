@@ -41,6 +41,7 @@ struct nlopt_opt_s {
     std::vector<nb200::NamedParam *> params;      // pointers stay valid: nlopt_nth_param hands out c_str()
 
     std::vector<double> lb, ub;
+    bool lb_uniform = true, ub_uniform = true;   // every entry equal (set by nlopt_set_*_bounds1): filled on device
     std::vector<nb200::ConstraintRec> fc, h;      // inequality / equality constraint objects
     nlopt_munge munge_on_destroy = nullptr, munge_on_copy = nullptr;
 

@@ -26,7 +26,7 @@ def main():
     rows = []
     ns = [10**7] if quick else [10**3, 10**4, 10**5, 10**6, 10**7, 10**8]
     ms = [4] if quick else [1, 4, 16]
-    pmaxes = [74, 148, 296, 592, 1184] if "--geometry" in sys.argv else [None]
+    pmaxes = [None]
     for n in ns:
         for m in ms:
             if 8 * n * (9 + 2 * m) > 150e9:
