@@ -81,6 +81,9 @@ struct DualArgs {
     unsigned long long seq;
     int publish_host;             // 1: single rank, results + flag go straight to the host
     int nvp;                      // stride of one record (>= 3 + chunk size)
+    // fused cross-rank exchange over NVLink peer memory (null box[0]: NCCL path instead)
+    double *box[8];               // box[r]: rank r's mailbox as mapped into this process (CUDA IPC)
+    int rank, world;
     // the multipliers and penalties
     int m;                        // total number of constraints (rows of G)
     int cons0, cons_n;            // this launch accumulates g_i for i in [cons0, cons0 + cons_n)
@@ -367,16 +370,52 @@ __global__ void __launch_bounds__(BLOCK, MINB) dual_eval_kernel(const __grid_con
                 for (unsigned v = 1; v < a.local_vshards; ++v) s = addx(s, __ldcg(a.vsums + (unsigned long long) v * a.nvp + lane));
                 a.out_host[lane] = s;
                 __threadfence_system();
-            } else {
+            } else if (a.box[0] == nullptr) {
                 const unsigned v0 = a.seg0 / a.segs_per_vshard;
                 for (unsigned v = 0; v < a.local_vshards; ++v)
                     a.out_dev[(unsigned long long) (v0 + v) * a.nvp + lane] = __ldcg(a.vsums + (unsigned long long) v * a.nvp + lane);
             }
         }
+        if (!a.publish_host && a.box[0] != nullptr) {
+            // ---- all-gather fused into the kernel: NVLink peer stores + flags (comm.hpp layout) ----
+            constexpr int kStride = 24, kFlagOff = 2 * 8 * kStride;
+            const int buf = (int) (a.seq & 1ull);
+            const unsigned v0 = a.seg0 / a.segs_per_vshard;
+            if (lane < NV)
+                for (int r = 0; r < a.world; ++r)
+                    for (unsigned v = 0; v < a.local_vshards; ++v) {
+                        volatile double *dst = a.box[r] + ((unsigned long long) buf * 8 + v0 + v) * kStride + lane;
+                        *dst = __ldcg(a.vsums + (unsigned long long) v * a.nvp + lane);
+                    }
+            __threadfence_system();
+            __syncwarp();
+            if (lane < a.world) {       // lane r raises this rank's flag in rank r's mailbox
+                volatile unsigned long long *f =
+                    reinterpret_cast<volatile unsigned long long *>(a.box[lane] + kFlagOff) + buf * 8 + a.rank;
+                *f = a.seq;
+            }
+            int timed_out = 0;
+            if (lane < a.world) {       // ... and waits for rank `lane`'s flag in our own mailbox
+                volatile unsigned long long *f =
+                    reinterpret_cast<volatile unsigned long long *>(a.box[a.rank] + kFlagOff) + buf * 8 + lane;
+                const long long t0 = clock64();
+                while (*f != a.seq)
+                    if (clock64() - t0 > 20000000000ll) { timed_out = 1; break; }      // ~10 s: a peer died
+            }
+            timed_out = __any_sync(0xffffffffu, timed_out);
+            __threadfence_system();
+            if (lane < NV) {            // fold the 8 shard records in index order, exactly like one rank does
+                volatile double *rec = a.box[a.rank] + (unsigned long long) buf * 8 * kStride + lane;
+                double s = rec[0];
+                for (int v = 1; v < kVirtualShards; ++v) s = addx(s, rec[v * kStride]);
+                a.out_host[lane] = timed_out ? __longlong_as_double(0x7ff8000000000000ll) : s;
+                __threadfence_system();
+            }
+        }
         __syncwarp();
         if (lane == 0) {
             for (unsigned v = 0; v <= a.local_vshards; ++v) a.tickets[v] = 0;    // ready for the next launch
-            if (a.publish_host) {
+            if (a.publish_host || a.box[0] != nullptr) {
                 *a.flag_host = a.seq;
                 __threadfence_system();
             }

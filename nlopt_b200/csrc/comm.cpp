@@ -5,6 +5,7 @@
 #include <dlfcn.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "../../include/nlopt_b200.h"
@@ -89,11 +90,71 @@ int Comm::init(const unsigned char id[128], int r, int w, int dev, std::string *
     std::memcpy(nid.internal, id, 128);
     int rc = api().init_rank(&comm_, w, nid, r);
     if (rc) { comm_ = nullptr; world = 1; rank = 0; if (err) *err = nccl_msg("ncclCommInitRank", rc); return -1; }
+    const char *ex = std::getenv("NLOPT_B200_EXCHANGE");
+    force_nccl_ = ex && std::strcmp(ex, "nccl") == 0;
+    std::string perr;
+    if (setup_p2p(&perr) != 0) {
+        std::fprintf(stderr, "nlopt_b200: peer mailboxes unavailable (%s); using NCCL all-gather per dual evaluation\n",
+                     perr.c_str());
+        teardown_p2p();
+    }
     return 0;
+}
+
+// Allocate this rank's mailbox, all-gather the CUDA IPC handles over NCCL, map every peer's mailbox.
+int Comm::setup_p2p(std::string *err)
+{
+    p2p_ready = false;
+    if (cudaMalloc(&box_local_, kBoxDoubles * sizeof(double)) != cudaSuccess) { *err = "cudaMalloc mailbox"; return -1; }
+    cudaMemset(box_local_, 0, kBoxDoubles * sizeof(double));
+    cudaIpcMemHandle_t mine;
+    if (cudaIpcGetMemHandle(&mine, box_local_) != cudaSuccess) { *err = "cudaIpcGetMemHandle"; cudaGetLastError(); return -1; }
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle is 64 bytes");
+    double *stage = nullptr;
+    const size_t per = sizeof(cudaIpcMemHandle_t) / sizeof(double);
+    if (cudaMalloc(&stage, (size_t) world * sizeof(cudaIpcMemHandle_t)) != cudaSuccess) { *err = "cudaMalloc stage"; return -1; }
+    cudaMemcpy(stage + (size_t) rank * per, &mine, sizeof mine, cudaMemcpyHostToDevice);
+    std::string e2;
+    if (all_gather_inplace(stage, per, 0, &e2) != 0) { *err = e2; cudaFree(stage); return -1; }
+    cudaStreamSynchronize(0);
+    cudaIpcMemHandle_t all[8];
+    cudaMemcpy(all, stage, (size_t) world * sizeof(cudaIpcMemHandle_t), cudaMemcpyDeviceToHost);
+    cudaFree(stage);
+    for (int r = 0; r < world; ++r) {
+        if (r == rank) { box_peer[r] = box_local_; continue; }
+        void *p = nullptr;
+        cudaError_t ce = cudaIpcOpenMemHandle(&p, all[r], cudaIpcMemLazyEnablePeerAccess);
+        if (ce != cudaSuccess) { *err = std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(ce); cudaGetLastError(); return -1; }
+        box_peer[r] = (double *) p;
+    }
+    // nobody may start writing before everyone has mapped and zeroed: one tiny all-reduce as a barrier
+    double *one = nullptr;
+    cudaMalloc(&one, sizeof(double));
+    cudaMemset(one, 0, sizeof(double));
+    all_reduce_sum(one, 1, 0, &e2);
+    cudaStreamSynchronize(0);
+    cudaFree(one);
+    p2p_ready = true;
+    return 0;
+}
+
+void Comm::teardown_p2p()
+{
+    for (int r = 0; r < 8; ++r) {
+        if (box_peer[r] && box_peer[r] != box_local_) cudaIpcCloseMemHandle(box_peer[r]);
+        box_peer[r] = nullptr;
+    }
+    if (box_local_) cudaFree(box_local_);
+    box_local_ = nullptr;
+    p2p_ready = false;
 }
 
 int Comm::finalize()
 {
+    if (comm_) {
+        cudaDeviceSynchronize();
+        teardown_p2p();
+    }
     if (comm_) api().destroy(comm_);
     comm_ = nullptr;
     rank = 0; world = 1;

@@ -22,11 +22,27 @@ struct Comm {
     int init(const unsigned char id[128], int rank, int world, int device, std::string *err);
     int finalize();
 
+    // Fused exchange: every rank owns a small mailbox in its HBM that all peers map through CUDA IPC
+    // (NVLink peer stores).  The dual kernel's last warp writes this rank's shard sums straight into
+    // every peer's mailbox, raises a per-rank flag and spins until all peers' flags for this sequence
+    // number arrive -- the all-gather happens inside the kernel, no NCCL call, no second launch.
+    // Layout (doubles): [2 buffers][8 virtual shards][kBoxStride] | flags: [2 buffers][8 ranks] (u64).
+    static constexpr int kBoxStride = 24;
+    static constexpr int kBoxFlagOffset = 2 * 8 * kBoxStride;          // in doubles
+    static constexpr int kBoxDoubles = kBoxFlagOffset + 2 * 8;
+    double *box_peer[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    bool p2p_ready = false;
+    bool use_p2p() const { return p2p_ready && !force_nccl_; }
+
     // collectives on a stream; return 0 on success
     int all_gather_inplace(double *buf, size_t count_per_rank, cudaStream_t s, std::string *err);
     int all_reduce_sum(double *buf, size_t count, cudaStream_t s, std::string *err);
 
 private:
+    int setup_p2p(std::string *err);
+    void teardown_p2p();
+    double *box_local_ = nullptr;
+    bool force_nccl_ = false;
     void *handle_ = nullptr;   // dlopen handle
     void *comm_ = nullptr;     // ncclComm_t
 };

@@ -524,6 +524,12 @@ bool DeviceBackend::launch_dual(const double *y, const DualScalars &sc, bool sto
     a.seq = ++seq_;
     a.publish_host = Comm::instance().active() ? 0 : 1;
     a.nvp = nvp_;
+    {
+        Comm &cm = Comm::instance();
+        a.rank = cm.rank;
+        a.world = cm.world;
+        for (int r = 0; r < 8; ++r) a.box[r] = (cm.active() && cm.use_p2p() && r < cm.world) ? cm.box_peer[r] : nullptr;
+    }
     a.m = (int) m_;
     a.cons0 = chunk0; a.cons_n = chunk_n;
     a.rho = sc.rho;
@@ -568,7 +574,7 @@ bool DeviceBackend::launch_dual(const double *y, const DualScalars &sc, bool sto
     if (time_kernels_) cudaEventRecord(e1, stream_);
     ++stats_->kernel_launches;
     NB_CUDA(cudaGetLastError());
-    if (!a.publish_host) {
+    if (!a.publish_host && a.box[0] == nullptr) {
         const int nv = 3 + (maxm > 0 ? maxm : 1);
         if (Comm::instance().all_gather_inplace(out_dev_, (size_t) geo_.local_vshards * nvp_, stream_, &err_)) return false;
         publish_kernel<<<1, 32, 0, stream_>>>(out_dev_, nv, nvp_, out_host_, flag_host_, a.seq);
@@ -587,6 +593,8 @@ bool DeviceBackend::dual_eval(const double *y, const DualScalars &sc, bool mater
     do {
         const int cn = (int) m_ - c0 < step ? (int) m_ - c0 : step;
         if (!launch_dual(y, sc, materialize && c0 == 0, c0, cn, true)) return false;
+        if (Comm::instance().active() && std::isnan(out_host_[0]) && std::isnan(out_host_[1]) && std::isnan(out_host_[2]))
+            return fail("the cross-rank exchange of the dual sums timed out or produced NaN (is every rank running the same calls?)");
         if (c0 == 0) {
             out->val = out_host_[0];
             out->gval = out_host_[1];
