@@ -70,10 +70,8 @@ struct DualArgs {
     unsigned segs_per_vshard;     // P
     unsigned local_vshards;       // 8 / world
     // reduction workspace
-    double *partials;             // [local groups * 8][nvp]   warp records
     double *grouprecs;            // [local groups][nvp]       group records
     double *vsums;                // [local_vshards][nvp]
-    unsigned *group_tickets;      // [local groups], zero between launches
     unsigned *tickets;            // [local_vshards + 1], zero between launches
     double *out_dev;              // [8][nvp] all-rank exchange buffer (this rank's slots filled)
     volatile double *out_host;    // mapped pinned [nvp]; written when publish_host
@@ -230,9 +228,10 @@ __device__ __forceinline__ double ccsaq_point(const DualArgs &a, double x, doubl
 // Persistent CTAs (grid sized to the machine).  A *group* is a contiguous run of 512-variable chunks;
 // the 8 warps of a group slot sweep it together -- sweep step t reads one 4 KB-contiguous chunk per array,
 // warp w taking lanes [32w, 32w+32) of it -- but every warp keeps its OWN m+3 accumulators over the group
-// and folds them with a fixed xor-butterfly into a warp record.  No shared memory and no block barrier
-// on the streaming path.  Fold tree (all in fixed order, all un-fused adds):
-//   warp record -> group record (8 warp records, by the warp that completes the group)
+// and folds them with a fixed xor-butterfly into a warp record.  The streaming loop has no barrier; one
+// slot barrier per group hands the 8 warp records to warp 0 through shared memory.
+// Fold tree (all in fixed order, all un-fused adds):
+//   warp record -> group record (8 warp records in warp order, by warp 0 of the slot)
 //               -> virtual-shard sum (P group records, by the warp that completes the shard)
 //               -> rank sum / exchange buffer (8/world shard sums, by the warp that completes the rank).
 // A record depends only on n (the cuts) -- never on the grid size, on which CTA swept the group or on the
@@ -269,6 +268,8 @@ __global__ void __launch_bounds__(BLOCK, MINB) dual_eval_kernel(const __grid_con
     const unsigned slot = blockIdx.x * SLOTS + (threadIdx.x >> 5) / kGroupWarps;
     const unsigned nslots = gridDim.x * SLOTS;
     const unsigned ngroups = a.segs_per_vshard * a.local_vshards;
+    __shared__ double s_rec[SLOTS][2][kGroupWarps * NV];
+    int parity = 0;
 
     const double2 *x2 = reinterpret_cast<const double2 *>(a.x);
     const double2 *lb2 = reinterpret_cast<const double2 *>(a.lb);
@@ -325,23 +326,25 @@ __global__ void __launch_bounds__(BLOCK, MINB) dual_eval_kernel(const __grid_con
             }
         }
 
-        // warp record
+        // warp record -> shared memory; group record = the 8 warp records added in warp order by warp 0 of
+        // the slot.  One slot barrier per group; the record buffer is double-buffered across iterations so
+        // the next group's writers can never overtake this group's reader.
         warp_fold<NV>(acc);
+        double *srec = s_rec[(threadIdx.x >> 5) / kGroupWarps][parity];
         if (lane == 0) {
-            double *rec = a.partials + ((unsigned long long) gl * kGroupWarps + sub) * a.nvp;
 #pragma unroll
-            for (int k = 0; k < NV; ++k) rec[k] = acc[k];
+            for (int k = 0; k < NV; ++k) srec[sub * NV + k] = acc[k];
         }
-        // group record, by the warp that completes the group
-        if (!warp_is_last(a.group_tickets + gl, kGroupWarps, lane)) continue;
+        if (SLOTS == 1) __syncthreads();
+        else asm volatile("bar.sync %0, %1;" ::"r"((int) ((threadIdx.x >> 5) / kGroupWarps) + 1), "r"(32 * kGroupWarps) : "memory");
+        parity ^= 1;
+        if (sub != 0) continue;
         if (lane < NV) {
-            const double *rec = a.partials + (unsigned long long) gl * kGroupWarps * a.nvp + lane;
-            double s = __ldcg(rec);
+            double s = srec[lane];
 #pragma unroll
-            for (int w = 1; w < kGroupWarps; ++w) s = addx(s, __ldcg(rec + (unsigned long long) w * a.nvp));
+            for (int w = 1; w < kGroupWarps; ++w) s = addx(s, srec[w * NV + lane]);
             a.grouprecs[(unsigned long long) gl * a.nvp + lane] = s;
         }
-        if (lane == 0) a.group_tickets[gl] = 0;
         __syncwarp();
 
         // virtual-shard sum, by the warp that completes the shard

@@ -83,6 +83,7 @@ int Comm::init(const unsigned char id[128], int r, int w, int dev, std::string *
     }
     if (comm_) finalize();
     rank = r; world = w; device = dev;
+    seq_counter_ = 0;
     if (w == 1) return 0;
     if (!load(err)) return -1;
     if (cudaSetDevice(dev) != cudaSuccess) { if (err) *err = "cudaSetDevice failed"; return -1; }

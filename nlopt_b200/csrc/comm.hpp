@@ -33,6 +33,10 @@ struct Comm {
     double *box_peer[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     bool p2p_ready = false;
     bool use_p2p() const { return p2p_ready && !force_nccl_; }
+    // Mailbox flags carry a launch sequence number.  The mailbox is shared by every solver object of the
+    // process, so the number is process-wide; all ranks issue the same launches in the same order, which
+    // keeps the counters of all ranks in lockstep.
+    unsigned long long next_seq() { return ++seq_counter_; }
 
     // collectives on a stream; return 0 on success
     int all_gather_inplace(double *buf, size_t count_per_rank, cudaStream_t s, std::string *err);
@@ -42,6 +46,7 @@ private:
     int setup_p2p(std::string *err);
     void teardown_p2p();
     double *box_local_ = nullptr;
+    unsigned long long seq_counter_ = 0;
     bool force_nccl_ = false;
     void *handle_ = nullptr;   // dlopen handle
     void *comm_ = nullptr;     // ncclComm_t

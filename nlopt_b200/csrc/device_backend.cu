@@ -254,10 +254,8 @@ bool DeviceBackend::alloc_workspace()
         nvp_ = (nv + 3) / 4 * 4;                  // records are multiples of 32 bytes
     }
     const size_t ng = geo_.nseg_local;
-    NB_CUDA(cudaMalloc(&partials_, ng * kGroupWarps * nvp_ * sizeof(double)));
+    NB_CUDA(cudaMalloc(&partials_, ng * nvp_ * sizeof(double)));   // end_outer_kernel: one record per group
     NB_CUDA(cudaMalloc(&grouprecs_, ng * nvp_ * sizeof(double)));
-    NB_CUDA(cudaMalloc(&group_tickets_, ng * sizeof(unsigned)));
-    NB_CUDA(cudaMemsetAsync(group_tickets_, 0, ng * sizeof(unsigned), stream_));
     NB_CUDA(cudaMalloc(&vsums_, (size_t) kV * 24 * sizeof(double)));
     if (!out_dev_) NB_CUDA(cudaMalloc(&out_dev_, (size_t) kV * 24 * sizeof(double)));
     if (!tickets_) {
@@ -518,10 +516,10 @@ bool DeviceBackend::launch_dual(const double *y, const DualScalars &sc, bool sto
     a.ld = geo_.ld;
     a.nchunks = geo_.nchunks; a.chunk0 = geo_.chunk0;
     a.nseg_total = geo_.S; a.seg0 = geo_.seg0; a.segs_per_vshard = geo_.P; a.local_vshards = geo_.local_vshards;
-    a.partials = partials_; a.grouprecs = grouprecs_; a.vsums = vsums_; a.group_tickets = group_tickets_;
+    a.grouprecs = grouprecs_; a.vsums = vsums_;
     a.tickets = tickets_; a.out_dev = out_dev_;
     a.out_host = out_host_; a.flag_host = flag_host_;
-    a.seq = ++seq_;
+    a.seq = seq_ = Comm::instance().active() ? Comm::instance().next_seq() : seq_ + 1;
     a.publish_host = Comm::instance().active() ? 0 : 1;
     a.nvp = nvp_;
     {
@@ -669,7 +667,7 @@ bool DeviceBackend::end_outer(unsigned k, double sigma_min, double *dnorm, doubl
     a.nseg_total = geo_.S; a.seg0 = geo_.seg0; a.segs_per_vshard = geo_.P; a.local_vshards = geo_.local_vshards;
     a.partials = partials_; a.vsums = vsums_; a.tickets = tickets_; a.out_dev = out_dev_;
     a.out_host = out_host_; a.flag_host = flag_host_;
-    a.seq = ++seq_;
+    a.seq = seq_ = Comm::instance().active() ? Comm::instance().next_seq() : seq_ + 1;
     a.publish_host = Comm::instance().active() ? 0 : 1;
     a.nvp = nvp_;
     a.update_sigma = k > 1;
