@@ -74,7 +74,7 @@ DualKernel pick_kernel(int maxm, int cfg, bool store)
 int default_cfg(Variant v, int maxm)
 {
     if (maxm >= 8) return 3;
-    if (maxm == 4) return 0;
+    if (maxm == 4) return v == kMMA ? 0 : 1;
     return v == kMMA ? 1 : 2;
 }
 
