@@ -59,6 +59,19 @@ public:
     // materialize == true also stores x*(y) into xcur.
     virtual bool dual_eval(const double *y, const DualScalars &sc, bool materialize, DualSums *out) = 0;
 
+    // Optional: the whole dual solve (mma.c:275-288: optimise y in [lo, hi] from the warm start, then
+    // the final evaluation that materialises x*(y)) as ONE device-side operation.  `stop6` =
+    // {ftol_rel, ftol_abs, xtol_rel, xtol_abs, maxeval, maxtime}.  On success y holds the solution, `out`
+    // the raw sums at it, *ret the dual optimiser's nlopt_result, *nevals its evaluation count (the final
+    // evaluation not included).  Backends without it return false from supports_dual_solve().
+    virtual bool supports_dual_solve() const { return false; }
+    virtual bool dual_solve(double *y, const double *lo, const double *hi, const double *stop6, const DualScalars &sc,
+                            DualSums *out, int *ret, long *nevals)
+    {
+        (void) y; (void) lo; (void) hi; (void) stop6; (void) sc; (void) out; (void) ret; (void) nevals;
+        return false;
+    }
+
     // x <- xcur, gradients <- candidate gradients (mma.c:374-377); O(1) buffer swaps
     virtual void accept_candidate() = 0;
 

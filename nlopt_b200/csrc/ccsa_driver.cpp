@@ -114,11 +114,8 @@ int ccsa_minimize(Variant variant, Backend &be, const std::vector<double> &tol, 
     raw.gc = sums.data();
     double g0 = 0, w = 0;            // approximant values at the latest x*(y)
     long long launches = 0;
-    auto dual_value = [&](const double *yy, double *grad, bool materialize, bool *ok) -> double {
-        sc.fval = fbase;
-        sc.rho = rho;
-        if (!be.dual_eval(yy, sc, materialize, &raw)) { *ok = false; return 0.0; }
-        ++launches;
+    // the O(m) constants around the n-term sums of one evaluation, in the reference's order
+    auto assemble = [&](const double *yy, double *grad) -> double {
         double val = fbase;                                    // mma.c:75-78
         for (unsigned i = 0; i < m; ++i) {
             const double ci = L.off(c[i]) ? 0.0 : c[i];
@@ -132,6 +129,14 @@ int ccsa_minimize(Variant variant, Backend &be, const std::vector<double> &tol, 
             for (unsigned i = 0; i < m; ++i) grad[i] = -gc[i];  // mma.c:135
         return -val;
     };
+    auto dual_value = [&](const double *yy, double *grad, bool materialize, bool *ok) -> double {
+        sc.fval = fbase;
+        sc.rho = rho;
+        if (!be.dual_eval(yy, sc, materialize, &raw)) { *ok = false; return 0.0; }
+        ++launches;
+        return assemble(yy, grad);
+    };
+    const bool fused = prm.fused_solve && m > 0 && be.supports_dual_solve();
 
     if (!be.first_outer()) return L.fail("state rotation");
     unsigned k = 0;
@@ -146,7 +151,23 @@ int ccsa_minimize(Variant variant, Backend &be, const std::vector<double> &tol, 
             // dual solve, warm-started from the previous multipliers (mma.c:275-288)
             launches = 0;
             bool ok = true;
-            if (m > 0) {
+            if (fused) {
+                // the whole dual solve + final evaluation as one persistent kernel
+                const double stop6[6] = {prm.dual_ftol_rel, prm.dual_ftol_abs, prm.dual_xtol_rel, prm.dual_xtol_abs,
+                                         (double) prm.dual_maxeval, stop.maxtime - (wall_seconds() - L.start)};
+                sc.fval = fbase;
+                sc.rho = rho;
+                int reti = 0;
+                long dn = 0;
+                if (!be.dual_solve(y.data(), ylo.data(), yhi.data(), stop6, sc, &raw, &reti, &dn)) return L.fail("dual solve");
+                if (reti < 0 || reti == R_MAXTIME) {              // mma.c:283-286
+                    if (reti == kRetInvalid && errmsg) *errmsg = "dual variables left their box";
+                    if (reti == kRetFailure) return L.fail("dual solve");
+                    return reti;
+                }
+                launches = dn + 1;
+                assemble(y.data(), nullptr);
+            } else if (m > 0) {
                 DualStop ds;
                 ds.ftol_rel = prm.dual_ftol_rel;
                 ds.ftol_abs = prm.dual_ftol_abs;
@@ -165,8 +186,10 @@ int ccsa_minimize(Variant variant, Backend &be, const std::vector<double> &tol, 
                     return reti;
                 }
             }
-            dual_value(y.data(), nullptr, true, &ok);             // mma.c:288: x*(y), g, w at the solution
-            if (!ok) return L.fail("dual evaluation");
+            if (!fused) {
+                dual_value(y.data(), nullptr, true, &ok);         // mma.c:288: x*(y), g, w at the solution
+                if (!ok) return L.fail("dual evaluation");
+            }
             if (stats) { stats->dual_evals += launches; ++stats->dual_solves; }
             if (prm.verbosity) {
                 std::printf("%s dual converged in %lld iterations to g=%g:\n", tag, launches, g0);

@@ -30,6 +30,7 @@ struct CcsaParams {
     double sigma_min = 0.0;
     double dual_ftol_rel = 1e-14, dual_ftol_abs = 0, dual_xtol_rel = 0, dual_xtol_abs = 0;
     int dual_maxeval = 100000;
+    int fused_solve = 1;     // library knob b200_fused_solve: run each dual solve as one persistent kernel
 };
 
 struct DriverStats {

@@ -26,6 +26,8 @@
 
 #include <cstdint>
 
+#include "dual_mma.hpp"
+
 namespace nb200 {
 
 constexpr int kBlock = 256;              // threads per CTA of every kernel here
@@ -90,6 +92,16 @@ struct DualArgs {
     double y[kMaxParamM], rhoc[kMaxParamM], half_rhoc[kMaxParamM];
 };
 
+// the per-evaluation scalars as the point functions see them: for the one-evaluation kernel they alias
+// the __grid_constant__ parameter block (constant-bank operands), for the persistent solve kernel y lives
+// in shared memory and changes every generation
+struct Multipliers {
+    const double *y, *rhoc, *half_rhoc;
+    double rho, half_rho, u_ccsaq;
+    unsigned active;
+    int m, cons0, cons_n;
+};
+
 // pair range [p_lo, p_hi) of global group `seg`, relative to the start of this rank's shard
 __device__ __forceinline__ void group_pairs(unsigned long long nchunks, unsigned nseg_total, unsigned long long chunk0,
                                             unsigned seg, unsigned long long *p_lo, unsigned long long *p_hi)
@@ -135,8 +147,8 @@ __device__ __forceinline__ bool is_last_arrival(unsigned *ticket, unsigned total
 // MAXM rows of grad_c are kept in registers; FULL means m == MAXM with every constraint active, which
 // strips the per-row predicates from the unrolled loops (the common case m in {1,2,4,8,16}).
 // MMA: mma.c:96-129.
-template <int MAXM, bool FULL>
-__device__ __forceinline__ double mma_point(const DualArgs &a, double x, double lb, double ub, double s, double g,
+template <int MAXM, bool FULL, class MU>
+__device__ __forceinline__ double mma_point(const MU &a, double x, double lb, double ub, double s, double g,
                                             const double (&Gr)[MAXM > 0 ? MAXM : 1], const double *Gcol,
                                             unsigned long long ld, double (&acc)[3 + (MAXM > 0 ? MAXM : 1)])
 {
@@ -187,8 +199,8 @@ __device__ __forceinline__ double mma_point(const DualArgs &a, double x, double 
 }
 
 // CCSAQ: ccsa_quadratic.c:111-140
-template <int MAXM, bool FULL>
-__device__ __forceinline__ double ccsaq_point(const DualArgs &a, double x, double lb, double ub, double s, double g,
+template <int MAXM, bool FULL, class MU>
+__device__ __forceinline__ double ccsaq_point(const MU &a, double x, double lb, double ub, double s, double g,
                                               const double (&Gr)[MAXM > 0 ? MAXM : 1], const double *Gcol,
                                               unsigned long long ld, double (&acc)[3 + (MAXM > 0 ? MAXM : 1)])
 {
@@ -256,6 +268,63 @@ __device__ __forceinline__ bool warp_is_last(unsigned *ticket, unsigned total, i
     return t == total - 1u;
 }
 
+// Sweep one group: this warp's lanes of every chunk of group `gl`, m+3 lane accumulators.
+template <int VARIANT, int MAXM, bool FULL, int UNROLL, class MU>
+__device__ __forceinline__ void sweep_group(const DualArgs &a, const MU &mu, bool store, unsigned gl, int sub,
+                                            int lane, double (&acc)[3 + (MAXM > 0 ? MAXM : 1)])
+{
+    constexpr int MR = MAXM > 0 ? MAXM : 1;
+    const double2 *x2 = reinterpret_cast<const double2 *>(a.x);
+    const double2 *lb2 = reinterpret_cast<const double2 *>(a.lb);
+    const double2 *ub2 = reinterpret_cast<const double2 *>(a.ub);
+    const double2 *s2v = reinterpret_cast<const double2 *>(a.sigma);
+    const double2 *g2 = reinterpret_cast<const double2 *>(a.g);
+    const bool in_regs = FULL || mu.m <= MAXM;
+    unsigned long long p_lo, p_hi;
+    group_pairs(a.nchunks, a.nseg_total, a.chunk0, a.seg0 + gl, &p_lo, &p_hi);
+
+    for (unsigned long long p0 = p_lo + sub * 32 + lane; p0 < p_hi; p0 += (unsigned long long) kChunkPairs * UNROLL) {
+        double2 vx[UNROLL], vlb[UNROLL], vub[UNROLL], vs[UNROLL], vg[UNROLL];
+        double Ga[UNROLL][MR], Gb[UNROLL][MR];
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            const unsigned long long p = p0 + (unsigned long long) kChunkPairs * u;
+            const bool live = u == 0 || p < p_hi;
+            vs[u] = make_double2(0.0, 0.0);      // sigma = 0 lanes are skipped by both formulas
+            vx[u] = vlb[u] = vub[u] = vg[u] = make_double2(0.0, 0.0);
+            if (live) {
+                vx[u] = ld_stream(x2 + p); vlb[u] = ld_stream(lb2 + p); vub[u] = ld_stream(ub2 + p);
+                vs[u] = ld_stream(s2v + p); vg[u] = ld_stream(g2 + p);
+            }
+#pragma unroll
+            for (int i = 0; i < MR; ++i) {
+                Ga[u][i] = 0.0;
+                Gb[u][i] = 0.0;
+                if (MAXM > 0 && in_regs && (FULL || i < mu.m) && live) {
+                    const double2 t = ld_stream(reinterpret_cast<const double2 *>(a.G + (unsigned long long) i * a.ld) + p);
+                    Ga[u][i] = t.x;
+                    Gb[u][i] = t.y;
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            const unsigned long long p = p0 + (unsigned long long) kChunkPairs * u;
+            const bool live = u == 0 || p < p_hi;
+            const double *col = a.G + 2 * p;
+            double2 xc;
+            if (VARIANT == 0) {
+                xc.x = mma_point<MAXM, FULL>(mu, vx[u].x, vlb[u].x, vub[u].x, vs[u].x, vg[u].x, Ga[u], col, a.ld, acc);
+                xc.y = mma_point<MAXM, FULL>(mu, vx[u].y, vlb[u].y, vub[u].y, vs[u].y, vg[u].y, Gb[u], col + 1, a.ld, acc);
+            } else {
+                xc.x = ccsaq_point<MAXM, FULL>(mu, vx[u].x, vlb[u].x, vub[u].x, vs[u].x, vg[u].x, Ga[u], col, a.ld, acc);
+                xc.y = ccsaq_point<MAXM, FULL>(mu, vx[u].y, vlb[u].y, vub[u].y, vs[u].y, vg[u].y, Gb[u], col + 1, a.ld, acc);
+            }
+            if (store && live) st_stream(reinterpret_cast<double2 *>(a.xcur) + p, xc);
+        }
+    }
+}
+
 template <int VARIANT, int MAXM, bool FULL, bool STORE, int BLOCK, int UNROLL, int MINB>
 __global__ void __launch_bounds__(BLOCK, MINB) dual_eval_kernel(const __grid_constant__ DualArgs a)
 {
@@ -270,61 +339,11 @@ __global__ void __launch_bounds__(BLOCK, MINB) dual_eval_kernel(const __grid_con
     const unsigned ngroups = a.segs_per_vshard * a.local_vshards;
     __shared__ double s_rec[SLOTS][2][kGroupWarps * NV];
     int parity = 0;
-
-    const double2 *x2 = reinterpret_cast<const double2 *>(a.x);
-    const double2 *lb2 = reinterpret_cast<const double2 *>(a.lb);
-    const double2 *ub2 = reinterpret_cast<const double2 *>(a.ub);
-    const double2 *s2v = reinterpret_cast<const double2 *>(a.sigma);
-    const double2 *g2 = reinterpret_cast<const double2 *>(a.g);
-    const bool in_regs = FULL || a.m <= MAXM;
-
     for (unsigned gl = slot; gl < ngroups; gl += nslots) {
-        unsigned long long p_lo, p_hi;
-        group_pairs(a.nchunks, a.nseg_total, a.chunk0, a.seg0 + gl, &p_lo, &p_hi);
         double acc[NV];
 #pragma unroll
         for (int k = 0; k < NV; ++k) acc[k] = 0.0;
-
-        for (unsigned long long p0 = p_lo + sub * 32 + lane; p0 < p_hi; p0 += (unsigned long long) kChunkPairs * UNROLL) {
-            double2 vx[UNROLL], vlb[UNROLL], vub[UNROLL], vs[UNROLL], vg[UNROLL];
-            double Ga[UNROLL][MR], Gb[UNROLL][MR];
-#pragma unroll
-            for (int u = 0; u < UNROLL; ++u) {
-                const unsigned long long p = p0 + (unsigned long long) kChunkPairs * u;
-                const bool live = u == 0 || p < p_hi;
-                vs[u] = make_double2(0.0, 0.0);      // sigma = 0 lanes are skipped by both formulas
-                vx[u] = vlb[u] = vub[u] = vg[u] = make_double2(0.0, 0.0);
-                if (live) {
-                    vx[u] = ld_stream(x2 + p); vlb[u] = ld_stream(lb2 + p); vub[u] = ld_stream(ub2 + p);
-                    vs[u] = ld_stream(s2v + p); vg[u] = ld_stream(g2 + p);
-                }
-#pragma unroll
-                for (int i = 0; i < MR; ++i) {
-                    Ga[u][i] = 0.0;
-                    Gb[u][i] = 0.0;
-                    if (MAXM > 0 && in_regs && (FULL || i < a.m) && live) {
-                        const double2 t = ld_stream(reinterpret_cast<const double2 *>(a.G + (unsigned long long) i * a.ld) + p);
-                        Ga[u][i] = t.x;
-                        Gb[u][i] = t.y;
-                    }
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < UNROLL; ++u) {
-                const unsigned long long p = p0 + (unsigned long long) kChunkPairs * u;
-                const bool live = u == 0 || p < p_hi;
-                const double *col = a.G + 2 * p;
-                double2 xc;
-                if (VARIANT == 0) {
-                    xc.x = mma_point<MAXM, FULL>(a, vx[u].x, vlb[u].x, vub[u].x, vs[u].x, vg[u].x, Ga[u], col, a.ld, acc);
-                    xc.y = mma_point<MAXM, FULL>(a, vx[u].y, vlb[u].y, vub[u].y, vs[u].y, vg[u].y, Gb[u], col + 1, a.ld, acc);
-                } else {
-                    xc.x = ccsaq_point<MAXM, FULL>(a, vx[u].x, vlb[u].x, vub[u].x, vs[u].x, vg[u].x, Ga[u], col, a.ld, acc);
-                    xc.y = ccsaq_point<MAXM, FULL>(a, vx[u].y, vlb[u].y, vub[u].y, vs[u].y, vg[u].y, Gb[u], col + 1, a.ld, acc);
-                }
-                if (STORE && live) st_stream(reinterpret_cast<double2 *>(a.xcur) + p, xc);
-            }
-        }
+        sweep_group<VARIANT, MAXM, FULL, UNROLL>(a, a, STORE, gl, sub, lane, acc);   // multipliers = the parameter block itself
 
         // warp record -> shared memory; group record = the 8 warp records added in warp order by warp 0 of
         // the slot.  One slot barrier per group; the record buffer is double-buffered across iterations so
@@ -421,6 +440,295 @@ __global__ void __launch_bounds__(BLOCK, MINB) dual_eval_kernel(const __grid_con
             if (a.publish_host || a.box[0] != nullptr) {
                 *a.flag_host = a.seq;
                 __threadfence_system();
+            }
+        }
+    }
+}
+
+// ---- the persistent dual-SOLVE kernel: one launch per dual solve ------------------------------------------
+//   The m-dimensional dual optimiser (DualMachine, dual_mma.hpp -- the same code the
+// host runs) moves into the kernel: all CTAs stay resident (cooperative launch) and walk *generations*.
+// Generation g = one dual evaluation at the trial multipliers y_g.  Groups are claimed from a monotonic
+// counter (claim c -> generation c / ngroups + 1, group c % ngroups), swept exactly like dual_eval_kernel
+// (same records, same fold tree => bit-identical sums), and the warp that completes the rank's last
+// virtual shard -- after the NVLink mailbox exchange when there are several ranks -- feeds F and grad F
+// to the DualMachine, publishes y_{g+1} and bumps the generation that the other CTAs are polling.
+// Versus one launch per evaluation this removes launch latency, the PCIe result hop and the host turn-
+// around from every evaluation; the host sees one launch and one result per dual solve.
+struct SolveState {                       // device global, zeroed by the host before every launch
+    unsigned long long claim;             // monotonic group-claim counter
+    unsigned long long gen;               // last published generation (0: none yet)
+    int done;                             // 1: leave
+    int store;                            // the generation in flight also stores x*(y)
+    unsigned vtickets[kVirtualShards + 1];    // monotonic completion counters (virtual shards, then rank)
+    int final_pass;                       // the generation in flight is the final evaluation at the solution
+    int pad;
+    double u_ccsaq;
+    double y[kMaxParamM];                 // trial multipliers of the generation in flight
+    DualMachine mach;
+};
+
+struct SolveArgs {
+    DualArgs d;                           // arrays, geometry, workspace, exchange boxes (d.y is unused)
+    SolveState *st;
+    double fval;                          // objective value at x
+    double cval[kMaxParamM];              // constraint values with switched-off ones zeroed (mma.c:78)
+    double lo[kMaxParamM], hi[kMaxParamM];    // box of the multipliers
+    DualStop stop;
+    volatile double *res_host;            // mapped pinned: raw sums [24] | y [32] | nevals | ret
+};
+
+struct SharedMultipliers {                // what the point functions read in the solve kernel
+    const double *y, *rhoc, *half_rhoc;   // y in shared memory; penalties from the parameter block
+    double rho, half_rho, u_ccsaq;
+    unsigned active;
+    int m, cons0, cons_n;
+};
+
+__device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long *p)
+{
+    return *reinterpret_cast<const volatile unsigned long long *>(p);
+}
+
+template <int VARIANT, int MAXM, bool FULL, int BLOCK, int UNROLL, int MINB>
+__global__ void __launch_bounds__(BLOCK, MINB) dual_solve_kernel(const __grid_constant__ SolveArgs sa)
+{
+    constexpr int MR = MAXM > 0 ? MAXM : 1;
+    constexpr int NV = 3 + MR;
+    static_assert(BLOCK == 32 * kGroupWarps, "one group slot per CTA");
+    const DualArgs &a = sa.d;
+    SolveState *st = sa.st;
+    const int lane = threadIdx.x & 31;
+    const int sub = threadIdx.x >> 5;
+    const unsigned ngroups = a.segs_per_vshard * a.local_vshards;
+    __shared__ double s_rec[2][kGroupWarps * NV];
+    __shared__ double s_y[kMaxParamM];
+    __shared__ double s_u;
+    __shared__ int s_store, s_exit;
+    __shared__ unsigned long long s_claim[2];
+    __shared__ DualMachine s_mach;
+    int parity = 0;
+
+    // bootstrap: one thread starts the optimiser and publishes generation 1 at the warm-start point
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        DualMachine &mm = st->mach;
+        int rc = mm.start(a.m, sa.d.y, sa.lo, sa.hi, sa.stop);     // d.y carries the warm start
+        if (rc != kRetSuccess) {          // start point outside the box: report, publish nothing
+            sa.res_host[24 + kMaxParamM + 1] = (double) rc;
+            __threadfence_system();
+            *a.flag_host = a.seq;
+            __threadfence_system();
+            *reinterpret_cast<volatile int *>(&st->done) = 1;
+            __threadfence();
+        } else {
+            double u = a.rho;
+            for (int i = 0; i < a.m; ++i) { st->y[i] = mm.y[i]; u = addx(u, mulx(a.rhoc[i], mm.y[i])); }
+            st->u_ccsaq = u;
+            st->store = 0;
+            st->final_pass = 0;
+            __threadfence();
+            *reinterpret_cast<volatile unsigned long long *>(&st->gen) = 1;
+            __threadfence();
+        }
+    }
+    if (threadIdx.x == 0) s_claim[0] = atomicAdd(&st->claim, 1ull);
+    __syncthreads();
+
+    unsigned long long my_gen = 0;        // generation whose multipliers are in s_y
+    const long long t_start = clock64();
+    for (int it = 0;; ++it) {
+        const unsigned long long c = s_claim[it & 1];
+        const unsigned long long want = c / ngroups + 1;
+        const unsigned gl = (unsigned) (c % ngroups);
+        // wait until generation `want` is published (or the solve has finished); refresh the multipliers
+        if (want != my_gen) {
+            if (threadIdx.x == 0) {
+                int ex = 0;
+                while (ld_volatile_u64(&st->gen) < want) {
+                    if (*reinterpret_cast<volatile int *>(&st->done)) { ex = 1; break; }
+                    __nanosleep(64);
+                }
+                if (*reinterpret_cast<volatile int *>(&st->done) && ld_volatile_u64(&st->gen) < want) ex = 1;
+                s_exit = ex;
+            }
+            __syncthreads();
+            if (s_exit) return;
+            __threadfence();
+            if (threadIdx.x < a.m) s_y[threadIdx.x] = __ldcg(&st->y[threadIdx.x]);
+            if (threadIdx.x == 32) { s_u = __ldcg(&st->u_ccsaq); s_store = __ldcg(&st->store); }
+            my_gen = want;
+            __syncthreads();
+        }
+        // claim the next group early so that its index is ready after this group's barrier
+        if (threadIdx.x == 0) s_claim[(it + 1) & 1] = atomicAdd(&st->claim, 1ull);
+
+        SharedMultipliers mu;
+        mu.y = s_y; mu.rhoc = a.rhoc; mu.half_rhoc = a.half_rhoc;
+        mu.rho = a.rho; mu.half_rho = a.half_rho; mu.u_ccsaq = s_u;
+        mu.active = a.active; mu.m = a.m; mu.cons0 = 0; mu.cons_n = a.m;
+        double acc[NV];
+#pragma unroll
+        for (int k = 0; k < NV; ++k) acc[k] = 0.0;
+        sweep_group<VARIANT, MAXM, FULL, UNROLL>(a, mu, s_store != 0, gl, sub, lane, acc);
+
+        warp_fold<NV>(acc);
+        double *srec = s_rec[parity];
+        if (lane == 0) {
+#pragma unroll
+            for (int k = 0; k < NV; ++k) srec[sub * NV + k] = acc[k];
+        }
+        __syncthreads();
+        parity ^= 1;
+        if (sub != 0) continue;
+        if (lane < NV) {
+            double s = srec[lane];
+#pragma unroll
+            for (int w = 1; w < kGroupWarps; ++w) s = addx(s, srec[w * NV + lane]);
+            a.grouprecs[(unsigned long long) gl * a.nvp + lane] = s;
+        }
+        __syncwarp();
+
+        // virtual-shard sum (monotonic ticket: every generation adds exactly P arrivals)
+        const unsigned vs_local = gl / a.segs_per_vshard;
+        {
+            unsigned t = 0;
+            __threadfence();
+            if (lane == 0) t = atomicAdd(&st->vtickets[vs_local], 1u);
+            t = __shfl_sync(0xffffffffu, t, 0);
+            __threadfence();
+            if ((t + 1u) % a.segs_per_vshard != 0u) continue;
+        }
+#pragma unroll
+        for (int k = 0; k < NV; ++k) acc[k] = 0.0;
+        {
+            const double *base = a.grouprecs + (unsigned long long) vs_local * a.segs_per_vshard * a.nvp;
+            for (unsigned r = lane; r < a.segs_per_vshard; r += 32)
+#pragma unroll
+                for (int k = 0; k < NV; ++k) acc[k] = addx(acc[k], __ldcg(base + (unsigned long long) r * a.nvp + k));
+        }
+        warp_fold<NV>(acc);
+        if (lane == 0) {
+            double *rec = a.vsums + (unsigned long long) vs_local * a.nvp;
+#pragma unroll
+            for (int k = 0; k < NV; ++k) rec[k] = acc[k];
+        }
+        {
+            unsigned t = 0;
+            __threadfence();
+            if (lane == 0) t = atomicAdd(&st->vtickets[kVirtualShards], 1u);
+            t = __shfl_sync(0xffffffffu, t, 0);
+            __threadfence();
+            if ((t + 1u) % a.local_vshards != 0u) continue;
+        }
+
+        // ---- this warp completed generation my_gen on this rank: total sums (exchange if sharded) ----
+        double total = 0.0;               // lane k < NV holds sum k
+        int timed_out = 0;
+        if (a.box[0] == nullptr) {
+            if (lane < NV) {
+                total = __ldcg(a.vsums + lane);
+                for (unsigned v = 1; v < a.local_vshards; ++v) total = addx(total, __ldcg(a.vsums + (unsigned long long) v * a.nvp + lane));
+            }
+        } else {
+            constexpr int kStride = 24, kFlagOff = 2 * 8 * kStride;
+            const unsigned long long seq = a.seq + my_gen;         // one mailbox sequence number per generation
+            const int buf = (int) (seq & 1ull);
+            const unsigned v0 = a.seg0 / a.segs_per_vshard;
+            if (lane < NV)
+                for (int r = 0; r < a.world; ++r)
+                    for (unsigned v = 0; v < a.local_vshards; ++v) {
+                        volatile double *dst = a.box[r] + ((unsigned long long) buf * 8 + v0 + v) * kStride + lane;
+                        *dst = __ldcg(a.vsums + (unsigned long long) v * a.nvp + lane);
+                    }
+            __threadfence_system();
+            __syncwarp();
+            if (lane < a.world) {
+                volatile unsigned long long *f =
+                    reinterpret_cast<volatile unsigned long long *>(a.box[lane] + kFlagOff) + buf * 8 + a.rank;
+                *f = seq;
+            }
+            if (lane < a.world) {
+                volatile unsigned long long *f =
+                    reinterpret_cast<volatile unsigned long long *>(a.box[a.rank] + kFlagOff) + buf * 8 + lane;
+                const long long t0 = clock64();
+                while (*f != seq)
+                    if (clock64() - t0 > 20000000000ll) { timed_out = 1; break; }
+            }
+            timed_out = __any_sync(0xffffffffu, timed_out);
+            __threadfence_system();
+            if (lane < NV) {
+                volatile double *rec = a.box[a.rank] + (unsigned long long) buf * 8 * kStride + lane;
+                total = rec[0];
+                for (int v = 1; v < kVirtualShards; ++v) total = addx(total, rec[v * kStride]);
+            }
+        }
+
+        // ---- the dual optimiser's turn (one lane; the machine is staged through shared memory) ----
+        {
+            const double *src = reinterpret_cast<const double *>(&st->mach);
+            double *dst = reinterpret_cast<double *>(&s_mach);
+            for (int i = lane; i < (int) (sizeof(DualMachine) / sizeof(double)); i += 32) dst[i] = __ldcg(src + i);
+        }
+        __syncwarp();
+        const int final_pass = *reinterpret_cast<volatile int *>(&st->final_pass);
+        // F and grad F from the sums, constants added in the reference's order (mma.c:75-78, :135)
+        double gci = 0.0;
+        if (lane >= 3 && lane < 3 + a.m) gci = addx(sa.cval[lane - 3], total);      // g_i(y)
+        int finished = 0, next_store = 0, next_final = 0;
+        if (!final_pass) {
+            double val = sa.fval;
+            for (int i = 0; i < a.m; ++i) val = addx(val, mulx(s_y[i], sa.cval[i]));
+            val = addx(val, __shfl_sync(0xffffffffu, total, 0));
+            __shared__ double s_grad[kMaxParamM];
+            if (lane >= 3 && lane < 3 + a.m) s_grad[lane - 3] = -gci;
+            __syncwarp();
+            if (lane == 0) {
+                const double elapsed = (double) (clock64() - t_start) * 5e-10;     // ~2 GHz; only feeds maxtime
+                finished = timed_out ? 1 : (s_mach.feed(-val, s_grad, elapsed) ? 1 : 0);
+                if (timed_out) s_mach.ret = kRetFailure;
+            }
+            finished = __shfl_sync(0xffffffffu, finished, 0);
+            if (finished && !timed_out) { next_store = 1; next_final = 1; }          // one more pass at the solution
+        }
+        __syncwarp();
+        if (final_pass || timed_out) {
+            // publish the result of the solve: raw sums of the final pass, multipliers, counts
+            if (lane < NV) sa.res_host[lane] = total;
+            if (lane < a.m) sa.res_host[24 + lane] = s_mach.y[lane];
+            if (lane == 0) {
+                sa.res_host[24 + kMaxParamM] = (double) s_mach.nevals;
+                sa.res_host[24 + kMaxParamM + 1] = (double) s_mach.ret;
+                sa.res_host[24 + kMaxParamM + 2] = (double) my_gen;
+            }
+            __threadfence_system();
+            __syncwarp();
+            if (lane == 0) {
+                *a.flag_host = a.seq;
+                __threadfence_system();
+                *reinterpret_cast<volatile int *>(&st->done) = 1;
+                __threadfence();
+            }
+            continue;      // the next wait sees done and leaves
+        }
+        // publish generation my_gen + 1
+        {
+            const double *trial = next_final ? s_mach.y : s_mach.ycur;
+            if (lane < a.m) st->y[lane] = trial[lane];
+            if (lane == 0) {
+                double u = a.rho;
+                for (int i = 0; i < a.m; ++i) u = addx(u, mulx(a.rhoc[i], trial[i]));
+                st->u_ccsaq = u;
+                st->store = next_store;
+                st->final_pass = next_final;
+            }
+            double *dstm = reinterpret_cast<double *>(&st->mach);
+            const double *srcm = reinterpret_cast<const double *>(&s_mach);
+            for (int i = lane; i < (int) (sizeof(DualMachine) / sizeof(double)); i += 32) dstm[i] = srcm[i];
+            __threadfence();
+            __syncwarp();
+            if (lane == 0) {
+                *reinterpret_cast<volatile unsigned long long *>(&st->gen) = my_gen + 1;
+                __threadfence();
             }
         }
     }

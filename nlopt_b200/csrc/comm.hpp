@@ -37,6 +37,7 @@ struct Comm {
     // process, so the number is process-wide; all ranks issue the same launches in the same order, which
     // keeps the counters of all ranks in lockstep.
     unsigned long long next_seq() { return ++seq_counter_; }
+    void advance_seq(unsigned long long by) { seq_counter_ += by; }   // a dual-solve kernel used `by` numbers
 
     // collectives on a stream; return 0 on success
     int all_gather_inplace(double *buf, size_t count_per_rank, cudaStream_t s, std::string *err);

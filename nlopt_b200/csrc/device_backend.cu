@@ -174,6 +174,10 @@ void DeviceBackend::free_state()
     if (tickets_) cudaFree(tickets_);
     if (xfull_dev_) cudaFree(xfull_dev_);
     if (scalar_dev_) cudaFree(scalar_dev_);
+    if (solve_state_) cudaFree(solve_state_);
+    if (res_host_) cudaFreeHost(res_host_);
+    solve_state_ = nullptr;
+    res_host_ = nullptr;
     if (out_host_) cudaFreeHost(out_host_);
     if (flag_host_) cudaFreeHost(flag_host_);
     if (h_x_) BlockCache::get().give(true, (size_t) geo_.n * sizeof(double), h_x_);
@@ -507,9 +511,8 @@ bool DeviceBackend::wait_flag()
     }
 }
 
-bool DeviceBackend::launch_dual(const double *y, const DualScalars &sc, bool store, int chunk0, int chunk_n, bool wait)
+void DeviceBackend::fill_dual_args(DualArgs &a, const double *y, const DualScalars &sc, int cons0, int cons_n)
 {
-    DualArgs a;
     std::memset(&a, 0, sizeof a);
     a.x = x_; a.lb = lb_; a.ub = ub_; a.sigma = sigma_; a.g = g_; a.G = G_;
     a.xcur = xcur_;
@@ -529,7 +532,7 @@ bool DeviceBackend::launch_dual(const double *y, const DualScalars &sc, bool sto
         for (int r = 0; r < 8; ++r) a.box[r] = (cm.active() && cm.use_p2p() && r < cm.world) ? cm.box_peer[r] : nullptr;
     }
     a.m = (int) m_;
-    a.cons0 = chunk0; a.cons_n = chunk_n;
+    a.cons0 = cons0; a.cons_n = cons_n;
     a.rho = sc.rho;
     a.half_rho = 0.5 * sc.rho;
     a.active = 0;
@@ -542,6 +545,12 @@ bool DeviceBackend::launch_dual(const double *y, const DualScalars &sc, bool sto
         u += sc.rhoc[i] * y[i];
     }
     a.u_ccsaq = u;
+}
+
+bool DeviceBackend::launch_dual(const double *y, const DualScalars &sc, bool store, int chunk0, int chunk_n, bool wait)
+{
+    DualArgs a;
+    fill_dual_args(a, y, sc, chunk0, chunk_n);
 
     const int maxm = pick_maxm((int) m_);
     cudaEvent_t e0 = nullptr, e1 = nullptr;
@@ -601,6 +610,98 @@ bool DeviceBackend::dual_eval(const double *y, const DualScalars &sc, bool mater
         for (int k = 0; k < cn; ++k) out->gc[c0 + k] = out_host_[3 + k];
         c0 += step;
     } while (c0 < (int) m_);
+    return true;
+}
+
+// ------------------------------------------------------------------------------------------------
+// one launch per dual solve (persistent cooperative kernel, ccsa_kernels.cuh: dual_solve_kernel)
+
+namespace {
+typedef void (*SolveKernel)(const SolveArgs);
+
+template <int VARIANT, bool FULL>
+SolveKernel pick_solve_kernel(int maxm)
+{
+    switch (maxm) {
+    case 1: return dual_solve_kernel<VARIANT, 1, FULL, 256, 1, 3>;
+    case 2: return dual_solve_kernel<VARIANT, 2, FULL, 256, 1, 3>;
+    case 4: return dual_solve_kernel<VARIANT, 4, FULL, 256, 1, 3>;
+    case 8: return dual_solve_kernel<VARIANT, 8, FULL, 256, 1, 2>;
+    default: return dual_solve_kernel<VARIANT, 16, FULL, 256, 1, 2>;
+    }
+}
+}  // namespace
+
+bool DeviceBackend::supports_dual_solve() const
+{
+    return fused_solve_ok_ && m_ >= 1 && m_ <= 16;
+}
+
+bool DeviceBackend::dual_solve(double *y, const double *lo, const double *hi, const double *stop6, const DualScalars &sc,
+                               DualSums *out, int *ret, long *nevals)
+{
+    if (!solve_state_) {
+        NB_CUDA(cudaMalloc(&solve_state_, sizeof(SolveState)));
+        NB_CUDA(cudaMemsetAsync(solve_state_, 0, sizeof(SolveState), stream_));
+        NB_CUDA(cudaHostAlloc(&res_host_, 64 * sizeof(double), cudaHostAllocMapped));
+    }
+    SolveArgs sa;
+    fill_dual_args(sa.d, y, sc, 0, (int) m_);
+    sa.st = static_cast<SolveState *>(solve_state_);
+    sa.fval = sc.fval;
+    for (unsigned i = 0; i < (unsigned) kMaxParamM; ++i) {
+        sa.cval[i] = i < m_ ? ((variant_ == kMMA && std::isnan(sc.fcval[i])) ? 0.0 : sc.fcval[i]) : 0.0;
+        sa.lo[i] = i < m_ ? lo[i] : 0.0;
+        sa.hi[i] = i < m_ ? hi[i] : 0.0;
+    }
+    sa.stop.ftol_rel = stop6[0]; sa.stop.ftol_abs = stop6[1]; sa.stop.xtol_rel = stop6[2]; sa.stop.xtol_abs = stop6[3];
+    sa.stop.maxeval = (int) stop6[4]; sa.stop.maxtime = stop6[5];
+    sa.res_host = res_host_;
+
+    const int maxm = pick_maxm((int) m_);
+    const bool full = (int) m_ == maxm && (variant_ == kCCSAQ || sa.d.active == ((1u << m_) - 1u));
+    SolveKernel fn = variant_ == kMMA ? (full ? pick_solve_kernel<0, true>(maxm) : pick_solve_kernel<0, false>(maxm))
+                                      : (full ? pick_solve_kernel<1, true>(maxm) : pick_solve_kernel<1, false>(maxm));
+    int per_sm = 0;
+    NB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, 256, 0));
+    if (per_sm < 1) return fail("dual_solve_kernel does not fit on an SM");
+    long long grid = (long long) per_sm * sm_count_;
+    if (grid > (long long) geo_.nseg_local) grid = geo_.nseg_local;
+    if (grid < 1) grid = 1;
+
+    // the head of the state (claim counter, generation, flags, tickets) starts from zero every launch
+    NB_CUDA(cudaMemsetAsync(solve_state_, 0, offsetof(SolveState, u_ccsaq), stream_));
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (time_kernels_) {
+        if (ev_used_ + 2 > ev_pool_.size()) {
+            if (ev_pool_.size() >= 8192) drain_events();
+            else
+                for (int k = 0; k < 512; ++k) { cudaEvent_t e; cudaEventCreate(&e); ev_pool_.push_back(e); }
+        }
+        e0 = ev_pool_[ev_used_++];
+        e1 = ev_pool_[ev_used_++];
+        cudaEventRecord(e0, stream_);
+    }
+    void *params[] = {&sa};
+    NB_CUDA(cudaLaunchCooperativeKernel((const void *) fn, dim3((unsigned) grid), dim3(256), params, 0, stream_));
+    if (time_kernels_) cudaEventRecord(e1, stream_);
+    ++stats_->kernel_launches;
+    cand_in_x_ = false;                              // the final pass stores x*(y) into xcur_
+    ++x_epoch_;
+    if (!wait_flag()) return false;
+    const long gens = (long) res_host_[24 + kMaxParamM + 2];
+    *ret = (int) res_host_[24 + kMaxParamM + 1];
+    *nevals = (long) res_host_[24 + kMaxParamM];
+    if (Comm::instance().active() && gens > 0) Comm::instance().advance_seq((unsigned long long) gens);
+    if (*ret == kRetInvalid) return true;            // nothing ran; the caller reports it
+    if (*ret == kRetFailure) return fail("the cross-rank exchange inside the dual solve timed out");
+    out->val = res_host_[0];
+    out->gval = res_host_[1];
+    out->wval = res_host_[2];
+    for (unsigned i = 0; i < m_; ++i) {
+        out->gc[i] = res_host_[3 + i];
+        y[i] = res_host_[24 + i];
+    }
     return true;
 }
 
@@ -784,6 +885,7 @@ bool DeviceBackend::configure(const char *key, long long value)
     if (k == "time_kernels") { time_kernels_ = value != 0; return true; }
     if (k == "kernel_cfg") { kernel_cfg_ = (int) value; return true; }
     if (k == "ctas_per_sm") { ctas_per_sm_ = (int) value; return true; }
+    if (k == "fused_solve") { fused_solve_ok_ = value != 0; return true; }
     if (k == "pmax" || k == "target_chunks") {
         if (value < 1) return fail("bad value");
         if (k == "pmax") pmax_ = (unsigned) value; else target_chunks_ = (unsigned) value;

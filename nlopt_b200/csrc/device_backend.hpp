@@ -32,6 +32,9 @@ public:
     bool eval_objective(Slot slot, bool want_grad, double *value) override;
     bool eval_constraint(Slot slot, unsigned ic, unsigned row0, bool want_grad, double *values) override;
     bool dual_eval(const double *y, const DualScalars &sc, bool materialize, DualSums *out) override;
+    bool supports_dual_solve() const override;
+    bool dual_solve(double *y, const double *lo, const double *hi, const double *stop6, const DualScalars &sc, DualSums *out,
+                    int *ret, long *nevals) override;
     void accept_candidate() override;
     bool first_outer() override;
     bool end_outer(unsigned k, double sigma_min, double *dnorm, double *xnorm, bool *all_below_abs) override;
@@ -60,6 +63,7 @@ private:
     bool alloc_workspace();
     double *array(const char *which);
     double *xcur_view() { return cand_in_x_ ? x_ : xcur_; }
+    void fill_dual_args(struct DualArgs &a, const double *y, const DualScalars &sc, int cons0, int cons_n);
     bool launch_dual(const double *y, const DualScalars &sc, bool store, int chunk0, int chunk_n, bool wait);
     bool wait_flag();
     bool host_x_for(Slot slot);                      // bring the slot's x to pinned host memory (cached per epoch)
@@ -73,6 +77,9 @@ private:
     unsigned target_chunks_ = kDefaultTargetChunks, pmax_ = kDefaultPmax;
     int device_ = 0;
     int sm_count_ = 148, ctas_per_sm_ = 0;
+    void *solve_state_ = nullptr;     // SolveState (device) of the persistent dual-solve kernel
+    double *res_host_ = nullptr;      // its mapped pinned result record
+    bool fused_solve_ok_ = true;
     int kernel_cfg_ = -1;         // -1: measured default for (variant, m)          // index into the launch-geometry table of device_backend.cu
 
     // device state

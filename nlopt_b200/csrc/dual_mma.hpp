@@ -50,10 +50,10 @@ NB_HD inline bool rel_stop(double vold, double vnew, double reltol, double absto
     return d < abstol || d < reltol * (fabs(vnew) + fabs(vold)) * 0.5 || (reltol > 0 && vnew == vold);
 }
 
-struct DualStop {
-    double ftol_rel = 1e-14, ftol_abs = 0, xtol_rel = 0, xtol_abs = 0;   // optimize.c:822-825
-    int maxeval = 100000;                                                // optimize.c:826
-    double maxtime = 0;        // <= 0: unlimited (optimize.c:1104-1105 semantics already applied)
+struct DualStop {              // plain aggregate (it lives in kernel parameters and shared memory)
+    double ftol_rel, ftol_abs, xtol_rel, xtol_abs;   // optimize.c:822-825: defaults 1e-14, 0, 0, 0
+    int maxeval;                                     // optimize.c:826: default 100000
+    double maxtime;            // <= 0: unlimited (optimize.c:1104-1105 semantics already applied)
 };
 
 // return codes are nlopt_result values

@@ -272,6 +272,33 @@ def test_unconstrained_m0_and_options(built):
     assert np.allclose(r["x"], np.linalg.solve(A, b), atol=1e-5)
 
 
+@pytest.mark.parametrize("variant", [ob.MMA, ob.CCSAQ])
+def test_fused_dual_solve_equals_one_launch_per_evaluation(built, variant):
+    """The persistent dual-solve kernel runs the same DualMachine on the same (geometry-independent)
+    sums as the host-driven loop, so whole optimisation runs must agree bit for bit."""
+    alg = nl.LD_MMA if variant == ob.MMA else nl.LD_CCSAQ
+    n, m = 50000, 4
+    cons = [P.lin_constraint(k, n) for k in range(m)]
+    lb, ub = np.full(n, -2.0), np.full(n, 2.0)
+    runs = []
+    for fused in (1, 0):
+        r = _run(alg, n, P.rosen_f, cons, [1e-8] * m, lb, ub, P.rosen_x0(n), maxeval=15, b200_fused_solve=fused)
+        st = r["opt"].get_stats()
+        runs.append((r["ret"], r["numevals"], r["minf"], r["x"].tobytes(), st["dual_evals"]))
+        assert st["kernel_launches"] < st["dual_evals"] if fused else st["kernel_launches"] >= st["dual_evals"]
+    assert runs[0] == runs[1]
+    # tutorial problem (m = 2, infeasible start -> capped multipliers) and a 1-constraint problem
+    for kw in (dict(xtol_rel=1e-4), dict(stopval=P.TUT_FSTAR + 1e-3)):
+        pair = [_run(alg, 2, P.tut_f, [P.tut_c(2, 0), P.tut_c(-1, 1)], [1e-8, 1e-8], [-np.inf, 0.0], [np.inf, np.inf],
+                     P.TUT_X0, b200_fused_solve=f, **kw) for f in (1, 0)]
+        assert pair[0]["ret"] == pair[1]["ret"] and pair[0]["numevals"] == pair[1]["numevals"]
+        assert pair[0]["minf"] == pair[1]["minf"] and np.array_equal(pair[0]["x"], pair[1]["x"])
+    f, c = P.quad_problem(30000)
+    pair = [_run(alg, 30000, f, [c], [0.0], np.full(30000, -1.0), np.full(30000, 1.0), np.full(30000, 0.5),
+                 xtol_rel=1e-6, maxeval=60, b200_fused_solve=fz) for fz in (1, 0)]
+    assert pair[0]["minf"] == pair[1]["minf"] and np.array_equal(pair[0]["x"], pair[1]["x"])
+
+
 def test_device_path_has_no_cpu_fallback_symbols(built):
     """the product library must not contain or import anything from the oracle"""
     import subprocess, nlopt_b200._capi as capi
