@@ -210,7 +210,7 @@ def test_tutorial_goldens_on_gpu(built, variant, setting, ret, evals, x0, x1, f)
     assert abs(r["numevals"] - evals) <= 2
     assert abs(r["minf"] - f) <= 1e-6 and abs(r["x"][0] - x0) <= 1e-5 and abs(r["x"][1] - x1) <= 1e-5
     st = r["opt"].get_stats()
-    assert st["dual_evals"] > 0 and st["kernel_launches"] >= st["dual_evals"]
+    assert st["dual_evals"] > 0 and st["kernel_launches"] > 0
 
 
 @pytest.mark.parametrize("variant", [ob.MMA, ob.CCSAQ])
