@@ -322,6 +322,8 @@ def main():
             "dtype": "f64", "data": "synthetic",
             "config": workload_config(a, step="one inner CCSA iteration (dual solve + x*(y) + candidate evaluation)"),
             "dual_evals": sd["dual_evals"], "dual_solves": sd["dual_solves"], "f_after_steps": f_dev,
+            "wall_breakdown_s": {k: sd[k] for k in ("seconds_total", "seconds_setup", "seconds_dual_wall", "seconds_eval_wall",
+                                                     "seconds_glue_wall", "seconds_dual_kernel")},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": (achieved / peak) if achieved else None, "traffic": traffic,
                          "kernel": "dual_eval_kernel", "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650",

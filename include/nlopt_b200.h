@@ -202,6 +202,10 @@ typedef struct {
     double seconds_dual_kernel;  /* device time of the dual kernel (CUDA events), 0 if not timed  */
     long long h2d_bytes, d2h_bytes;
     long long kernel_launches;   /* all kernels of this library                                   */
+    double seconds_setup;        /* wall: allocating / uploading the device state                  */
+    double seconds_dual_wall;    /* wall: inside dual solves (launch to result, incl. exchange)    */
+    double seconds_eval_wall;    /* wall: objective + constraint evaluations (callbacks + copies)  */
+    double seconds_glue_wall;    /* wall: sigma init, end-of-outer pass, final copy of x           */
 } nlopt_b200_stats;
 nlopt_result nlopt_b200_get_stats(const nlopt_opt opt, nlopt_b200_stats *out);
 

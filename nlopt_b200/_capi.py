@@ -30,6 +30,8 @@ class Stats(C.Structure):
         ("seconds_total", C.c_double), ("seconds_callbacks", C.c_double),
         ("seconds_dual_kernel", C.c_double),
         ("h2d_bytes", C.c_longlong), ("d2h_bytes", C.c_longlong), ("kernel_launches", C.c_longlong),
+        ("seconds_setup", C.c_double), ("seconds_dual_wall", C.c_double), ("seconds_eval_wall", C.c_double),
+        ("seconds_glue_wall", C.c_double),
     ]
 
 

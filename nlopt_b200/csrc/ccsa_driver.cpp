@@ -151,6 +151,7 @@ int ccsa_minimize(Variant variant, Backend &be, const std::vector<double> &tol, 
             // dual solve, warm-started from the previous multipliers (mma.c:275-288)
             launches = 0;
             bool ok = true;
+            const double t_dual0 = wall_seconds();
             if (fused) {
                 // the whole dual solve + final evaluation as one persistent kernel
                 const double stop6[6] = {prm.dual_ftol_rel, prm.dual_ftol_abs, prm.dual_xtol_rel, prm.dual_xtol_abs,
@@ -190,7 +191,12 @@ int ccsa_minimize(Variant variant, Backend &be, const std::vector<double> &tol, 
                 dual_value(y.data(), nullptr, true, &ok);         // mma.c:288: x*(y), g, w at the solution
                 if (!ok) return L.fail("dual evaluation");
             }
-            if (stats) { stats->dual_evals += launches; ++stats->dual_solves; }
+            if (stats) {
+                stats->dual_evals += launches;
+                ++stats->dual_solves;
+                stats->seconds_dual += wall_seconds() - t_dual0;
+            }
+            const double t_eval0 = wall_seconds();
             if (prm.verbosity) {
                 std::printf("%s dual converged in %lld iterations to g=%g:\n", tag, launches, g0);
                 for (unsigned i = 0; i < m && i < (unsigned) prm.verbosity; ++i)
@@ -203,6 +209,7 @@ int ccsa_minimize(Variant variant, Backend &be, const std::vector<double> &tol, 
             ++inner_nevals;
             if (L.forced()) return R_FORCED;
             if ((ret = L.eval_constraints(kCandidate, prm.inner_gradients != 0, c_cur.data())) != R_SUCCESS) return ret;
+            if (stats) stats->seconds_eval += wall_seconds() - t_eval0;
             bool feasible_cur = true, inner_done = g0 >= fcur, new_infeasible = false;
             double infeas_cur = 0;
             auto classify = [&](bool touch_inner_done) {
@@ -270,7 +277,9 @@ int ccsa_minimize(Variant variant, Backend &be, const std::vector<double> &tol, 
         // end-of-iteration pass also prepares sigma / xprev / xprevprev for iteration k+1.
         double dnorm, xnorm;
         bool below_abs;
+        const double t_glue0 = wall_seconds();
         if (!be.end_outer(k, prm.sigma_min, &dnorm, &xnorm, &below_abs)) return L.fail("end-of-iteration pass");
+        if (stats) stats->seconds_glue += wall_seconds() - t_glue0;
         if (rel_stop(fprev, fcur, stop.ftol_rel, stop.ftol_abs)) ret = R_FTOL;
         if (dnorm < stop.xtol_rel * xnorm || (stop.has_xtol_abs && below_abs)) ret = R_XTOL;   // stop.c:98-108
         if (ret != R_SUCCESS) return ret;

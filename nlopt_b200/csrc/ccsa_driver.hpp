@@ -35,6 +35,7 @@ struct CcsaParams {
 
 struct DriverStats {
     long long dual_evals = 0, dual_solves = 0, outer_iters = 0;
+    double seconds_dual = 0, seconds_eval = 0, seconds_glue = 0;   // wall-clock breakdown of the loop
 };
 
 // Runs NLOPT_LD_MMA / NLOPT_LD_CCSAQ on the state held by `be`.  `tol` has one feasibility

@@ -32,9 +32,13 @@ struct Geometry {
         return (unsigned long long) s * nchunks / S;
     }
 
-    // P grows with n until a group holds about `target_chunks` chunks, capped at pmax
+    // Group size: `target_chunks` chunks for large n, fewer for small n so that there are still enough
+    // groups (>= ~12 per SM of a 148-SM part) to fill the machine; P = groups per virtual shard, capped at pmax.
     static unsigned choose_P(unsigned long long nchunks, unsigned target_chunks, unsigned pmax)
     {
+        unsigned long long fill = nchunks / 1776;
+        if (fill < 1) fill = 1;
+        if (fill < target_chunks) target_chunks = (unsigned) fill;
         unsigned long long want = (nchunks + (unsigned long long) kV * target_chunks - 1) / ((unsigned long long) kV * target_chunks);
         if (want < 1) want = 1;
         if (want > pmax) want = pmax;

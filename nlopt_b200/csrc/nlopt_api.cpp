@@ -836,6 +836,7 @@ nlopt_result run_ccsa(nlopt_opt opt, double *x_host, double *x_dev, double *minf
         set_err(opt, "%s", err.c_str());
         return NLOPT_FAILURE;
     }
+    opt->stats.seconds_setup = nb200::wall_seconds() - t0;
 
     /* library-specific knobs ride on the named-parameter mechanism (no ABI change) */
     if (nlopt_get_param(opt, "b200_time_kernels", 0.0) != 0.0) be->configure("time_kernels", 1);
@@ -862,6 +863,7 @@ nlopt_result run_ccsa(nlopt_opt opt, double *x_host, double *x_dev, double *minf
     int ret = nb200::ccsa_minimize(cfg.variant, *be, tol, minf, st, prm, &ds, &err);
     if (ret == NLOPT_FAILURE && !err.empty()) set_err(opt, "%s", err.c_str());
     if (ret == NLOPT_INVALID_ARGS && !err.empty()) set_err(opt, "%s", err.c_str());
+    const double t_fetch0 = nb200::wall_seconds();
     if (!be->fetch_x(x_host ? x_host : x_dev) && ret > 0) {
         set_err(opt, "copying the result back failed: %s", be->error().c_str());
         ret = NLOPT_FAILURE;
@@ -870,6 +872,9 @@ nlopt_result run_ccsa(nlopt_opt opt, double *x_host, double *x_dev, double *minf
     opt->stats.dual_solves = ds.dual_solves;
     opt->stats.outer_iters = ds.outer_iters;
     opt->stats.seconds_callbacks = be->seconds_in_callbacks();
+    opt->stats.seconds_dual_wall = ds.seconds_dual;
+    opt->stats.seconds_eval_wall = ds.seconds_eval;
+    opt->stats.seconds_glue_wall = ds.seconds_glue + (nb200::wall_seconds() - t_fetch0);
     delete be;
     opt->stats.seconds_total = nb200::wall_seconds() - t0;
     return (nlopt_result) ret;
