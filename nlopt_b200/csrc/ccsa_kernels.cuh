@@ -54,6 +54,50 @@ __device__ __forceinline__ void st_stream(double2 *p, double2 v)
     asm volatile("st.global.L1::no_allocate.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(v.x), "d"(v.y) : "memory");
 }
 
+// ---- tagged 128-bit mailbox slots (cross-rank exchange) ---------------------------------------------------
+__device__ __forceinline__ void box_put(double *slot, double value, unsigned long long tag)
+{
+    asm volatile("st.volatile.global.v2.b64 [%0], {%1, %2};" ::"l"(slot), "l"(__double_as_longlong(value)), "l"(tag) : "memory");
+}
+__device__ __forceinline__ bool box_get(const double *slot, unsigned long long tag, double *value)
+{
+    long long v;
+    unsigned long long t;
+    asm volatile("ld.volatile.global.v2.b64 {%0, %1}, [%2];" : "=l"(v), "=l"(t) : "l"(slot) : "memory");
+    *value = __longlong_as_double(v);
+    return t == tag;
+}
+constexpr int kBoxStride = 24;           // slots per virtual shard record (comm.hpp)
+
+// Lane k < nv: write this rank's shard records into every peer's mailbox, then gather all 8 records of
+// sum k from the own mailbox and fold them in index order.  Returns the total in lanes < nv; *timed_out is
+// warp-uniform.
+__device__ __forceinline__ double box_exchange(double *const *box, int rank, int world, unsigned long long seq,
+                                               const double *vsums, int nvp, unsigned local_vshards, unsigned v0,
+                                               int nv, int lane, int *timed_out)
+{
+    const int buf = (int) (seq & 1ull);
+    double total = 0.0;
+    int to = 0;
+    if (lane < nv) {
+        for (unsigned v = 0; v < local_vshards; ++v) {
+            const double val = __ldcg(vsums + (unsigned long long) v * nvp + lane);
+            for (int r = 0; r < world; ++r)
+                box_put(box[r] + 2ull * (((unsigned long long) buf * 8 + v0 + v) * kBoxStride + lane), val, seq);
+        }
+        const double *mine = box[rank] + 2ull * ((unsigned long long) buf * 8 * kBoxStride + lane);
+        const long long t0 = clock64();
+        for (int v = 0; v < kVirtualShards; ++v) {
+            double x;
+            while (!box_get(mine + 2ull * v * kBoxStride, seq, &x))
+                if (clock64() - t0 > 20000000000ll) { to = 1; break; }      // ~10 s: a peer died
+            total = v == 0 ? x : addx(total, x);
+        }
+    }
+    *timed_out = __any_sync(0xffffffffu, to);
+    return total;
+}
+
 // ---- arguments of one dual evaluation -------------------------------------------------------
 constexpr int kGroupWarps = 8;           // warps that sweep one group together (fixed: part of the reduction order)
 constexpr int kChunkPairs = 32 * kGroupWarps;   // 256 double2 pairs = 512 variables = 4 KB per array per sweep step
@@ -399,38 +443,12 @@ __global__ void __launch_bounds__(BLOCK, MINB) dual_eval_kernel(const __grid_con
             }
         }
         if (!a.publish_host && a.box[0] != nullptr) {
-            // ---- all-gather fused into the kernel: NVLink peer stores + flags (comm.hpp layout) ----
-            constexpr int kStride = 24, kFlagOff = 2 * 8 * kStride;
-            const int buf = (int) (a.seq & 1ull);
-            const unsigned v0 = a.seg0 / a.segs_per_vshard;
-            if (lane < NV)
-                for (int r = 0; r < a.world; ++r)
-                    for (unsigned v = 0; v < a.local_vshards; ++v) {
-                        volatile double *dst = a.box[r] + ((unsigned long long) buf * 8 + v0 + v) * kStride + lane;
-                        *dst = __ldcg(a.vsums + (unsigned long long) v * a.nvp + lane);
-                    }
-            __threadfence_system();
-            __syncwarp();
-            if (lane < a.world) {       // lane r raises this rank's flag in rank r's mailbox
-                volatile unsigned long long *f =
-                    reinterpret_cast<volatile unsigned long long *>(a.box[lane] + kFlagOff) + buf * 8 + a.rank;
-                *f = a.seq;
-            }
+            // ---- all-gather fused into the kernel: tagged NVLink peer stores (comm.hpp layout) ----
             int timed_out = 0;
-            if (lane < a.world) {       // ... and waits for rank `lane`'s flag in our own mailbox
-                volatile unsigned long long *f =
-                    reinterpret_cast<volatile unsigned long long *>(a.box[a.rank] + kFlagOff) + buf * 8 + lane;
-                const long long t0 = clock64();
-                while (*f != a.seq)
-                    if (clock64() - t0 > 20000000000ll) { timed_out = 1; break; }      // ~10 s: a peer died
-            }
-            timed_out = __any_sync(0xffffffffu, timed_out);
-            __threadfence_system();
-            if (lane < NV) {            // fold the 8 shard records in index order, exactly like one rank does
-                volatile double *rec = a.box[a.rank] + (unsigned long long) buf * 8 * kStride + lane;
-                double s = rec[0];
-                for (int v = 1; v < kVirtualShards; ++v) s = addx(s, rec[v * kStride]);
-                a.out_host[lane] = timed_out ? __longlong_as_double(0x7ff8000000000000ll) : s;
+            const double total = box_exchange(a.box, a.rank, a.world, a.seq, a.vsums, a.nvp, a.local_vshards,
+                                              a.seg0 / a.segs_per_vshard, NV, lane, &timed_out);
+            if (lane < NV) {
+                a.out_host[lane] = timed_out ? __longlong_as_double(0x7ff8000000000000ll) : total;
                 __threadfence_system();
             }
         }
@@ -630,37 +648,8 @@ __global__ void __launch_bounds__(BLOCK, MINB) dual_solve_kernel(const __grid_co
                 for (unsigned v = 1; v < a.local_vshards; ++v) total = addx(total, __ldcg(a.vsums + (unsigned long long) v * a.nvp + lane));
             }
         } else {
-            constexpr int kStride = 24, kFlagOff = 2 * 8 * kStride;
-            const unsigned long long seq = a.seq + my_gen;         // one mailbox sequence number per generation
-            const int buf = (int) (seq & 1ull);
-            const unsigned v0 = a.seg0 / a.segs_per_vshard;
-            if (lane < NV)
-                for (int r = 0; r < a.world; ++r)
-                    for (unsigned v = 0; v < a.local_vshards; ++v) {
-                        volatile double *dst = a.box[r] + ((unsigned long long) buf * 8 + v0 + v) * kStride + lane;
-                        *dst = __ldcg(a.vsums + (unsigned long long) v * a.nvp + lane);
-                    }
-            __threadfence_system();
-            __syncwarp();
-            if (lane < a.world) {
-                volatile unsigned long long *f =
-                    reinterpret_cast<volatile unsigned long long *>(a.box[lane] + kFlagOff) + buf * 8 + a.rank;
-                *f = seq;
-            }
-            if (lane < a.world) {
-                volatile unsigned long long *f =
-                    reinterpret_cast<volatile unsigned long long *>(a.box[a.rank] + kFlagOff) + buf * 8 + lane;
-                const long long t0 = clock64();
-                while (*f != seq)
-                    if (clock64() - t0 > 20000000000ll) { timed_out = 1; break; }
-            }
-            timed_out = __any_sync(0xffffffffu, timed_out);
-            __threadfence_system();
-            if (lane < NV) {
-                volatile double *rec = a.box[a.rank] + (unsigned long long) buf * 8 * kStride + lane;
-                total = rec[0];
-                for (int v = 1; v < kVirtualShards; ++v) total = addx(total, rec[v * kStride]);
-            }
+            total = box_exchange(a.box, a.rank, a.world, a.seq + my_gen, a.vsums, a.nvp, a.local_vshards,
+                                 a.seg0 / a.segs_per_vshard, NV, lane, &timed_out);     // one tag per generation
         }
 
         // ---- the dual optimiser's turn (one lane; the machine is staged through shared memory) ----

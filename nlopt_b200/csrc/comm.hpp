@@ -26,10 +26,11 @@ struct Comm {
     // (NVLink peer stores).  The dual kernel's last warp writes this rank's shard sums straight into
     // every peer's mailbox, raises a per-rank flag and spins until all peers' flags for this sequence
     // number arrive -- the all-gather happens inside the kernel, no NCCL call, no second launch.
-    // Layout (doubles): [2 buffers][8 virtual shards][kBoxStride] | flags: [2 buffers][8 ranks] (u64).
+    // Layout: [2 buffers][8 virtual shards][kBoxStride] slots of 16 bytes {double value; u64 tag}.  Value and
+    // tag (= the exchange's sequence number) travel in ONE 128-bit store, so a reader that sees the tag
+    // also sees the value: no fences, no separate flag (the "LL128" idea of NCCL's low-latency protocol).
     static constexpr int kBoxStride = 24;
-    static constexpr int kBoxFlagOffset = 2 * 8 * kBoxStride;          // in doubles
-    static constexpr int kBoxDoubles = kBoxFlagOffset + 2 * 8;
+    static constexpr int kBoxDoubles = 2 * 8 * kBoxStride * 2;
     double *box_peer[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     bool p2p_ready = false;
     bool use_p2p() const { return p2p_ready && !force_nccl_; }

@@ -101,7 +101,7 @@ public:
         std::lock_guard<std::mutex> g(mu_);
         auto &pool = pinned ? pinned_ : device_;
         pool.emplace(bytes, p);
-        while (pool.size() > 4) {                 // keep the cache small: drop the smallest block
+        while (pool.size() > 48) {                // keep the cache bounded: drop the smallest block
             auto it = pool.begin();
             if (pinned) cudaFreeHost(it->second); else cudaFree(it->second);
             pool.erase(it);
@@ -131,7 +131,7 @@ cudaError_t cached_malloc(double **p, size_t bytes)
 cudaError_t cached_host_alloc(double **p, size_t bytes)
 {
     if (void *q = BlockCache::get().take(true, bytes)) { *p = (double *) q; return cudaSuccess; }
-    return cudaHostAlloc(p, bytes, cudaHostAllocDefault);
+    return cudaHostAlloc(p, bytes, cudaHostAllocMapped);
 }
 
 int pick_maxm(int m) { return m == 0 ? 0 : m <= 1 ? 1 : m <= 2 ? 2 : m <= 4 ? 4 : m <= 8 ? 8 : 16; }
@@ -166,20 +166,11 @@ void DeviceBackend::free_state()
     if (pool_) BlockCache::get().give(false, pool_bytes_, pool_);
     if (w_dev_) cudaFree(w_dev_);
     if (xtol_abs_dev_) cudaFree(xtol_abs_dev_);
-    if (partials_) cudaFree(partials_);
-    if (grouprecs_) cudaFree(grouprecs_);
-    if (group_tickets_) cudaFree(group_tickets_);
-    if (vsums_) cudaFree(vsums_);
-    if (out_dev_) cudaFree(out_dev_);
-    if (tickets_) cudaFree(tickets_);
+    for (const Owned &o : owned_) BlockCache::get().give(o.pinned, o.bytes, o.p);   // every small buffer
+    owned_.clear();
     if (xfull_dev_) cudaFree(xfull_dev_);
-    if (scalar_dev_) cudaFree(scalar_dev_);
-    if (solve_state_) cudaFree(solve_state_);
-    if (res_host_) cudaFreeHost(res_host_);
     solve_state_ = nullptr;
     res_host_ = nullptr;
-    if (out_host_) cudaFreeHost(out_host_);
-    if (flag_host_) cudaFreeHost(flag_host_);
     if (h_x_) BlockCache::get().give(true, (size_t) geo_.n * sizeof(double), h_x_);
     for (int b = 0; b < 2; ++b) {
         if (h_grad_[b]) BlockCache::get().give(true, h_grad_cap_ * sizeof(double), h_grad_[b]);
@@ -223,11 +214,7 @@ bool DeviceBackend::alloc_state()
     if (m_ > (unsigned) kMaxParamM)
         return fail("more than 32 inequality constraints are not supported by this build of the dual kernel");
 
-    {
-        cudaDeviceProp prop;
-        NB_CUDA(cudaGetDeviceProperties(&prop, device_));
-        sm_count_ = prop.multiProcessorCount;
-    }
+    NB_CUDA(cudaDeviceGetAttribute(&sm_count_, cudaDevAttrMultiProcessorCount, device_));
     NB_CUDA(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
     NB_CUDA(cudaStreamCreateWithFlags(&copy_stream_, cudaStreamNonBlocking));
     NB_CUDA(cudaEventCreateWithFlags(&copied_, cudaEventDisableTiming));
@@ -246,29 +233,58 @@ bool DeviceBackend::alloc_state()
     return alloc_workspace();
 }
 
+// small buffers go through the same cache (cudaMalloc / cudaHostAlloc / cudaFree are slow and synchronising);
+// they are handed back in free_state()
+bool DeviceBackend::small_dev(void **p, size_t bytes)
+{
+    double *q = nullptr;
+    if (cached_malloc(&q, bytes) != cudaSuccess) return fail("cudaMalloc", cudaGetLastError());
+    *p = q;
+    owned_.push_back({q, bytes, false});
+    return true;
+}
+
+bool DeviceBackend::small_pinned(void **p, size_t bytes)
+{
+    double *q = nullptr;
+    if (cached_host_alloc(&q, bytes) != cudaSuccess) return fail("cudaHostAlloc", cudaGetLastError());
+    *p = q;
+    owned_.push_back({q, bytes, true});
+    return true;
+}
+
+void DeviceBackend::release_small(void *p)
+{
+    for (size_t i = 0; i < owned_.size(); ++i)
+        if (owned_[i].p == p) {
+            BlockCache::get().give(owned_[i].pinned, owned_[i].bytes, p);
+            owned_.erase(owned_.begin() + (long) i);
+            return;
+        }
+}
+
 bool DeviceBackend::alloc_workspace()
 {
-    if (partials_) { cudaFree(partials_); partials_ = nullptr; }
-    if (grouprecs_) { cudaFree(grouprecs_); grouprecs_ = nullptr; }
-    if (group_tickets_) { cudaFree(group_tickets_); group_tickets_ = nullptr; }
-    if (vsums_) { cudaFree(vsums_); vsums_ = nullptr; }
+    if (partials_) { release_small(partials_); partials_ = nullptr; }
+    if (grouprecs_) { release_small(grouprecs_); grouprecs_ = nullptr; }
+    if (vsums_) { release_small(vsums_); vsums_ = nullptr; }
     {
         const int maxm = pick_maxm((int) m_);
         const int nv = 3 + (maxm > 0 ? maxm : 1);
         nvp_ = (nv + 3) / 4 * 4;                  // records are multiples of 32 bytes
     }
     const size_t ng = geo_.nseg_local;
-    NB_CUDA(cudaMalloc(&partials_, ng * nvp_ * sizeof(double)));   // end_outer_kernel: one record per group
-    NB_CUDA(cudaMalloc(&grouprecs_, ng * nvp_ * sizeof(double)));
-    NB_CUDA(cudaMalloc(&vsums_, (size_t) kV * 24 * sizeof(double)));
-    if (!out_dev_) NB_CUDA(cudaMalloc(&out_dev_, (size_t) kV * 24 * sizeof(double)));
+    if (!small_dev((void **) &partials_, ng * nvp_ * sizeof(double))) return false;   // end_outer_kernel: one record per group
+    if (!small_dev((void **) &grouprecs_, ng * nvp_ * sizeof(double))) return false;
+    if (!small_dev((void **) &vsums_, (size_t) kV * 24 * sizeof(double))) return false;
+    if (!out_dev_ && !small_dev((void **) &out_dev_, (size_t) kV * 24 * sizeof(double) + 64)) return false;
     if (!tickets_) {
-        NB_CUDA(cudaMalloc(&tickets_, (kV + 1) * sizeof(unsigned)));
+        if (!small_dev((void **) &tickets_, 256)) return false;
         NB_CUDA(cudaMemsetAsync(tickets_, 0, (kV + 1) * sizeof(unsigned), stream_));
     }
     if (!out_host_) {
-        NB_CUDA(cudaHostAlloc(&out_host_, 24 * sizeof(double), cudaHostAllocMapped));
-        NB_CUDA(cudaHostAlloc(&flag_host_, 64, cudaHostAllocMapped));
+        if (!small_pinned((void **) &out_host_, 24 * sizeof(double))) return false;
+        if (!small_pinned((void **) &flag_host_, 128)) return false;
         *flag_host_ = 0;
     }
     NB_CUDA(cudaStreamSynchronize(stream_));
@@ -327,7 +343,7 @@ bool DeviceBackend::setup(const BackendConfig &cfg)
         if (Comm::instance().active())
             NB_CUDA(cudaMalloc(&xfull_dev_, (size_t) Comm::instance().world * shard_cap_ * sizeof(double)));
     }
-    if (Comm::instance().active()) NB_CUDA(cudaMalloc(&scalar_dev_, 64 * sizeof(double)));
+    if (Comm::instance().active() && !small_dev((void **) &scalar_dev_, 64 * sizeof(double))) return false;
     if (cfg.x0_host) {
         NB_CUDA(cudaMemcpyAsync(x_, cfg.x0_host + j0, nl * sizeof(double), cudaMemcpyHostToDevice, stream_));
         stats_->h2d_bytes += nl * sizeof(double);
@@ -634,6 +650,9 @@ SolveKernel pick_solve_kernel(int maxm)
 
 bool DeviceBackend::supports_dual_solve() const
 {
+    // several ranks: the in-kernel optimiser needs the in-kernel (mailbox) exchange
+    const Comm &cm = Comm::instance();
+    if (cm.active() && !cm.use_p2p()) return false;
     return fused_solve_ok_ && m_ >= 1 && m_ <= 16;
 }
 
@@ -641,9 +660,9 @@ bool DeviceBackend::dual_solve(double *y, const double *lo, const double *hi, co
                                DualSums *out, int *ret, long *nevals)
 {
     if (!solve_state_) {
-        NB_CUDA(cudaMalloc(&solve_state_, sizeof(SolveState)));
+        if (!small_dev(&solve_state_, (sizeof(SolveState) + 255) / 256 * 256)) return false;
         NB_CUDA(cudaMemsetAsync(solve_state_, 0, sizeof(SolveState), stream_));
-        NB_CUDA(cudaHostAlloc(&res_host_, 64 * sizeof(double), cudaHostAllocMapped));
+        if (!small_pinned((void **) &res_host_, 64 * sizeof(double))) return false;
     }
     SolveArgs sa;
     fill_dual_args(sa.d, y, sc, 0, (int) m_);

@@ -69,6 +69,11 @@ private:
     bool host_x_for(Slot slot);                      // bring the slot's x to pinned host memory (cached per epoch)
     bool push_grad_rows(Slot slot, int row0, unsigned rows, bool is_objective, const double *host_grad);
     double *staging(unsigned rows);
+    struct Owned { void *p; size_t bytes; bool pinned; };
+    std::vector<Owned> owned_;                       // small buffers borrowed from the block cache
+    bool small_dev(void **p, size_t bytes);
+    bool small_pinned(void **p, size_t bytes);
+    void release_small(void *p);
 
     BackendConfig cfg_;
     Variant variant_ = kMMA;
