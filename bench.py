@@ -4,22 +4,26 @@
 Workload (config.workload): BASELINE configs[2] -- NLOPT_LD_CCSAQ on the n = 1e7 chained-Rosenbrock
 problem with m = 4 dense linear inequality constraints, fp64, box [-2,2]^n.
 
-  step      = one inner CCSA iteration: one dual solve (K_i launches of the fused dual-evaluation
-              kernel, driven by the host-side m-dimensional dual optimiser), the final evaluation
-              that materialises x*(y), one objective + constraint evaluation, acceptance.
+  step      = one inner CCSA iteration: one dual solve (K_i dual evaluations -- by default inside ONE
+              persistent dual_solve_kernel launch that also runs the m-dimensional dual optimiser; with
+              b200_fused_solve=0 K_i launches of dual_eval_kernel driven from the host), the final
+              evaluation that materialises x*(y), one objective + constraint evaluation, acceptance.
               `--steps K` runs exactly K of them (maxeval = K + 1), `--warmup W` a separate
               W-iteration run first.
   value     = dual evaluations / second with everything resident in HBM (__device__ objective and
-              constraints, x on the device): total launches of the dual kernel in the K steps /
-              device-timed duration of the nlopt_b200_optimize_device call.
+              constraints, x on the device): dual evaluations performed in the K steps /
+              device-timed duration of the nlopt_b200_optimize_device call (setup, objective and
+              constraint evaluations, acceptance and stopping tests included).
   e2e       = the same through plain nlopt_optimize(): HOST x, HOST callbacks (C functions of
               libnlopt_b200_problems.so); every step pulls x*(y) to pinned host memory and pushes
               (1+m) gradient rows back.  Rate = dual evaluations / (wall - time inside the user's
               callbacks), the definition BASELINE.md uses for the reference; the rate including
               callback time is reported next to it.
-  roofline  = dominant kernel (dual_eval_kernel): algorithmic bytes 8 n (5+m) per launch (+8 n on
-              the launches that store x*), divided by the CUDA-event duration of those launches
-              measured inside the timed region, against MEASURED_PEAKS.json hbm_gbs.
+  roofline  = dominant kernel (dual_solve_kernel / dual_eval_kernel): algorithmic bytes 8 n (5+m) per
+              dual evaluation (+8 n on the evaluations that store x*), divided by the CUDA-event
+              duration of those kernels measured inside the timed region (for the persistent kernel
+              this includes its in-kernel optimiser steps and generation hand-offs), against
+              MEASURED_PEAKS.json hbm_gbs.
   cpu_baseline / --impl reference = the reference's own dual_func (oracle/_ref, include-trick on
               the unmodified src/algs/mma/ccsa_quadratic.c) on the same arrays, one thread.
 
@@ -73,7 +77,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -326,7 +330,7 @@ def main():
                                                      "seconds_glue_wall", "seconds_dual_kernel")},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": (achieved / peak) if achieved else None, "traffic": traffic,
-                         "kernel": "dual_eval_kernel", "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650",
+                         "kernel": "dual_solve_kernel (persistent; sweeps = dual_eval_kernel body)", "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650",
                          "avg_launch_us": 1e6 * kern_s / max(1, sd["dual_evals"]),
                          "kernel_share_of_step": kern_s / (ms_dev * 1e-3)},
             "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks, "gpu_launches": int(launches_dev),
