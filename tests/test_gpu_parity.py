@@ -299,6 +299,89 @@ def test_fused_dual_solve_equals_one_launch_per_evaluation(built, variant):
     assert pair[0]["minf"] == pair[1]["minf"] and np.array_equal(pair[0]["x"], pair[1]["x"])
 
 
+@pytest.mark.parametrize("variant", [ob.MMA, ob.CCSAQ])
+def test_device_functor_problems_match_host_callbacks(built, variant):
+    """bench.py's __device__ objective / constraints (nlopt_b200/csrc/problems.cu through
+    include/nlopt_b200_device.cuh) against the numpy host callbacks of tests/problems.py and against the
+    plain-C host callbacks of the same library: gradients are bit-identical, values differ only in
+    summation order, so short runs must agree to rounding."""
+    import torch
+    from nlopt_b200.problems import Problem
+    alg = nl.LD_MMA if variant == ob.MMA else nl.LD_CCSAQ
+    n, m = 20001, 4
+    x0 = P.rosen_x0(n)
+    # (a) device functors, x on the device
+    od = nl.opt(alg, n); od.set_lower_bounds(-2.0); od.set_upper_bounds(2.0); od.set_maxeval(20)
+    pd = Problem(); pd.rosenbrock_device(od, m)
+    xd = torch.from_numpy(x0.copy()).cuda()
+    od.optimize_device(xd.data_ptr())
+    # (b) plain-C host callbacks through nlopt_optimize
+    oh = nl.opt(alg, n); oh.set_lower_bounds(-2.0); oh.set_upper_bounds(2.0); oh.set_maxeval(20)
+    ph = Problem(); ph.rosenbrock_host(oh, m)
+    xh = oh.optimize(x0)
+    # (c) numpy host callbacks
+    cons = [P.lin_constraint(k, n) for k in range(m)]
+    r = _run(alg, n, P.rosen_f, cons, [1e-8] * m, np.full(n, -2.0), np.full(n, 2.0), x0, maxeval=20)
+    for got_f, got_x, evals in ((od.last_optimum_value(), xd.cpu().numpy(), od.get_numevals()),
+                                (oh.last_optimum_value(), xh, oh.get_numevals())):
+        assert evals == r["numevals"] == 20
+        assert abs(got_f - r["minf"]) <= 1e-9 * abs(r["minf"])
+        assert np.max(np.abs(got_x - r["x"])) <= 1e-7
+    # separable quadratic + mean constraint (config-2 shape) on the device vs numpy
+    n = 30000
+    f, c = P.quad_problem(n)
+    oq = nl.opt(alg, n); oq.set_lower_bounds(-1.0); oq.set_upper_bounds(1.0); oq.set_maxeval(15)
+    pq = Problem(); pq.quadratic_device(oq)
+    xq = torch.full((n,), -0.5, dtype=torch.float64, device="cuda")
+    oq.optimize_device(xq.data_ptr())
+    rq = _run(alg, n, f, [c], [0.0], np.full(n, -1.0), np.full(n, 1.0), np.full(n, -0.5), maxeval=15)
+    assert oq.get_numevals() == rq["numevals"]
+    assert abs(oq.last_optimum_value() - rq["minf"]) <= 1e-9 * abs(rq["minf"])
+    assert np.max(np.abs(xq.cpu().numpy() - rq["x"])) <= 1e-7
+
+
+def test_weights_abs_tolerance_vector_constraint_and_maximize_on_gpu(built):
+    """the remaining option surface of the path end to end on the device: x_weights / xtol_abs
+    (stop.c:98-108), a vector-valued constraint (nlopt_add_inequality_mconstraint), maximisation."""
+    lb, ub = [-np.inf, 0.0], [np.inf, np.inf]
+    cons, tols = [P.tut_c(2, 0), P.tut_c(-1, 1)], [1e-8, 1e-8]
+    ref = ob.port_minimize(ob.MMA, P.tut_f, cons, tols, lb, ub, P.TUT_X0, xtol_rel=1e-4, x_weights=[1.0, 3.0])
+    o = nl.opt(nl.LD_MMA, 2); o.set_lower_bounds(lb); o.set_min_objective(P.tut_f)
+    for c in cons:
+        o.add_inequality_constraint(c, 1e-8)
+    o.set_xtol_rel(1e-4); o.set_x_weights([1.0, 3.0])
+    x = o.optimize(P.TUT_X0)
+    assert o.last_optimize_result() == ref["ret"] and abs(o.last_optimum_value() - ref["minf"]) <= 1e-6
+    ref = ob.port_minimize(ob.CCSAQ, P.tut_f, cons, tols, lb, ub, P.TUT_X0, xtol_abs=[1e-3, 1e-3])
+    o = nl.opt(nl.LD_CCSAQ, 2); o.set_lower_bounds(lb); o.set_min_objective(P.tut_f)
+    for c in cons:
+        o.add_inequality_constraint(c, 1e-8)
+    o.set_xtol_abs(1e-3)
+    x = o.optimize(P.TUT_X0)
+    assert o.last_optimize_result() == ref["ret"] == nl.XTOL_REACHED and abs(o.last_optimum_value() - ref["minf"]) <= 1e-5
+    # vector constraint == two scalar constraints
+    a = _run(nl.LD_MMA, 2, P.tut_f, cons, tols, lb, ub, P.TUT_X0, xtol_rel=1e-4)
+    o = nl.opt(nl.LD_MMA, 2); o.set_lower_bounds(lb); o.set_min_objective(P.tut_f); o.set_xtol_rel(1e-4)
+
+    def both(result, xx, grad):
+        result[0] = cons[0](xx, grad[0] if grad.size else grad)
+        result[1] = cons[1](xx, grad[1] if grad.size else grad)
+    o.add_inequality_mconstraint(both, [1e-8, 1e-8])
+    x = o.optimize(P.TUT_X0)
+    assert np.array_equal(x, a["x"]) and o.last_optimum_value() == a["minf"]
+    # maximise -f
+    def negf(xx, g):
+        v = P.tut_f(xx, g)
+        if g.size:
+            g[:] = -g
+        return -v
+    o = nl.opt(nl.LD_MMA, 2); o.set_lower_bounds(lb); o.set_max_objective(negf); o.set_xtol_rel(1e-4)
+    for c in cons:
+        o.add_inequality_constraint(c, 1e-8)
+    x = o.optimize(P.TUT_X0)
+    assert np.array_equal(x, a["x"]) and o.last_optimum_value() == -a["minf"]
+
+
 def test_device_path_has_no_cpu_fallback_symbols(built):
     """the product library must not contain or import anything from the oracle"""
     import subprocess, nlopt_b200._capi as capi
