@@ -463,6 +463,194 @@ __global__ void __launch_bounds__(BLOCK, MINB) dual_eval_kernel(const __grid_con
     }
 }
 
+// ---- the dual evaluation kernel, TMA-staged form -------------------------------------------------------------
+// Same groups, same per-warp accumulators, same fold tree (=> same bits) as dual_eval_kernel; what changes is
+// how the operands arrive.  A producer warp issues 1-D TMA bulk copies (cp.async.bulk + mbarrier
+// complete_tx): one 4 KB chunk of each of the 5+m arrays per stage, STAGES stages deep, running ahead
+// across group boundaries so the pipeline never drains.  The 8 consumer warps wait on the stage's "full"
+// barrier, read their double2 lanes from shared memory, and release the stage on its "empty" barrier.
+// No load ever occupies a consumer register before it is needed, so many more bytes are in flight per SM
+// than the register form can hold at the same occupancy.
+__device__ __forceinline__ unsigned smem_addr(const void *p) { return (unsigned) __cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity)
+{
+    unsigned ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(smem_addr(bar)), "r"(parity) : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void tma_bulk_load(void *smem_dst, const void *gmem_src, unsigned bytes, unsigned long long *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_addr(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_addr(bar)) : "memory");
+}
+
+constexpr int kTmaBlock = 32 * (kGroupWarps + 1);        // 8 consumer warps + 1 producer warp
+constexpr unsigned kChunkBytes = kChunkPairs * 16;       // 4 KB per array per stage
+
+template <int VARIANT, int MAXM, bool STORE, int STAGES, int MINB>
+__global__ void __launch_bounds__(kTmaBlock, MINB) dual_eval_tma_kernel(const __grid_constant__ DualArgs a)
+{
+    constexpr int MR = MAXM > 0 ? MAXM : 1;
+    constexpr int NV = 3 + MR;
+    constexpr int NARR = 5 + MAXM;                            // x lb ub sigma g + MAXM gradient rows
+    extern __shared__ __align__(128) unsigned char s_raw[];
+    double2 *s_tile = reinterpret_cast<double2 *>(s_raw);     // [STAGES][NARR][kChunkPairs]
+    __shared__ unsigned long long s_full[STAGES], s_empty[STAGES];
+    __shared__ double s_rec[2][kGroupWarps * NV];
+
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const unsigned ngroups = a.segs_per_vshard * a.local_vshards;
+
+    if (threadIdx.x == 0) {
+        for (int st = 0; st < STAGES; ++st) {
+            mbar_init(&s_full[st], 1);                        // one arrive.expect_tx by the producer
+            mbar_init(&s_empty[st], kGroupWarps);             // one arrive per consumer warp
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (warp == kGroupWarps) {
+        // ---------------- producer ----------------
+        if (lane == 0) {
+            const double *src[NARR];
+            src[0] = a.x; src[1] = a.lb; src[2] = a.ub; src[3] = a.sigma; src[4] = a.g;
+#pragma unroll
+            for (int i = 0; i < MAXM; ++i) src[5 + i] = a.G + (unsigned long long) i * a.ld;
+            int st = 0;
+            unsigned phase = 0;
+            for (unsigned gl = blockIdx.x; gl < ngroups; gl += gridDim.x) {
+                unsigned long long p_lo, p_hi;
+                group_pairs(a.nchunks, a.nseg_total, a.chunk0, a.seg0 + gl, &p_lo, &p_hi);
+                for (unsigned long long p = p_lo; p < p_hi; p += kChunkPairs) {
+                    mbar_wait(&s_empty[st], phase ^ 1u);      // passes at once on a fresh barrier
+                    mbar_expect_tx(&s_full[st], NARR * kChunkBytes);
+#pragma unroll
+                    for (int k = 0; k < NARR; ++k)
+                        tma_bulk_load(s_tile + ((size_t) st * NARR + k) * kChunkPairs, src[k] + 2 * p, kChunkBytes, &s_full[st]);
+                    if (++st == STAGES) { st = 0; phase ^= 1u; }
+                }
+            }
+        }
+        return;
+    }
+
+    // ---------------- consumers ----------------
+    const int sub = warp;
+    int st = 0;
+    unsigned phase = 0;
+    int parity = 0;
+    for (unsigned gl = blockIdx.x; gl < ngroups; gl += gridDim.x) {
+        unsigned long long p_lo, p_hi;
+        group_pairs(a.nchunks, a.nseg_total, a.chunk0, a.seg0 + gl, &p_lo, &p_hi);
+        double acc[NV];
+#pragma unroll
+        for (int k = 0; k < NV; ++k) acc[k] = 0.0;
+        for (unsigned long long p = p_lo; p < p_hi; p += kChunkPairs) {
+            mbar_wait(&s_full[st], phase);
+            const double2 *t = s_tile + (size_t) st * NARR * kChunkPairs + sub * 32 + lane;
+            const double2 vx = t[0], vlb = t[kChunkPairs], vub = t[2 * kChunkPairs], vs = t[3 * kChunkPairs],
+                          vg = t[4 * kChunkPairs];
+            double Ga[MR], Gb[MR];
+#pragma unroll
+            for (int i = 0; i < MR; ++i) {
+                Ga[i] = 0.0; Gb[i] = 0.0;
+                if (MAXM > 0) { const double2 g2 = t[(5 + i) * kChunkPairs]; Ga[i] = g2.x; Gb[i] = g2.y; }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s_empty[st]);         // operands are in registers: release the stage
+            if (++st == STAGES) { st = 0; phase ^= 1u; }
+            double2 xc;
+            if (VARIANT == 0) {
+                xc.x = mma_point<MAXM, true>(a, vx.x, vlb.x, vub.x, vs.x, vg.x, Ga, nullptr, a.ld, acc);
+                xc.y = mma_point<MAXM, true>(a, vx.y, vlb.y, vub.y, vs.y, vg.y, Gb, nullptr, a.ld, acc);
+            } else {
+                xc.x = ccsaq_point<MAXM, true>(a, vx.x, vlb.x, vub.x, vs.x, vg.x, Ga, nullptr, a.ld, acc);
+                xc.y = ccsaq_point<MAXM, true>(a, vx.y, vlb.y, vub.y, vs.y, vg.y, Gb, nullptr, a.ld, acc);
+            }
+            if (STORE) st_stream(reinterpret_cast<double2 *>(a.xcur) + p + sub * 32 + lane, xc);
+        }
+
+        warp_fold<NV>(acc);
+        double *srec = s_rec[parity];
+        if (lane == 0) {
+#pragma unroll
+            for (int k = 0; k < NV; ++k) srec[sub * NV + k] = acc[k];
+        }
+        asm volatile("bar.sync 1, %0;" ::"r"(32 * kGroupWarps) : "memory");      // the 8 consumer warps only
+        parity ^= 1;
+        if (sub != 0) continue;
+        if (lane < NV) {
+            double s = srec[lane];
+#pragma unroll
+            for (int w = 1; w < kGroupWarps; ++w) s = addx(s, srec[w * NV + lane]);
+            a.grouprecs[(unsigned long long) gl * a.nvp + lane] = s;
+        }
+        __syncwarp();
+        const unsigned vs_local = gl / a.segs_per_vshard;
+        if (!warp_is_last(a.tickets + vs_local, a.segs_per_vshard, lane)) continue;
+#pragma unroll
+        for (int k = 0; k < NV; ++k) acc[k] = 0.0;
+        {
+            const double *base = a.grouprecs + (unsigned long long) vs_local * a.segs_per_vshard * a.nvp;
+            for (unsigned r = lane; r < a.segs_per_vshard; r += 32)
+#pragma unroll
+                for (int k = 0; k < NV; ++k) acc[k] = addx(acc[k], __ldcg(base + (unsigned long long) r * a.nvp + k));
+        }
+        warp_fold<NV>(acc);
+        if (lane == 0) {
+            double *rec = a.vsums + (unsigned long long) vs_local * a.nvp;
+#pragma unroll
+            for (int k = 0; k < NV; ++k) rec[k] = acc[k];
+        }
+        if (!warp_is_last(a.tickets + a.local_vshards, a.local_vshards, lane)) continue;
+        if (lane < NV) {
+            if (a.publish_host) {
+                double s = __ldcg(a.vsums + lane);
+                for (unsigned v = 1; v < a.local_vshards; ++v) s = addx(s, __ldcg(a.vsums + (unsigned long long) v * a.nvp + lane));
+                a.out_host[lane] = s;
+                __threadfence_system();
+            } else if (a.box[0] == nullptr) {
+                const unsigned v0 = a.seg0 / a.segs_per_vshard;
+                for (unsigned v = 0; v < a.local_vshards; ++v)
+                    a.out_dev[(unsigned long long) (v0 + v) * a.nvp + lane] = __ldcg(a.vsums + (unsigned long long) v * a.nvp + lane);
+            }
+        }
+        if (!a.publish_host && a.box[0] != nullptr) {
+            int timed_out = 0;
+            const double total = box_exchange(a.box, a.rank, a.world, a.seq, a.vsums, a.nvp, a.local_vshards,
+                                              a.seg0 / a.segs_per_vshard, NV, lane, &timed_out);
+            if (lane < NV) {
+                a.out_host[lane] = timed_out ? __longlong_as_double(0x7ff8000000000000ll) : total;
+                __threadfence_system();
+            }
+        }
+        __syncwarp();
+        if (lane == 0) {
+            for (unsigned v = 0; v <= a.local_vshards; ++v) a.tickets[v] = 0;
+            if (a.publish_host || a.box[0] != nullptr) {
+                *a.flag_host = a.seq;
+                __threadfence_system();
+            }
+        }
+    }
+}
+
 // ---- the persistent dual-SOLVE kernel: one launch per dual solve ------------------------------------------
 //   The m-dimensional dual optimiser (DualMachine, dual_mma.hpp -- the same code the
 // host runs) moves into the kernel: all CTAs stay resident (cooperative launch) and walk *generations*.

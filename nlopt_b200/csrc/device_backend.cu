@@ -70,6 +70,25 @@ DualKernel pick_kernel(int maxm, int cfg, bool store)
     }
 }
 
+// TMA-staged variant (kernel_cfg 10/11/12 = 3/2/4 stages): full-m cases only
+template <int VARIANT, int MAXM, int STAGES, int MINB>
+DualKernel tma_kernel_for(bool store)
+{
+    return store ? (DualKernel) dual_eval_tma_kernel<VARIANT, MAXM, true, STAGES, MINB>
+                 : (DualKernel) dual_eval_tma_kernel<VARIANT, MAXM, false, STAGES, MINB>;
+}
+
+template <int VARIANT>
+DualKernel pick_tma_kernel(int maxm, int stages, bool store)
+{
+    switch (maxm) {
+    case 1: return stages == 2 ? tma_kernel_for<VARIANT, 1, 2, 3>(store) : stages == 4 ? tma_kernel_for<VARIANT, 1, 4, 2>(store) : tma_kernel_for<VARIANT, 1, 3, 3>(store);
+    case 4: return stages == 2 ? tma_kernel_for<VARIANT, 4, 2, 3>(store) : stages == 4 ? tma_kernel_for<VARIANT, 4, 4, 1>(store) : tma_kernel_for<VARIANT, 4, 3, 2>(store);
+    case 16: return stages == 2 ? tma_kernel_for<VARIANT, 16, 2, 1>(store) : tma_kernel_for<VARIANT, 16, 2, 1>(store);
+    default: return nullptr;
+    }
+}
+
 // measured best geometry per (variant, rows in registers)
 int default_cfg(Variant v, int maxm)
 {
@@ -580,9 +599,24 @@ bool DeviceBackend::launch_dual(const double *y, const DualScalars &sc, bool sto
         e1 = ev_pool_[ev_used_++];
         cudaEventRecord(e0, stream_);
     }
-    {
+    const bool full_m = (int) m_ == maxm && (variant_ == kCCSAQ || a.active == (m_ >= 32 ? 0xffffffffu : ((1u << m_) - 1u)));
+    if (kernel_cfg_ >= 10 && kernel_cfg_ <= 12 && full_m && (maxm == 1 || maxm == 4 || maxm == 16)) {
+        // TMA-staged form: producer warp + 8 consumer warps, dynamic shared memory = stages x (5+m) x 4 KB
+        int stages = kernel_cfg_ == 10 ? 3 : kernel_cfg_ == 11 ? 2 : 4;
+        if (maxm == 16) stages = 2;
+        DualKernel fn = variant_ == kMMA ? pick_tma_kernel<0>(maxm, stages, store) : pick_tma_kernel<1>(maxm, stages, store);
+        const size_t smem = (size_t) stages * (5 + maxm) * kChunkBytes;
+        NB_CUDA(cudaFuncSetAttribute((const void *) fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+        int per_sm = 0;
+        NB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kTmaBlock, smem));
+        if (per_sm < 1) return fail("dual_eval_tma_kernel does not fit on an SM");
+        long long pgrid = (long long) sm_count_ * (ctas_per_sm_ > 0 ? ctas_per_sm_ : per_sm);
+        if (pgrid > (long long) geo_.nseg_local) pgrid = geo_.nseg_local;
+        fn<<<(unsigned) (pgrid < 1 ? 1 : pgrid), kTmaBlock, smem, stream_>>>(a);
+    } else {
         // persistent kernel: the grid is sized to the machine, not to the problem
         int cfg = kernel_cfg_ >= 0 && kernel_cfg_ < kNumCfgs ? kernel_cfg_ : default_cfg(variant_, maxm);
+        (void) full_m;
         if (maxm >= 8) cfg = 3;
         const KernelCfg c = kCfgs[cfg];
         const bool full = (int) m_ == maxm && (variant_ == kCCSAQ || a.active == (m_ >= 32 ? 0xffffffffu : ((1u << m_) - 1u)));

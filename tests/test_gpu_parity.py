@@ -56,7 +56,7 @@ def test_dual_kernel_vs_oracle(built, variant, n, m):
 
 
 @pytest.mark.parametrize("variant", [ob.MMA, ob.CCSAQ])
-@pytest.mark.parametrize("n,m", [(3, 1), (4097, 4), (300001, 4), (70000, 16), (9999, 20), (50000, 0), (200000, 3)])
+@pytest.mark.parametrize("n,m", [(3, 1), (4097, 4), (300001, 4), (70000, 16), (9999, 20), (50000, 0), (200000, 3), (1200000, 1)])
 def test_launch_geometry_independence(built, variant, n, m):
     """Every launch geometry of the persistent kernel (threads per CTA, chunks per sweep step, CTAs per
     SM, i.e. grid size): x* bit-exact, sums to rounding, and -- because a record never depends on which
@@ -64,7 +64,7 @@ def test_launch_geometry_independence(built, variant, n, m):
     inst = synth.kernel_instance(n, m)
     want = ob.port_dual(variant, inst)
     seen = []
-    for cfg, cps in ((-1, 0), (0, 1), (1, 5), (2, 2), (3, 8), (0, 12), (2, 1)):
+    for cfg, cps in ((-1, 0), (0, 1), (1, 5), (2, 2), (3, 8), (0, 12), (2, 1), (10, 0), (11, 0), (12, 1)):   # 10-12: TMA-staged
         h = DualHandle(variant, inst)
         h.configure("kernel_cfg", cfg)
         h.configure("ctas_per_sm", cps)

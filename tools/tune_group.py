@@ -48,6 +48,23 @@ def main():
                                          target_chunks=tc, groups=h.query("segments"), ms=t, gbs=byts / t / 1e6,
                                          frac=byts / t / 1e6 / peak))
                         print(json.dumps(rows[-1]), flush=True)
+            # TMA-staged variants (kernel_cfg 10 / 11 / 12 = 3 / 2 / 4 stages)
+            h.configure("target_chunks", 8)
+            for cfg in (10, 11, 12):
+                h.configure("kernel_cfg", cfg)
+                for cps in (0, 1, 2, 3, 4, 6):
+                    h.configure("ctas_per_sm", cps)
+                    try:
+                        h.time(y, 0, 4)
+                        t = min(h.time(y, 0, 25) for _ in range(3))
+                    except RuntimeError as e:
+                        print("fail", name, cfg, cps, e, flush=True)
+                        continue
+                    byts = 8.0 * n * (5 + m)
+                    rows.append(dict(n=n, m=m, variant=name, cfg=cfg, block=288, unroll=1, minb=0, ctas_per_sm=cps,
+                                     target_chunks=8, groups=h.query("segments"), ms=t, gbs=byts / t / 1e6,
+                                     frac=byts / t / 1e6 / peak))
+                    print(json.dumps(rows[-1]), flush=True)
             del h
     best = {}
     for r in rows:
