@@ -87,12 +87,20 @@ __device__ __forceinline__ double box_exchange(double *const *box, int rank, int
         }
         const double *mine = box[rank] + 2ull * ((unsigned long long) buf * 8 * kBoxStride + lane);
         const long long t0 = clock64();
-        for (int v = 0; v < kVirtualShards; ++v) {
-            double x;
-            while (!box_get(mine + 2ull * v * kBoxStride, seq, &x))
-                if (clock64() - t0 > 20000000000ll) { to = 1; break; }      // ~10 s: a peer died
-            total = v == 0 ? x : addx(total, x);
+        double x[kVirtualShards];
+        for (;;) {                         // all 8 slots are fetched together: one L2 round trip per poll
+            bool ok[kVirtualShards];
+#pragma unroll
+            for (int v = 0; v < kVirtualShards; ++v) ok[v] = box_get(mine + 2ull * v * kBoxStride, seq, &x[v]);
+            bool all = true;
+#pragma unroll
+            for (int v = 0; v < kVirtualShards; ++v) all = all && ok[v];
+            if (all) break;
+            if (clock64() - t0 > 20000000000ll) { to = 1; break; }          // ~10 s: a peer died
         }
+        total = x[0];
+#pragma unroll
+        for (int v = 1; v < kVirtualShards; ++v) total = addx(total, x[v]);
     }
     *timed_out = __any_sync(0xffffffffu, to);
     return total;
@@ -417,7 +425,8 @@ __global__ void __launch_bounds__(BLOCK, MINB) dual_eval_kernel(const __grid_con
         for (int k = 0; k < NV; ++k) acc[k] = 0.0;
         {
             const double *base = a.grouprecs + (unsigned long long) vs_local * a.segs_per_vshard * a.nvp;
-            for (unsigned r = lane; r < a.segs_per_vshard; r += 32)
+#pragma unroll 4
+            for (unsigned r = lane; r < a.segs_per_vshard; r += 32)      // loads of 4 rounds in flight, adds in order
 #pragma unroll
                 for (int k = 0; k < NV; ++k) acc[k] = addx(acc[k], __ldcg(base + (unsigned long long) r * a.nvp + k));
         }
@@ -608,7 +617,8 @@ __global__ void __launch_bounds__(kTmaBlock, MINB) dual_eval_tma_kernel(const __
         for (int k = 0; k < NV; ++k) acc[k] = 0.0;
         {
             const double *base = a.grouprecs + (unsigned long long) vs_local * a.segs_per_vshard * a.nvp;
-            for (unsigned r = lane; r < a.segs_per_vshard; r += 32)
+#pragma unroll 4
+            for (unsigned r = lane; r < a.segs_per_vshard; r += 32)      // loads of 4 rounds in flight, adds in order
 #pragma unroll
                 for (int k = 0; k < NV; ++k) acc[k] = addx(acc[k], __ldcg(base + (unsigned long long) r * a.nvp + k));
         }
@@ -808,7 +818,8 @@ __global__ void __launch_bounds__(BLOCK, MINB) dual_solve_kernel(const __grid_co
         for (int k = 0; k < NV; ++k) acc[k] = 0.0;
         {
             const double *base = a.grouprecs + (unsigned long long) vs_local * a.segs_per_vshard * a.nvp;
-            for (unsigned r = lane; r < a.segs_per_vshard; r += 32)
+#pragma unroll 4
+            for (unsigned r = lane; r < a.segs_per_vshard; r += 32)      // loads of 4 rounds in flight, adds in order
 #pragma unroll
                 for (int k = 0; k < NV; ++k) acc[k] = addx(acc[k], __ldcg(base + (unsigned long long) r * a.nvp + k));
         }
