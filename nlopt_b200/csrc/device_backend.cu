@@ -600,9 +600,13 @@ bool DeviceBackend::launch_dual(const double *y, const DualScalars &sc, bool sto
         cudaEventRecord(e0, stream_);
     }
     const bool full_m = (int) m_ == maxm && (variant_ == kCCSAQ || a.active == (m_ >= 32 ? 0xffffffffu : ((1u << m_) - 1u)));
-    if (kernel_cfg_ >= 10 && kernel_cfg_ <= 12 && full_m && (maxm == 1 || maxm == 4 || maxm == 16)) {
+    // MMA with 16 gradient rows is register-starved in the register form (64 % of peak); the TMA-staged form
+    // reaches 72 % (profiles/r01_tune_tma.jsonl) and is the default there.  Everywhere else the register
+    // form is faster and the TMA form is opt-in (kernel_cfg 10 / 11 / 12 = 3 / 2 / 4 stages).
+    const bool tma_default = kernel_cfg_ < 0 && variant_ == kMMA && maxm == 16 && full_m;
+    if ((tma_default || (kernel_cfg_ >= 10 && kernel_cfg_ <= 12)) && full_m && (maxm == 1 || maxm == 4 || maxm == 16)) {
         // TMA-staged form: producer warp + 8 consumer warps, dynamic shared memory = stages x (5+m) x 4 KB
-        int stages = kernel_cfg_ == 10 ? 3 : kernel_cfg_ == 11 ? 2 : 4;
+        int stages = kernel_cfg_ == 10 ? 3 : kernel_cfg_ == 11 ? 2 : kernel_cfg_ == 12 ? 4 : 2;
         if (maxm == 16) stages = 2;
         DualKernel fn = variant_ == kMMA ? pick_tma_kernel<0>(maxm, stages, store) : pick_tma_kernel<1>(maxm, stages, store);
         const size_t smem = (size_t) stages * (5 + maxm) * kChunkBytes;
@@ -610,7 +614,7 @@ bool DeviceBackend::launch_dual(const double *y, const DualScalars &sc, bool sto
         int per_sm = 0;
         NB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kTmaBlock, smem));
         if (per_sm < 1) return fail("dual_eval_tma_kernel does not fit on an SM");
-        long long pgrid = (long long) sm_count_ * (ctas_per_sm_ > 0 ? ctas_per_sm_ : per_sm);
+        long long pgrid = (long long) sm_count_ * (ctas_per_sm_ > 0 ? ctas_per_sm_ : 6);     // oversubscribed 2-3x: evens out the tail
         if (pgrid > (long long) geo_.nseg_local) pgrid = geo_.nseg_local;
         fn<<<(unsigned) (pgrid < 1 ? 1 : pgrid), kTmaBlock, smem, stream_>>>(a);
     } else {
@@ -669,13 +673,15 @@ bool DeviceBackend::dual_eval(const double *y, const DualScalars &sc, bool mater
 namespace {
 typedef void (*SolveKernel)(const SolveArgs);
 
+// `deep`: few groups per resident CTA (small shards, e.g. n = 1e7 over 8 GPUs) -- the sweep is then bound by
+// the latency of each sweep step, so two chunks per step are kept in flight instead of one
 template <int VARIANT, bool FULL>
-SolveKernel pick_solve_kernel(int maxm)
+SolveKernel pick_solve_kernel(int maxm, bool deep)
 {
     switch (maxm) {
-    case 1: return dual_solve_kernel<VARIANT, 1, FULL, 256, 1, 3>;
-    case 2: return dual_solve_kernel<VARIANT, 2, FULL, 256, 1, 3>;
-    case 4: return dual_solve_kernel<VARIANT, 4, FULL, 256, 1, 3>;
+    case 1: return deep ? dual_solve_kernel<VARIANT, 1, FULL, 256, 2, 3> : dual_solve_kernel<VARIANT, 1, FULL, 256, 1, 3>;
+    case 2: return deep ? dual_solve_kernel<VARIANT, 2, FULL, 256, 2, 3> : dual_solve_kernel<VARIANT, 2, FULL, 256, 1, 3>;
+    case 4: return deep ? dual_solve_kernel<VARIANT, 4, FULL, 256, 2, 3> : dual_solve_kernel<VARIANT, 4, FULL, 256, 1, 3>;
     case 8: return dual_solve_kernel<VARIANT, 8, FULL, 256, 1, 2>;
     default: return dual_solve_kernel<VARIANT, 16, FULL, 256, 1, 2>;
     }
@@ -687,6 +693,7 @@ bool DeviceBackend::supports_dual_solve() const
     // several ranks: the in-kernel optimiser needs the in-kernel (mailbox) exchange
     const Comm &cm = Comm::instance();
     if (cm.active() && !cm.use_p2p()) return false;
+    if (variant_ == kMMA && m_ > 8) return false;      // the TMA-staged evaluation kernel wins there (see launch_dual)
     return fused_solve_ok_ && m_ >= 1 && m_ <= 16;
 }
 
@@ -713,8 +720,9 @@ bool DeviceBackend::dual_solve(double *y, const double *lo, const double *hi, co
 
     const int maxm = pick_maxm((int) m_);
     const bool full = (int) m_ == maxm && (variant_ == kCCSAQ || sa.d.active == ((1u << m_) - 1u));
-    SolveKernel fn = variant_ == kMMA ? (full ? pick_solve_kernel<0, true>(maxm) : pick_solve_kernel<0, false>(maxm))
-                                      : (full ? pick_solve_kernel<1, true>(maxm) : pick_solve_kernel<1, false>(maxm));
+    const bool deep = solve_deep_ >= 0 ? solve_deep_ != 0 : (long long) geo_.nseg_local <= 3ll * sm_count_;
+    SolveKernel fn = variant_ == kMMA ? (full ? pick_solve_kernel<0, true>(maxm, deep) : pick_solve_kernel<0, false>(maxm, deep))
+                                      : (full ? pick_solve_kernel<1, true>(maxm, deep) : pick_solve_kernel<1, false>(maxm, deep));
     int per_sm = 0;
     NB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, 256, 0));
     if (per_sm < 1) return fail("dual_solve_kernel does not fit on an SM");
@@ -939,6 +947,7 @@ bool DeviceBackend::configure(const char *key, long long value)
     if (k == "kernel_cfg") { kernel_cfg_ = (int) value; return true; }
     if (k == "ctas_per_sm") { ctas_per_sm_ = (int) value; return true; }
     if (k == "fused_solve") { fused_solve_ok_ = value != 0; return true; }
+    if (k == "solve_deep") { solve_deep_ = (int) value; return true; }
     if (k == "pmax" || k == "target_chunks") {
         if (value < 1) return fail("bad value");
         if (k == "pmax") pmax_ = (unsigned) value; else target_chunks_ = (unsigned) value;
