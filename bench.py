@@ -88,17 +88,27 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(",")])
 
-    def stop(self):
+    def mark(self):
+        return len(self.rows)
+
+    def stop(self, i0=0, i1=None):
+        """summary of the samples taken between two mark()s (the timed region); if the region was too short to
+        catch one, the nearest samples around it are used and `window` says so"""
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.05)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
+        i1 = len(self.rows) if i1 is None else i1
+        rows, window = self.rows[i0:i1], "timed region"
+        if not rows:
+            rows, window = self.rows[max(0, i0 - 3):i1 + 3], "nearest samples around the (short) timed region"
         sm, mx, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for r in rows:
             try:
                 sm.append(float(r[0])); mx = float(r[1])
             except Exception:
@@ -107,7 +117,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(nm)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "window": window}
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -263,12 +273,14 @@ def main():
         od.set_maxeval(steps + 1)
         od.optimize_device(xdev.data_ptr())
 
-    run_dev(a.warmup)
     sampler = ClockSampler(local)
     if rank == 0:
-        sampler.start()
+        sampler.start()            # nvidia-smi needs ~0.1 s to deliver its first sample: start before the warm-up
+    run_dev(a.warmup)
+    i0 = sampler.mark()
     ms_dev = timed(run_dev, a.steps)
-    clocks = sampler.stop() if rank == 0 else None
+    i1 = sampler.mark()
+    clocks = sampler.stop(i0, i1) if rank == 0 else None
     sd = od.get_stats()
     f_dev = od.last_optimum_value()
     value = sd["dual_evals"] / (ms_dev * 1e-3)

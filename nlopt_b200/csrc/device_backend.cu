@@ -948,9 +948,11 @@ bool DeviceBackend::configure(const char *key, long long value)
     if (k == "ctas_per_sm") { ctas_per_sm_ = (int) value; return true; }
     if (k == "fused_solve") { fused_solve_ok_ = value != 0; return true; }
     if (k == "solve_deep") { solve_deep_ = (int) value; return true; }
-    if (k == "pmax" || k == "target_chunks") {
+    if (k == "pmax" || k == "target_chunks" || k == "fill_div") {
         if (value < 1) return fail("bad value");
-        if (k == "pmax") pmax_ = (unsigned) value; else target_chunks_ = (unsigned) value;
+        if (k == "pmax") pmax_ = (unsigned) value;
+        else if (k == "target_chunks") target_chunks_ = (unsigned) value;
+        else Geometry::fill_div() = (unsigned) value;
         if (pool_) {
             Geometry g2 = Geometry::make(geo_.n, geo_.world, geo_.rank, target_chunks_, pmax_);
             if (g2.ld != geo_.ld || g2.j0 != geo_.j0)

@@ -27,6 +27,9 @@ struct Geometry {
     unsigned long long j0 = 0, n_local = 0;      // this rank's variable range
     unsigned long long ld = 0;                   // padded local length: whole chunks (multiple of 512 doubles)
 
+    // tuning constant of choose_P (process-wide): groups wanted before groups start to grow
+    static unsigned &fill_div() { static unsigned v = 1776; return v; }
+
     static unsigned long long cut(unsigned s, unsigned long long nchunks, unsigned S)
     {
         return (unsigned long long) s * nchunks / S;
@@ -36,7 +39,7 @@ struct Geometry {
     // groups (>= ~12 per SM of a 148-SM part) to fill the machine; P = groups per virtual shard, capped at pmax.
     static unsigned choose_P(unsigned long long nchunks, unsigned target_chunks, unsigned pmax)
     {
-        unsigned long long fill = nchunks / 1776;
+        unsigned long long fill = nchunks / fill_div();
         if (fill < 1) fill = 1;
         if (fill < target_chunks) target_chunks = (unsigned) fill;
         unsigned long long want = (nchunks + (unsigned long long) kV * target_chunks - 1) / ((unsigned long long) kV * target_chunks);
