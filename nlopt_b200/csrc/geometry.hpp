@@ -28,7 +28,7 @@ struct Geometry {
     unsigned long long ld = 0;                   // padded local length: whole chunks (multiple of 512 doubles)
 
     // tuning constant of choose_P (process-wide): groups wanted before groups start to grow
-    static unsigned &fill_div() { static unsigned v = 1776; return v; }
+    static unsigned &fill_div() { static unsigned v = 888; return v; }
 
     static unsigned long long cut(unsigned s, unsigned long long nchunks, unsigned S)
     {
@@ -36,7 +36,7 @@ struct Geometry {
     }
 
     // Group size: `target_chunks` chunks for large n, fewer for small n so that there are still enough
-    // groups (>= ~12 per SM of a 148-SM part) to fill the machine; P = groups per virtual shard, capped at pmax.
+    // groups (about 1000: measured optimum at n = 1e6..3e6, profiles/r01_summary.md) to fill the machine; P = groups per virtual shard, capped at pmax.
     static unsigned choose_P(unsigned long long nchunks, unsigned target_chunks, unsigned pmax)
     {
         unsigned long long fill = nchunks / fill_div();
