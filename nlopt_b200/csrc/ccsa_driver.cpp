@@ -136,7 +136,7 @@ int ccsa_minimize(Variant variant, Backend &be, const std::vector<double> &tol, 
         ++launches;
         return assemble(yy, grad);
     };
-    const bool fused = prm.fused_solve && m > 0 && be.supports_dual_solve();
+    bool fused = prm.fused_solve && m > 0 && be.supports_dual_solve();
 
     if (!be.first_outer()) return L.fail("state rotation");
     unsigned k = 0;
@@ -160,7 +160,11 @@ int ccsa_minimize(Variant variant, Backend &be, const std::vector<double> &tol, 
                 sc.rho = rho;
                 int reti = 0;
                 long dn = 0;
-                if (!be.dual_solve(y.data(), ylo.data(), yhi.data(), stop6, sc, &raw, &reti, &dn)) return L.fail("dual solve");
+                if (!be.dual_solve(y.data(), ylo.data(), yhi.data(), stop6, sc, &raw, &reti, &dn)) {
+                    if (be.supports_dual_solve()) return L.fail("dual solve");
+                    fused = false;                                // persistent kernel unavailable: host-driven from now on
+                    continue;                                     // redo this inner iteration's dual solve
+                }
                 if (reti < 0 || reti == R_MAXTIME) {              // mma.c:283-286
                     if (reti == kRetInvalid && errmsg) *errmsg = "dual variables left their box";
                     if (reti == kRetFailure) return L.fail("dual solve");

@@ -195,18 +195,16 @@ void DeviceBackend::free_state()
         if (h_grad_[b]) BlockCache::get().give(true, h_grad_cap_ * sizeof(double), h_grad_[b]);
         if (h_grad_done_[b]) cudaEventDestroy(h_grad_done_[b]);
     }
-    if (copied_) cudaEventDestroy(copied_);
     if (stream_) cudaStreamDestroy(stream_);
     if (copy_stream_) cudaStreamDestroy(copy_stream_);
     pool_ = w_dev_ = xtol_abs_dev_ = partials_ = vsums_ = out_dev_ = xfull_dev_ = scalar_dev_ = nullptr;
-    tickets_ = group_tickets_ = nullptr;
+    tickets_ = nullptr;
     grouprecs_ = nullptr;
     out_host_ = nullptr;
     flag_host_ = nullptr;
     h_x_ = nullptr;
     h_grad_[0] = h_grad_[1] = nullptr;
     h_grad_done_[0] = h_grad_done_[1] = nullptr;
-    copied_ = nullptr;
     stream_ = copy_stream_ = nullptr;
 }
 
@@ -236,7 +234,6 @@ bool DeviceBackend::alloc_state()
     NB_CUDA(cudaDeviceGetAttribute(&sm_count_, cudaDevAttrMultiProcessorCount, device_));
     NB_CUDA(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
     NB_CUDA(cudaStreamCreateWithFlags(&copy_stream_, cudaStreamNonBlocking));
-    NB_CUDA(cudaEventCreateWithFlags(&copied_, cudaEventDisableTiming));
 
     const size_t ld = geo_.ld;
     const size_t total = (9 + 2 * (size_t) m_) * ld;
@@ -540,7 +537,9 @@ bool DeviceBackend::wait_flag()
                 if (__atomic_load_n(flag_host_, __ATOMIC_ACQUIRE) == seq_) return true;
                 return fail("dual kernel finished without publishing its result");
             }
-            if (std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > 120.0)
+            // a whole dual solve (up to dual_maxeval evaluations) can legitimately run for minutes at n = 1e8;
+            // in-kernel timeouts cover dead peers, this one only a kernel that never ends
+            if (std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > 3600.0)
                 return fail("timed out waiting for the dual kernel");
         }
     }
@@ -744,7 +743,17 @@ bool DeviceBackend::dual_solve(double *y, const double *lo, const double *hi, co
         cudaEventRecord(e0, stream_);
     }
     void *params[] = {&sa};
-    NB_CUDA(cudaLaunchCooperativeKernel((const void *) fn, dim3((unsigned) grid), dim3(256), params, 0, stream_));
+    {
+        cudaError_t le = cudaLaunchCooperativeKernel((const void *) fn, dim3((unsigned) grid), dim3(256), params, 0, stream_);
+        if (le != cudaSuccess) {
+            // e.g. co-residency not available (MPS, another context): not fatal -- switch this object to one
+            // launch per evaluation; the caller sees supports_dual_solve() == false and takes the host loop
+            cudaGetLastError();
+            fused_solve_ok_ = false;
+            if (ev_used_ >= 2 && time_kernels_) ev_used_ -= 2;
+            return fail("cooperative launch of dual_solve_kernel", le);
+        }
+    }
     if (time_kernels_) cudaEventRecord(e1, stream_);
     ++stats_->kernel_launches;
     cand_in_x_ = false;                              // the final pass stores x*(y) into xcur_

@@ -95,11 +95,10 @@ private:
            *sigma_ = nullptr, *g_ = nullptr, *gcur_ = nullptr, *G_ = nullptr, *Gcur_ = nullptr;
     double *w_dev_ = nullptr, *xtol_abs_dev_ = nullptr;
     bool cand_in_x_ = true;       // the latest candidate's values live in x_ (start point / just accepted)
-    bool bounds_set_ = false;
 
     // reduction workspace + result mailbox
     double *partials_ = nullptr, *grouprecs_ = nullptr, *vsums_ = nullptr, *out_dev_ = nullptr;
-    unsigned *tickets_ = nullptr, *group_tickets_ = nullptr;
+    unsigned *tickets_ = nullptr;
     double *out_host_ = nullptr;                     // mapped pinned
     unsigned long long *flag_host_ = nullptr;        // mapped pinned
     unsigned long long seq_ = 0;
@@ -118,7 +117,6 @@ private:
     int h_x_slot_ = -1;
 
     cudaStream_t stream_ = nullptr, copy_stream_ = nullptr;
-    cudaEvent_t copied_ = nullptr;
 
     // optional per-launch timing of the dual kernel
     bool time_kernels_ = false;
