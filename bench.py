@@ -60,6 +60,7 @@ def parse():
     ap.add_argument("--alg", default="ccsaq", choices=["ccsaq", "mma"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--param", action="append", default=[], help="extra nlopt_set_param name=value (tuning experiments)")
     return ap.parse_args()
 
 
@@ -244,6 +245,9 @@ def main():
         else:
             p.rosenbrock_host(o, m)
         o.set_param("b200_time_kernels", 1)
+        for kv in a.param:
+            k, v = kv.split("=")
+            o.set_param(k, float(v))
         return o, p
 
     def timed(run, steps):
@@ -326,7 +330,9 @@ def main():
                "seconds_in_user_callbacks": cb_s, "dual_evals": sh["dual_evals"],
                "note": "rate over wall time minus time inside the user's host callbacks (BASELINE.md definition); "
                        "includes all H2D/D2H copies, launches and the host-side dual optimiser",
-               "f_after_steps": oh.last_optimum_value()}
+               "f_after_steps": oh.last_optimum_value(),
+               "wall_breakdown_s": {k: sh[k] for k in ("seconds_total", "seconds_setup", "seconds_dual_wall", "seconds_eval_wall",
+                                                        "seconds_glue_wall", "seconds_callbacks")}}
 
     # ---- cpu baseline: reference dual_func on host cores (rank 0, N = 1 only) ----------------------------
     cpu = None

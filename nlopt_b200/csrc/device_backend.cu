@@ -675,12 +675,13 @@ typedef void (*SolveKernel)(const SolveArgs);
 // `deep`: few groups per resident CTA (small shards, e.g. n = 1e7 over 8 GPUs) -- the sweep is then bound by
 // the latency of each sweep step, so two chunks per step are kept in flight instead of one
 template <int VARIANT, bool FULL>
-SolveKernel pick_solve_kernel(int maxm, bool deep)
+SolveKernel pick_solve_kernel(int maxm, bool deep, bool dense)
 {
+    // dense: 4 CTAs/SM (64 registers) -- the measured optimum of the CCSAQ sweep with <= 4 rows; MMA keeps 3
     switch (maxm) {
-    case 1: return deep ? dual_solve_kernel<VARIANT, 1, FULL, 256, 2, 3> : dual_solve_kernel<VARIANT, 1, FULL, 256, 1, 3>;
-    case 2: return deep ? dual_solve_kernel<VARIANT, 2, FULL, 256, 2, 3> : dual_solve_kernel<VARIANT, 2, FULL, 256, 1, 3>;
-    case 4: return deep ? dual_solve_kernel<VARIANT, 4, FULL, 256, 2, 3> : dual_solve_kernel<VARIANT, 4, FULL, 256, 1, 3>;
+    case 1: return deep ? dual_solve_kernel<VARIANT, 1, FULL, 256, 2, 3> : dense ? dual_solve_kernel<VARIANT, 1, FULL, 256, 1, 4> : dual_solve_kernel<VARIANT, 1, FULL, 256, 1, 3>;
+    case 2: return deep ? dual_solve_kernel<VARIANT, 2, FULL, 256, 2, 3> : dense ? dual_solve_kernel<VARIANT, 2, FULL, 256, 1, 4> : dual_solve_kernel<VARIANT, 2, FULL, 256, 1, 3>;
+    case 4: return deep ? dual_solve_kernel<VARIANT, 4, FULL, 256, 2, 3> : dense ? dual_solve_kernel<VARIANT, 4, FULL, 256, 1, 4> : dual_solve_kernel<VARIANT, 4, FULL, 256, 1, 3>;
     case 8: return dual_solve_kernel<VARIANT, 8, FULL, 256, 1, 2>;
     default: return dual_solve_kernel<VARIANT, 16, FULL, 256, 1, 2>;
     }
@@ -719,9 +720,10 @@ bool DeviceBackend::dual_solve(double *y, const double *lo, const double *hi, co
 
     const int maxm = pick_maxm((int) m_);
     const bool full = (int) m_ == maxm && (variant_ == kCCSAQ || sa.d.active == ((1u << m_) - 1u));
-    const bool deep = solve_deep_ >= 0 ? solve_deep_ != 0 : (long long) geo_.nseg_local <= 3ll * sm_count_;
-    SolveKernel fn = variant_ == kMMA ? (full ? pick_solve_kernel<0, true>(maxm, deep) : pick_solve_kernel<0, false>(maxm, deep))
-                                      : (full ? pick_solve_kernel<1, true>(maxm, deep) : pick_solve_kernel<1, false>(maxm, deep));
+    const bool deep = solve_deep_ > 0;       // opt-in: measured slower at n = 1e7 over 8 GPUs (39.3 vs 32.3 us per evaluation)
+    const bool dense = solve_dense_ >= 0 ? solve_dense_ != 0 : variant_ == kCCSAQ;
+    SolveKernel fn = variant_ == kMMA ? (full ? pick_solve_kernel<0, true>(maxm, deep, dense) : pick_solve_kernel<0, false>(maxm, deep, dense))
+                                      : (full ? pick_solve_kernel<1, true>(maxm, deep, dense) : pick_solve_kernel<1, false>(maxm, deep, dense));
     int per_sm = 0;
     NB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, 256, 0));
     if (per_sm < 1) return fail("dual_solve_kernel does not fit on an SM");
@@ -957,6 +959,7 @@ bool DeviceBackend::configure(const char *key, long long value)
     if (k == "ctas_per_sm") { ctas_per_sm_ = (int) value; return true; }
     if (k == "fused_solve") { fused_solve_ok_ = value != 0; return true; }
     if (k == "solve_deep") { solve_deep_ = (int) value; return true; }
+    if (k == "solve_dense") { solve_dense_ = (int) value; return true; }
     if (k == "pmax" || k == "target_chunks" || k == "fill_div") {
         if (value < 1) return fail("bad value");
         if (k == "pmax") pmax_ = (unsigned) value;
