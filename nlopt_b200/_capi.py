@@ -21,7 +21,9 @@ NLOPT_B200_DFUNC = C.CFUNCTYPE(C.c_double, C.c_uint, C.c_ulonglong, C.c_void_p, 
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 REPO_DIR = os.path.dirname(PKG_DIR)
-DEFAULT_LIB = os.path.join(PKG_DIR, "libnlopt_b200.so")
+# NLOPT_B200_LIBDIR: load an alternative build of the same library (tools/trace_solve.py: instrumented build)
+LIB_DIR = os.environ.get("NLOPT_B200_LIBDIR", PKG_DIR)
+DEFAULT_LIB = os.path.join(LIB_DIR, "libnlopt_b200.so")
 
 
 class Stats(C.Structure):

@@ -671,6 +671,23 @@ __global__ void __launch_bounds__(kTmaBlock, MINB) dual_eval_tma_kernel(const __
 // to the DualMachine, publishes y_{g+1} and bumps the generation that the other CTAs are polling.
 // Versus one launch per evaluation this removes launch latency, the PCIe result hop and the host turn-
 // around from every evaluation; the host sees one launch and one result per dual solve.
+// Timeline instrumentation (tools/trace_solve.py builds a separate library with -DNB200_TRACE; the product build
+// contains none of it).  Per generation g, 16 counters at trace[16 g]: 0 published | 1 ~min / 2 max "CTA saw it" |
+// 3 ~min / 4 max "group record done" | 5 rank complete | 6 totals ready | 7 optimiser done | 8 sum / 9 count of
+// per-group sweep times.  Row 0 holds the CTA start times.  All in %globaltimer nanoseconds.
+#ifdef NB200_TRACE
+constexpr int kTraceGens = 512;
+__device__ __forceinline__ unsigned long long nb_gtime()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define NB_TR(...) __VA_ARGS__
+#else
+#define NB_TR(...)
+#endif
+
 struct SolveState {                       // device global, zeroed by the host before every launch
     unsigned long long claim;             // monotonic group-claim counter
     unsigned long long gen;               // last published generation (0: none yet)
@@ -692,6 +709,7 @@ struct SolveArgs {
     double lo[kMaxParamM], hi[kMaxParamM];    // box of the multipliers
     DualStop stop;
     volatile double *res_host;            // mapped pinned: raw sums [24] | y [32] | nevals | ret
+    NB_TR(unsigned long long *trace;)
 };
 
 struct SharedMultipliers {                // what the point functions read in the solve kernel
@@ -743,11 +761,13 @@ __global__ void __launch_bounds__(BLOCK, MINB) dual_solve_kernel(const __grid_co
             st->store = 0;
             st->final_pass = 0;
             __threadfence();
+            NB_TR(sa.trace[16] = nb_gtime();)
             *reinterpret_cast<volatile unsigned long long *>(&st->gen) = 1;
             __threadfence();
         }
     }
     if (threadIdx.x == 0) s_claim[0] = atomicAdd(&st->claim, 1ull);
+    NB_TR(if (threadIdx.x == 0) { const unsigned long long t = nb_gtime(); atomicMax(&sa.trace[1], ~t); atomicMax(&sa.trace[2], t); })
     __syncthreads();
 
     unsigned long long my_gen = 0;        // generation whose multipliers are in s_y
@@ -769,6 +789,8 @@ __global__ void __launch_bounds__(BLOCK, MINB) dual_solve_kernel(const __grid_co
             }
             __syncthreads();
             if (s_exit) return;
+            NB_TR(if (threadIdx.x == 0 && want < kTraceGens) { const unsigned long long t = nb_gtime();
+                      atomicMax(&sa.trace[16 * want + 1], ~t); atomicMax(&sa.trace[16 * want + 2], t); })
             __threadfence();
             if (threadIdx.x < a.m) s_y[threadIdx.x] = __ldcg(&st->y[threadIdx.x]);
             if (threadIdx.x == 32) { s_u = __ldcg(&st->u_ccsaq); s_store = __ldcg(&st->store); }
@@ -785,6 +807,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) dual_solve_kernel(const __grid_co
         double acc[NV];
 #pragma unroll
         for (int k = 0; k < NV; ++k) acc[k] = 0.0;
+        NB_TR(const unsigned long long tr_s0 = nb_gtime();)
         sweep_group<VARIANT, MAXM, FULL, UNROLL>(a, mu, s_store != 0, gl, sub, lane, acc);
 
         warp_fold<NV>(acc);
@@ -803,6 +826,8 @@ __global__ void __launch_bounds__(BLOCK, MINB) dual_solve_kernel(const __grid_co
             a.grouprecs[(unsigned long long) gl * a.nvp + lane] = s;
         }
         __syncwarp();
+        NB_TR(if (lane == 0 && my_gen < kTraceGens) { const unsigned long long t = nb_gtime(); unsigned long long *r = sa.trace + 16 * my_gen;
+                  atomicMax(r + 3, ~t); atomicMax(r + 4, t); atomicAdd(r + 8, t - tr_s0); atomicAdd(r + 9, 1ull); })
 
         // virtual-shard sum (monotonic ticket: every generation adds exactly P arrivals)
         const unsigned vs_local = gl / a.segs_per_vshard;
@@ -841,6 +866,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) dual_solve_kernel(const __grid_co
         // ---- this warp completed generation my_gen on this rank: total sums (exchange if sharded) ----
         double total = 0.0;               // lane k < NV holds sum k
         int timed_out = 0;
+        NB_TR(if (lane == 0 && my_gen < kTraceGens) sa.trace[16 * my_gen + 5] = nb_gtime();)
         if (a.box[0] == nullptr) {
             if (lane < NV) {
                 total = __ldcg(a.vsums + lane);
@@ -851,6 +877,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) dual_solve_kernel(const __grid_co
                                  a.seg0 / a.segs_per_vshard, NV, lane, &timed_out);     // one tag per generation
         }
 
+        NB_TR(if (lane == 0 && my_gen < kTraceGens) sa.trace[16 * my_gen + 6] = nb_gtime();)
         // ---- the dual optimiser's turn (one lane; the machine is staged through shared memory) ----
         {
             const double *src = reinterpret_cast<const double *>(&st->mach);
@@ -879,6 +906,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) dual_solve_kernel(const __grid_co
             if (finished && !timed_out) { next_store = 1; next_final = 1; }          // one more pass at the solution
         }
         __syncwarp();
+        NB_TR(if (lane == 0 && my_gen < kTraceGens) sa.trace[16 * my_gen + 7] = nb_gtime();)
         if (final_pass || timed_out) {
             // publish the result of the solve: raw sums of the final pass, multipliers, counts
             if (lane < NV) sa.res_host[lane] = total;
@@ -915,6 +943,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) dual_solve_kernel(const __grid_co
             __threadfence();
             __syncwarp();
             if (lane == 0) {
+                NB_TR(if (my_gen + 1 < kTraceGens) sa.trace[16 * (my_gen + 1)] = nb_gtime();)
                 *reinterpret_cast<volatile unsigned long long *>(&st->gen) = my_gen + 1;
                 __threadfence();
             }

@@ -6,9 +6,11 @@
 #include <chrono>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
+#include <vector>
 
 #include "ccsa_kernels.cuh"
 #include "comm.hpp"
@@ -672,16 +674,16 @@ bool DeviceBackend::dual_eval(const double *y, const DualScalars &sc, bool mater
 namespace {
 typedef void (*SolveKernel)(const SolveArgs);
 
-// `deep`: few groups per resident CTA (small shards, e.g. n = 1e7 over 8 GPUs) -- the sweep is then bound by
-// the latency of each sweep step, so two chunks per step are kept in flight instead of one
+// One configuration per row count.  Two alternatives were measured on the box and removed (profiles/r01_summary.md):
+// two chunks in flight per sweep step (slower at n = 1e7 over 8 GPUs, 39.3 vs 32.3 us per evaluation) and
+// 4 CTAs/SM at 64 registers (spills: 149 vs 129 us per CCSAQ evaluation at n = 1e7, m = 4).
 template <int VARIANT, bool FULL>
-SolveKernel pick_solve_kernel(int maxm, bool deep, bool dense)
+SolveKernel pick_solve_kernel(int maxm)
 {
-    // dense: 4 CTAs/SM (64 registers) -- the measured optimum of the CCSAQ sweep with <= 4 rows; MMA keeps 3
     switch (maxm) {
-    case 1: return deep ? dual_solve_kernel<VARIANT, 1, FULL, 256, 2, 3> : dense ? dual_solve_kernel<VARIANT, 1, FULL, 256, 1, 4> : dual_solve_kernel<VARIANT, 1, FULL, 256, 1, 3>;
-    case 2: return deep ? dual_solve_kernel<VARIANT, 2, FULL, 256, 2, 3> : dense ? dual_solve_kernel<VARIANT, 2, FULL, 256, 1, 4> : dual_solve_kernel<VARIANT, 2, FULL, 256, 1, 3>;
-    case 4: return deep ? dual_solve_kernel<VARIANT, 4, FULL, 256, 2, 3> : dense ? dual_solve_kernel<VARIANT, 4, FULL, 256, 1, 4> : dual_solve_kernel<VARIANT, 4, FULL, 256, 1, 3>;
+    case 1: return dual_solve_kernel<VARIANT, 1, FULL, 256, 1, 3>;
+    case 2: return dual_solve_kernel<VARIANT, 2, FULL, 256, 1, 3>;
+    case 4: return dual_solve_kernel<VARIANT, 4, FULL, 256, 1, 3>;
     case 8: return dual_solve_kernel<VARIANT, 8, FULL, 256, 1, 2>;
     default: return dual_solve_kernel<VARIANT, 16, FULL, 256, 1, 2>;
     }
@@ -717,13 +719,17 @@ bool DeviceBackend::dual_solve(double *y, const double *lo, const double *hi, co
     sa.stop.ftol_rel = stop6[0]; sa.stop.ftol_abs = stop6[1]; sa.stop.xtol_rel = stop6[2]; sa.stop.xtol_abs = stop6[3];
     sa.stop.maxeval = (int) stop6[4]; sa.stop.maxtime = stop6[5];
     sa.res_host = res_host_;
+#ifdef NB200_TRACE
+    static unsigned long long *trace_buf = nullptr;
+    if (!trace_buf) NB_CUDA(cudaMalloc(&trace_buf, sizeof(unsigned long long) * 16 * kTraceGens));
+    NB_CUDA(cudaMemsetAsync(trace_buf, 0, sizeof(unsigned long long) * 16 * kTraceGens, stream_));
+    sa.trace = trace_buf;
+#endif
 
     const int maxm = pick_maxm((int) m_);
     const bool full = (int) m_ == maxm && (variant_ == kCCSAQ || sa.d.active == ((1u << m_) - 1u));
-    const bool deep = solve_deep_ > 0;       // opt-in: measured slower at n = 1e7 over 8 GPUs (39.3 vs 32.3 us per evaluation)
-    const bool dense = solve_dense_ >= 0 ? solve_dense_ != 0 : variant_ == kCCSAQ;
-    SolveKernel fn = variant_ == kMMA ? (full ? pick_solve_kernel<0, true>(maxm, deep, dense) : pick_solve_kernel<0, false>(maxm, deep, dense))
-                                      : (full ? pick_solve_kernel<1, true>(maxm, deep, dense) : pick_solve_kernel<1, false>(maxm, deep, dense));
+    SolveKernel fn = variant_ == kMMA ? (full ? pick_solve_kernel<0, true>(maxm) : pick_solve_kernel<0, false>(maxm))
+                                      : (full ? pick_solve_kernel<1, true>(maxm) : pick_solve_kernel<1, false>(maxm));
     int per_sm = 0;
     NB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, 256, 0));
     if (per_sm < 1) return fail("dual_solve_kernel does not fit on an SM");
@@ -761,6 +767,27 @@ bool DeviceBackend::dual_solve(double *y, const double *lo, const double *hi, co
     cand_in_x_ = false;                              // the final pass stores x*(y) into xcur_
     ++x_epoch_;
     if (!wait_flag()) return false;
+#ifdef NB200_TRACE
+    if (const char *tf = std::getenv("NLOPT_B200_TRACE_FILE")) {      // one line per generation, ns relative to publication
+        static std::vector<unsigned long long> h(16 * kTraceGens);
+        cudaStreamSynchronize(stream_);
+        cudaMemcpy(h.data(), trace_buf, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+        if (FILE *f = std::fopen(tf, "a")) {
+            const unsigned long long t00 = ~h[1];
+            std::fprintf(f, "solve n_local=%llu m=%u grid=%lld groups=%u cta_start_spread_ns=%llu first_publish_ns=%llu\n", (unsigned long long) geo_.n_local, m_, grid,
+                         geo_.nseg_local, h[2] - t00, h[16] - t00);
+            for (int g = 1; g < kTraceGens && h[16 * g]; ++g) {
+                const unsigned long long *r = &h[16 * g];
+                const unsigned long long p = r[0];
+                std::fprintf(f, "  gen %d seen[%lld..%lld] recs[%lld..%lld] rank_done %lld totals %lld machine %lld next_pub %lld | mean_group_sweep %llu ns x %llu\n", g,
+                             (long long) (~r[1] - p), (long long) (r[2] - p), (long long) (~r[3] - p), (long long) (r[4] - p),
+                             (long long) (r[5] - p), (long long) (r[6] - p), (long long) (r[7] - p),
+                             (long long) (h[16 * (g + 1)] ? h[16 * (g + 1)] - p : 0), r[9] ? r[8] / r[9] : 0ull, r[9]);
+            }
+            std::fclose(f);
+        }
+    }
+#endif
     const long gens = (long) res_host_[24 + kMaxParamM + 2];
     *ret = (int) res_host_[24 + kMaxParamM + 1];
     *nevals = (long) res_host_[24 + kMaxParamM];
@@ -958,8 +985,6 @@ bool DeviceBackend::configure(const char *key, long long value)
     if (k == "kernel_cfg") { kernel_cfg_ = (int) value; return true; }
     if (k == "ctas_per_sm") { ctas_per_sm_ = (int) value; return true; }
     if (k == "fused_solve") { fused_solve_ok_ = value != 0; return true; }
-    if (k == "solve_deep") { solve_deep_ = (int) value; return true; }
-    if (k == "solve_dense") { solve_dense_ = (int) value; return true; }
     if (k == "pmax" || k == "target_chunks" || k == "fill_div") {
         if (value < 1) return fail("bad value");
         if (k == "pmax") pmax_ = (unsigned) value;

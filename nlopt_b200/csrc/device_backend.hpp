@@ -85,8 +85,6 @@ private:
     void *solve_state_ = nullptr;     // SolveState (device) of the persistent dual-solve kernel
     double *res_host_ = nullptr;      // its mapped pinned result record
     bool fused_solve_ok_ = true;
-    int solve_dense_ = -1;            // -1: by variant; 0/1: force 3 / 4 CTAs per SM in the persistent kernel
-    int solve_deep_ = -1;             // -1: choose by shard size; 0/1: force one/two chunks per sweep step
     int kernel_cfg_ = -1;         // -1: measured default for (variant, m)          // index into the launch-geometry table of device_backend.cu
 
     // device state

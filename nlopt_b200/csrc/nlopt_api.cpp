@@ -844,8 +844,6 @@ nlopt_result run_ccsa(nlopt_opt opt, double *x_host, double *x_dev, double *minf
     if (nlopt_has_param(opt, "b200_target_chunks"))
         be->configure("target_chunks", (long long) nlopt_get_param(opt, "b200_target_chunks", 0.0));
     prm.fused_solve = (int) nlopt_get_param(opt, "b200_fused_solve", 1.0);
-    if (nlopt_has_param(opt, "b200_solve_dense")) be->configure("solve_dense", (long long) nlopt_get_param(opt, "b200_solve_dense", -1.0));
-    if (nlopt_has_param(opt, "b200_solve_deep")) be->configure("solve_deep", (long long) nlopt_get_param(opt, "b200_solve_deep", -1.0));
     if (nlopt_has_param(opt, "b200_kernel_cfg")) be->configure("kernel_cfg", (long long) nlopt_get_param(opt, "b200_kernel_cfg", 0.0));
     if (nlopt_has_param(opt, "b200_ctas_per_sm")) be->configure("ctas_per_sm", (long long) nlopt_get_param(opt, "b200_ctas_per_sm", 0.0));
 

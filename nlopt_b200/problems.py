@@ -9,9 +9,9 @@ import os
 
 import numpy as np
 
-from ._capi import NLOPT_FUNC, PKG_DIR, c_double_p
+from ._capi import LIB_DIR, NLOPT_FUNC, c_double_p
 
-LIB_PATH = os.path.join(PKG_DIR, "libnlopt_b200_problems.so")
+LIB_PATH = os.path.join(LIB_DIR, "libnlopt_b200_problems.so")
 
 
 def _load():
