@@ -69,9 +69,45 @@ __device__ __forceinline__ bool box_get(const double *slot, unsigned long long t
 }
 constexpr int kBoxStride = 24;           // slots per virtual shard record (comm.hpp)
 
+// The same slots inside one GPU (group records and published multipliers of the persistent solve kernel):
+// gpu-scope relaxed accesses are served by the L2.  (The .volatile = system-scope forms above, needed across
+// NVLink, measured ~9 ns per lane request when 32 lanes hit 32 different lines.)
+__device__ __forceinline__ void slot_put(double *slot, double value, unsigned long long tag)
+{
+    asm volatile("st.relaxed.gpu.global.v2.b64 [%0], {%1, %2};" ::"l"(slot), "l"(__double_as_longlong(value)), "l"(tag) : "memory");
+}
+// Polling many slots per thread: strong (volatile / relaxed) loads of one thread complete one after the other
+// (measured: the folder's tail grew with the number of strong loads per thread, ~0.3 us each on an idle memory
+// system), weak loads pipeline.  ld.global.cg always reads the L2 -- where the producers' stores land -- and the
+// tag travels in the same 16 bytes as the value, so a slot whose tag matches is complete.
+__device__ __forceinline__ bool slot_peek(const double *slot, unsigned long long tag, double *value)
+{
+    long long v;
+    unsigned long long t;
+    asm volatile("ld.global.cg.v2.b64 {%0, %1}, [%2];" : "=l"(v), "=l"(t) : "l"(slot) : "memory");
+    *value = __longlong_as_double(v);
+    return t == tag;
+}
+__device__ __forceinline__ int ld_gpu_s32(const int *p)
+{
+    int v;
+    asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ bool slot_get(const double *slot, unsigned long long tag, double *value)
+{
+    long long v;
+    unsigned long long t;
+    asm volatile("ld.relaxed.gpu.global.v2.b64 {%0, %1}, [%2];" : "=l"(v), "=l"(t) : "l"(slot) : "memory");
+    *value = __longlong_as_double(v);
+    return t == tag;
+}
+
 // Lane k < nv: write this rank's shard records into every peer's mailbox, then gather all 8 records of
 // sum k from the own mailbox and fold them in index order.  Returns the total in lanes < nv; *timed_out is
 // warp-uniform.
+// VS_LOCAL: the shard sums were written by this CTA (shared memory or own global writes ordered by a barrier): plain loads.
+template <bool VS_LOCAL = false>
 __device__ __forceinline__ double box_exchange(double *const *box, int rank, int world, unsigned long long seq,
                                                const double *vsums, int nvp, unsigned local_vshards, unsigned v0,
                                                int nv, int lane, int *timed_out)
@@ -81,7 +117,7 @@ __device__ __forceinline__ double box_exchange(double *const *box, int rank, int
     int to = 0;
     if (lane < nv) {
         for (unsigned v = 0; v < local_vshards; ++v) {
-            const double val = __ldcg(vsums + (unsigned long long) v * nvp + lane);
+            const double val = VS_LOCAL ? vsums[(unsigned long long) v * nvp + lane] : __ldcg(vsums + (unsigned long long) v * nvp + lane);
             for (int r = 0; r < world; ++r)
                 box_put(box[r] + 2ull * (((unsigned long long) buf * 8 + v0 + v) * kBoxStride + lane), val, seq);
         }
@@ -320,6 +356,27 @@ __device__ __forceinline__ bool warp_is_last(unsigned *ticket, unsigned total, i
     return t == total - 1u;
 }
 
+// Virtual-shard sum of P group records, canonical order (the order the solve kernel's folder CTA produces with
+// its 256 threads): chain t in [0, 256) adds records t, t+256, ... in index order; the 32 chains of "fold warp"
+// w = t / 32 meet in an xor butterfly; the 8 fold-warp results are added in warp order.  Here one warp plays
+// the 8 fold warps in turn.  Every lane returns all NV sums.
+template <int NV>
+__device__ __forceinline__ void fold_shard_records(const double *base, unsigned P, int nvp, int lane, double (&tot)[NV])
+{
+#pragma unroll 1
+    for (int w = 0; w < kGroupWarps; ++w) {
+        double acc[NV];
+#pragma unroll
+        for (int k = 0; k < NV; ++k) acc[k] = 0.0;
+        for (unsigned r = 32 * w + lane; r < P; r += 32 * kGroupWarps)
+#pragma unroll
+            for (int k = 0; k < NV; ++k) acc[k] = addx(acc[k], __ldcg(base + (unsigned long long) r * nvp + k));
+        warp_fold<NV>(acc);
+#pragma unroll
+        for (int k = 0; k < NV; ++k) tot[k] = w == 0 ? acc[k] : addx(tot[k], acc[k]);
+    }
+}
+
 // Sweep one group: this warp's lanes of every chunk of group `gl`, m+3 lane accumulators.
 template <int VARIANT, int MAXM, bool FULL, int UNROLL, class MU>
 __device__ __forceinline__ void sweep_group(const DualArgs &a, const MU &mu, bool store, unsigned gl, int sub,
@@ -421,16 +478,8 @@ __global__ void __launch_bounds__(BLOCK, MINB) dual_eval_kernel(const __grid_con
         // virtual-shard sum, by the warp that completes the shard
         const unsigned vs_local = gl / a.segs_per_vshard;
         if (!warp_is_last(a.tickets + vs_local, a.segs_per_vshard, lane)) continue;
-#pragma unroll
-        for (int k = 0; k < NV; ++k) acc[k] = 0.0;
-        {
-            const double *base = a.grouprecs + (unsigned long long) vs_local * a.segs_per_vshard * a.nvp;
-#pragma unroll 4
-            for (unsigned r = lane; r < a.segs_per_vshard; r += 32)      // loads of 4 rounds in flight, adds in order
-#pragma unroll
-                for (int k = 0; k < NV; ++k) acc[k] = addx(acc[k], __ldcg(base + (unsigned long long) r * a.nvp + k));
-        }
-        warp_fold<NV>(acc);
+        fold_shard_records<NV>(a.grouprecs + (unsigned long long) vs_local * a.segs_per_vshard * a.nvp, a.segs_per_vshard,
+                               a.nvp, lane, acc);
         if (lane == 0) {
             double *rec = a.vsums + (unsigned long long) vs_local * a.nvp;
 #pragma unroll
@@ -613,16 +662,8 @@ __global__ void __launch_bounds__(kTmaBlock, MINB) dual_eval_tma_kernel(const __
         __syncwarp();
         const unsigned vs_local = gl / a.segs_per_vshard;
         if (!warp_is_last(a.tickets + vs_local, a.segs_per_vshard, lane)) continue;
-#pragma unroll
-        for (int k = 0; k < NV; ++k) acc[k] = 0.0;
-        {
-            const double *base = a.grouprecs + (unsigned long long) vs_local * a.segs_per_vshard * a.nvp;
-#pragma unroll 4
-            for (unsigned r = lane; r < a.segs_per_vshard; r += 32)      // loads of 4 rounds in flight, adds in order
-#pragma unroll
-                for (int k = 0; k < NV; ++k) acc[k] = addx(acc[k], __ldcg(base + (unsigned long long) r * a.nvp + k));
-        }
-        warp_fold<NV>(acc);
+        fold_shard_records<NV>(a.grouprecs + (unsigned long long) vs_local * a.segs_per_vshard * a.nvp, a.segs_per_vshard,
+                               a.nvp, lane, acc);
         if (lane == 0) {
             double *rec = a.vsums + (unsigned long long) vs_local * a.nvp;
 #pragma unroll
@@ -664,17 +705,28 @@ __global__ void __launch_bounds__(kTmaBlock, MINB) dual_eval_tma_kernel(const __
 // ---- the persistent dual-SOLVE kernel: one launch per dual solve ------------------------------------------
 //   The m-dimensional dual optimiser (DualMachine, dual_mma.hpp -- the same code the
 // host runs) moves into the kernel: all CTAs stay resident (cooperative launch) and walk *generations*.
-// Generation g = one dual evaluation at the trial multipliers y_g.  Groups are claimed from a monotonic
-// counter (claim c -> generation c / ngroups + 1, group c % ngroups), swept exactly like dual_eval_kernel
-// (same records, same fold tree => bit-identical sums), and the warp that completes the rank's last
-// virtual shard -- after the NVLink mailbox exchange when there are several ranks -- feeds F and grad F
-// to the DualMachine, publishes y_{g+1} and bumps the generation that the other CTAs are polling.
+// Generation g = one dual evaluation at the trial multipliers y_g.
+//
+//   sweeper CTAs (all but the last): claim groups from a monotonic counter (claim c -> generation
+//     c / ngroups + 1, group c % ngroups), sweep them exactly like dual_eval_kernel (same warp records,
+//     same group records => same bits) and drop each group record into a *tagged* 16-byte slot
+//     {value, tag(launch, generation)} with one 128-bit store.  No fence, no ticket, no atomic on the
+//     record path: the timeline of the previous (ticket) design showed warp 0 of every CTA spending
+//     ~4.6 us per group in fence + atomic + fence under full memory load while its seven sibling warps
+//     waited at the next slot barrier (profiles/r01_trace_summary_ticket_design.txt).
+//   the folder CTA (the last one): warp v polls the P slots of local virtual shard v in index order
+//     (lane l takes records l, l+32, ...; then the xor butterfly -- the fold tree of dual_eval_kernel),
+//     one CTA barrier hands the <= 8 shard sums to warp 0, which exchanges them over the NVLink mailbox
+//     when there are several ranks, feeds F and grad F to the DualMachine held in ITS shared memory,
+//     and publishes y_{g+1} as tagged slots the sweepers poll (again no fence: a slot is valid iff its
+//     tag is the awaited generation).
 // Versus one launch per evaluation this removes launch latency, the PCIe result hop and the host turn-
 // around from every evaluation; the host sees one launch and one result per dual solve.
+//
 // Timeline instrumentation (tools/trace_solve.py builds a separate library with -DNB200_TRACE; the product build
 // contains none of it).  Per generation g, 16 counters at trace[16 g]: 0 published | 1 ~min / 2 max "CTA saw it" |
-// 3 ~min / 4 max "group record done" | 5 rank complete | 6 totals ready | 7 optimiser done | 8 sum / 9 count of
-// per-group sweep times.  Row 0 holds the CTA start times.  All in %globaltimer nanoseconds.
+// 3 ~min / 4 max "group record stored" | 5 all shard sums in | 6 totals ready | 7 optimiser done | 8 sum / 9 count
+// of per-group sweep times.  Row 0 holds the CTA start times.  All in %globaltimer nanoseconds.
 #ifdef NB200_TRACE
 constexpr int kTraceGens = 512;
 __device__ __forceinline__ unsigned long long nb_gtime()
@@ -688,27 +740,25 @@ __device__ __forceinline__ unsigned long long nb_gtime()
 #define NB_TR(...)
 #endif
 
-struct SolveState {                       // device global, zeroed by the host before every launch
+constexpr int kPubSlots = kMaxParamM + 2;     // y_i | u_ccsaq | flags
+struct SolveState {                       // device global; the head is zeroed by the host before every launch
     unsigned long long claim;             // monotonic group-claim counter
-    unsigned long long gen;               // last published generation (0: none yet)
     int done;                             // 1: leave
-    int store;                            // the generation in flight also stores x*(y)
-    unsigned vtickets[kVirtualShards + 1];    // monotonic completion counters (virtual shards, then rank)
-    int final_pass;                       // the generation in flight is the final evaluation at the solution
     int pad;
-    double u_ccsaq;
-    double y[kMaxParamM];                 // trial multipliers of the generation in flight
-    DualMachine mach;
+    double pub[2 * kPubSlots];            // tagged slots {value, tag}: trial multipliers of the generation in flight,
+                                          // u = rho + sum rhoc_i y_i, and (as an integer) bit 0 = also store x*(y)
 };
 
 struct SolveArgs {
-    DualArgs d;                           // arrays, geometry, workspace, exchange boxes (d.y is unused)
+    DualArgs d;                           // arrays, geometry, workspace, exchange boxes (d.y: the warm start)
     SolveState *st;
+    double *grouptags;                    // [nvp][local groups] tagged slots {value, tag}
+    unsigned long long tag0;              // launch id << 40; generation g carries tag0 | g
     double fval;                          // objective value at x
     double cval[kMaxParamM];              // constraint values with switched-off ones zeroed (mma.c:78)
     double lo[kMaxParamM], hi[kMaxParamM];    // box of the multipliers
     DualStop stop;
-    volatile double *res_host;            // mapped pinned: raw sums [24] | y [32] | nevals | ret
+    volatile double *res_host;            // mapped pinned: raw sums [24] | y [32] | nevals | ret | generations
     NB_TR(unsigned long long *trace;)
 };
 
@@ -719,9 +769,173 @@ struct SharedMultipliers {                // what the point functions read in th
     int m, cons0, cons_n;
 };
 
-__device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long *p)
+// The folder CTA's loop (kept out of line so that its registers do not weigh on the sweep loop).
+template <int NV>
+__device__ __noinline__ void solve_folder(const SolveArgs &sa)
 {
-    return *reinterpret_cast<const volatile unsigned long long *>(p);
+    const DualArgs &a = sa.d;
+    SolveState *st = sa.st;
+    const int lane = threadIdx.x & 31;
+    const int sub = threadIdx.x >> 5;
+    const unsigned ngroups = a.segs_per_vshard * a.local_vshards;
+    __shared__ int s_exit;
+    __shared__ DualMachine s_mach;
+    __shared__ double s_grad[kMaxParamM];
+    __shared__ double s_vs[kVirtualShards * NV];      // the shard sums of the generation in flight
+    __shared__ double s_w[kVirtualShards * kGroupWarps * NV];     // per shard: the 8 fold-warp results
+    __shared__ double s_gt[kMaxParamM], s_wt[kMaxParamM];
+    __shared__ int s_has[kMaxParamM];
+    // ================================ the folder CTA ================================
+    int final_pass = 0;
+    if (threadIdx.x == 0) {
+        s_exit = 0;
+        const int rc = s_mach.start(a.m, a.y, sa.lo, sa.hi, sa.stop);      // d.y carries the warm start
+        if (rc != kRetSuccess) {          // start point outside the box: report, publish nothing
+            sa.res_host[24 + kMaxParamM + 1] = (double) rc;
+            __threadfence_system();
+            *a.flag_host = a.seq;
+            __threadfence_system();
+            *reinterpret_cast<volatile int *>(&st->done) = 1;
+            s_exit = 1;
+        } else {
+            double u = a.rho;
+            for (int i = 0; i < a.m; ++i) u = addx(u, mulx(a.rhoc[i], s_mach.y[i]));
+            NB_TR(sa.trace[16] = nb_gtime();)
+            for (int i = 0; i < a.m; ++i) slot_put(st->pub + 2 * i, s_mach.y[i], sa.tag0 | 1ull);
+            slot_put(st->pub + 2 * kMaxParamM, u, sa.tag0 | 1ull);
+            slot_put(st->pub + 2 * (kMaxParamM + 1), __longlong_as_double(0ll), sa.tag0 | 1ull);
+        }
+    }
+    __syncthreads();
+    if (s_exit) return;
+    const long long t_start = clock64();
+    for (unsigned long long gen = 1;; ++gen) {
+        const unsigned long long tag = sa.tag0 | gen;
+        // ---- shard sums, canonical order (see fold_shard_records): all 256 threads take one shard after the
+        // other -- shards complete roughly in index order, so when the last record of the generation lands only
+        // ceil(P / 256) polls of the last shard are still outstanding ----
+        for (unsigned v = 0; v < a.local_vshards; ++v) {
+            double acc[NV];
+#pragma unroll
+            for (int k = 0; k < NV; ++k) acc[k] = 0.0;
+            // slot (group gl, sum k) lives at [k][gl]: the 32 lanes of a poll read 512 contiguous bytes
+            const double *base = sa.grouptags + 2ull * (unsigned long long) v * a.segs_per_vshard;
+            // warp-uniform control flow: a warp polls until all of its lanes have their record (measured: a warp
+            // whose lanes left the poll loop at different times took ~9 us per shard instead of < 1 us)
+            for (unsigned r0 = 32u * sub; r0 < a.segs_per_vshard; r0 += 32 * kGroupWarps) {
+                const unsigned r = r0 + lane;
+                const bool has = r < a.segs_per_vshard;
+                const double *rec = base + 2ull * (has ? r : 0u);
+                double val[NV];
+                for (;;) {                // the NV slots of a record are fetched together: one round trip per poll
+                    bool all = true;
+#pragma unroll
+                    for (int k = 0; k < NV; ++k) all = slot_peek(rec + 2ull * k * ngroups, tag, &val[k]) && all;
+                    NB_TR(if (threadIdx.x == 0 && gen < kTraceGens) atomicAdd(&sa.trace[16 * gen + 13], 1ull);)
+                    if (__all_sync(0xffffffffu, all || !has)) break;
+                    __nanosleep(20);
+                }
+                if (has) {
+#pragma unroll
+                    for (int k = 0; k < NV; ++k) acc[k] = addx(acc[k], val[k]);
+                }
+            }
+            NB_TR(if (threadIdx.x == 0 && gen < kTraceGens && (v == 0 || v == 3 || v == 7)) sa.trace[16 * gen + (v == 0 ? 10 : v == 3 ? 11 : 12)] = nb_gtime();)
+            warp_fold<NV>(acc);
+            if (lane == 0) {
+#pragma unroll
+                for (int k = 0; k < NV; ++k) s_w[(v * kGroupWarps + sub) * NV + k] = acc[k];
+            }
+        }
+        NB_TR(if (threadIdx.x == 0 && gen < kTraceGens) sa.trace[16 * gen + 14] = nb_gtime();)
+        __syncthreads();
+        if (sub == 0 && lane < NV) {
+            for (unsigned v = 0; v < a.local_vshards; ++v) {
+                double t = s_w[(v * kGroupWarps) * NV + lane];
+#pragma unroll
+                for (int w = 1; w < kGroupWarps; ++w) t = addx(t, s_w[(v * kGroupWarps + w) * NV + lane]);
+                s_vs[v * NV + lane] = t;
+            }
+        }
+        __syncwarp();
+        // ---- warp 0: totals (exchange if sharded), the dual optimiser's turn, publication ----
+        if (sub == 0) {
+            NB_TR(if (lane == 0 && gen < kTraceGens) sa.trace[16 * gen + 5] = nb_gtime();)
+            double total = 0.0;               // lane k < NV holds sum k
+            int timed_out = 0;
+            if (a.box[0] == nullptr) {
+                if (lane < NV) {
+                    total = s_vs[lane];
+                    for (unsigned v = 1; v < a.local_vshards; ++v) total = addx(total, s_vs[v * NV + lane]);
+                }
+            } else {
+                total = box_exchange<true>(a.box, a.rank, a.world, a.seq + gen, s_vs, NV, a.local_vshards,
+                                           a.seg0 / a.segs_per_vshard, NV, lane, &timed_out);     // one tag per generation
+            }
+            NB_TR(if (lane == 0 && gen < kTraceGens) sa.trace[16 * gen + 6] = nb_gtime();)
+            // F and grad F from the sums, constants added in the reference's order (mma.c:75-78, :135)
+            int finished = 0, next_final = 0;
+            if (!final_pass) {
+                if (lane >= 3 && lane < 3 + a.m) s_grad[lane - 3] = -addx(sa.cval[lane - 3], total);   // -g_i(y)
+                const double sum0 = __shfl_sync(0xffffffffu, total, 0);
+                __syncwarp();
+                if (lane == 0) {
+                    const double *yt = s_mach.trial();
+                    double val = sa.fval;
+                    for (int i = 0; i < a.m; ++i) val = addx(val, mulx(yt[i], sa.cval[i]));
+                    val = addx(val, sum0);
+                    const double elapsed = (double) (clock64() - t_start) * 5e-10;     // ~2 GHz; only feeds maxtime
+                    finished = timed_out ? 1 : (s_mach.feed_pre(-val, s_grad, elapsed) ? 1 : 0);
+                    if (timed_out) s_mach.ret = kRetFailure;
+                }
+                finished = __shfl_sync(0xffffffffu, finished, 0);
+                if (!finished) {          // the m terms of the next trial point side by side (divisions, square root)
+                    __syncwarp();
+                    if (lane < a.m) s_has[lane] = s_mach.step_term(lane, &s_gt[lane], &s_wt[lane]) ? 1 : 0;
+                    __syncwarp();
+                    if (lane == 0) s_mach.step_sum(s_gt, s_wt, s_has);
+                    __syncwarp();
+                }
+                if (finished && !timed_out) next_final = 1;          // one more pass at the solution, storing x*(y)
+            }
+            __syncwarp();
+            NB_TR(if (lane == 0 && gen < kTraceGens) sa.trace[16 * gen + 7] = nb_gtime();)
+            if (final_pass || timed_out) {
+                // publish the result of the solve: raw sums of the final pass, multipliers, counts
+                if (lane < NV) sa.res_host[lane] = total;
+                if (lane < a.m) sa.res_host[24 + lane] = s_mach.y[lane];
+                if (lane == 0) {
+                    sa.res_host[24 + kMaxParamM] = (double) s_mach.nevals;
+                    sa.res_host[24 + kMaxParamM + 1] = (double) s_mach.ret;
+                    sa.res_host[24 + kMaxParamM + 2] = (double) gen;
+                }
+                __threadfence_system();
+                __syncwarp();
+                if (lane == 0) {
+                    *a.flag_host = a.seq;
+                    __threadfence_system();
+                    *reinterpret_cast<volatile int *>(&st->done) = 1;
+                    s_exit = 1;
+                }
+            } else {
+                // publish generation gen + 1
+                const double *trial = next_final ? s_mach.y : s_mach.ycur;
+                const unsigned long long ntag = sa.tag0 | (gen + 1);
+                NB_TR(if (lane == 0 && gen + 1 < kTraceGens) sa.trace[16 * (gen + 1)] = nb_gtime();)
+                if (lane < a.m) slot_put(st->pub + 2 * lane, trial[lane], ntag);
+                if (lane == 0) {
+                    double u = a.rho;
+                    for (int i = 0; i < a.m; ++i) u = addx(u, mulx(a.rhoc[i], trial[i]));
+                    slot_put(st->pub + 2 * kMaxParamM, u, ntag);
+                    slot_put(st->pub + 2 * (kMaxParamM + 1), __longlong_as_double((long long) next_final), ntag);
+                }
+                final_pass = next_final;
+            }
+            final_pass = __shfl_sync(0xffffffffu, final_pass, 0);
+        }
+        __syncthreads();
+        if (s_exit) return;
+    }
 }
 
 template <int VARIANT, int MAXM, bool FULL, int BLOCK, int UNROLL, int MINB>
@@ -730,6 +944,11 @@ __global__ void __launch_bounds__(BLOCK, MINB) dual_solve_kernel(const __grid_co
     constexpr int MR = MAXM > 0 ? MAXM : 1;
     constexpr int NV = 3 + MR;
     static_assert(BLOCK == 32 * kGroupWarps, "one group slot per CTA");
+    static_assert(kGroupWarps == kVirtualShards, "the folder CTA gives one warp to each virtual shard");
+    if (blockIdx.x == gridDim.x - 1) {
+        solve_folder<NV>(sa);
+        return;
+    }
     const DualArgs &a = sa.d;
     SolveState *st = sa.st;
     const int lane = threadIdx.x & 31;
@@ -740,65 +959,48 @@ __global__ void __launch_bounds__(BLOCK, MINB) dual_solve_kernel(const __grid_co
     __shared__ double s_u;
     __shared__ int s_store, s_exit;
     __shared__ unsigned long long s_claim[2];
-    __shared__ DualMachine s_mach;
-    int parity = 0;
 
-    // bootstrap: one thread starts the optimiser and publishes generation 1 at the warm-start point
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-        DualMachine &mm = st->mach;
-        int rc = mm.start(a.m, sa.d.y, sa.lo, sa.hi, sa.stop);     // d.y carries the warm start
-        if (rc != kRetSuccess) {          // start point outside the box: report, publish nothing
-            sa.res_host[24 + kMaxParamM + 1] = (double) rc;
-            __threadfence_system();
-            *a.flag_host = a.seq;
-            __threadfence_system();
-            *reinterpret_cast<volatile int *>(&st->done) = 1;
-            __threadfence();
-        } else {
-            double u = a.rho;
-            for (int i = 0; i < a.m; ++i) { st->y[i] = mm.y[i]; u = addx(u, mulx(a.rhoc[i], mm.y[i])); }
-            st->u_ccsaq = u;
-            st->store = 0;
-            st->final_pass = 0;
-            __threadfence();
-            NB_TR(sa.trace[16] = nb_gtime();)
-            *reinterpret_cast<volatile unsigned long long *>(&st->gen) = 1;
-            __threadfence();
-        }
-    }
-    if (threadIdx.x == 0) s_claim[0] = atomicAdd(&st->claim, 1ull);
+    // ================================ sweeper CTAs ================================
+    unsigned long long next_c = 0;
+    if (threadIdx.x == 0) { s_exit = 0; s_claim[0] = atomicAdd(&st->claim, 1ull); }
     NB_TR(if (threadIdx.x == 0) { const unsigned long long t = nb_gtime(); atomicMax(&sa.trace[1], ~t); atomicMax(&sa.trace[2], t); })
     __syncthreads();
 
+    int parity = 0;
     unsigned long long my_gen = 0;        // generation whose multipliers are in s_y
-    const long long t_start = clock64();
     for (int it = 0;; ++it) {
         const unsigned long long c = s_claim[it & 1];
         const unsigned long long want = c / ngroups + 1;
         const unsigned gl = (unsigned) (c % ngroups);
         // wait until generation `want` is published (or the solve has finished); refresh the multipliers
         if (want != my_gen) {
-            if (threadIdx.x == 0) {
+            if (sub == 0) {                   // warp 0 polls, warp-uniformly: lane i < m: y_i, lane m: u, the others: flags
+                const int slot = lane < a.m ? lane : (lane == a.m ? kMaxParamM : kMaxParamM + 1);
+                const unsigned long long tag = sa.tag0 | want;
+                double v;
                 int ex = 0;
-                while (ld_volatile_u64(&st->gen) < want) {
-                    if (*reinterpret_cast<volatile int *>(&st->done)) { ex = 1; break; }
-                    __nanosleep(64);
+                unsigned spins = 0;
+                for (;;) {
+                    if (__all_sync(0xffffffffu, slot_get(st->pub + 2 * slot, tag, &v))) break;
+                    if ((++spins & 7u) == 0u && __any_sync(0xffffffffu, ld_gpu_s32(&st->done))) {
+                        ex = !__all_sync(0xffffffffu, slot_get(st->pub + 2 * slot, tag, &v));     // published before done was raised?
+                        break;
+                    }
+                    __nanosleep(20);
                 }
-                if (*reinterpret_cast<volatile int *>(&st->done) && ld_volatile_u64(&st->gen) < want) ex = 1;
-                s_exit = ex;
+                if (ex) s_exit = 1;
+                else if (lane < a.m) s_y[lane] = v;
+                else if (lane == a.m) s_u = v;
+                else if (lane == a.m + 1) s_store = (int) (__double_as_longlong(v) & 1ll);
             }
             __syncthreads();
             if (s_exit) return;
             NB_TR(if (threadIdx.x == 0 && want < kTraceGens) { const unsigned long long t = nb_gtime();
                       atomicMax(&sa.trace[16 * want + 1], ~t); atomicMax(&sa.trace[16 * want + 2], t); })
-            __threadfence();
-            if (threadIdx.x < a.m) s_y[threadIdx.x] = __ldcg(&st->y[threadIdx.x]);
-            if (threadIdx.x == 32) { s_u = __ldcg(&st->u_ccsaq); s_store = __ldcg(&st->store); }
             my_gen = want;
-            __syncthreads();
         }
-        // claim the next group early so that its index is ready after this group's barrier
-        if (threadIdx.x == 0) s_claim[(it + 1) & 1] = atomicAdd(&st->claim, 1ull);
+        // claim the next group now; the result is parked in a register until the sweep is over
+        if (threadIdx.x == 0) next_c = atomicAdd(&st->claim, 1ull);
 
         SharedMultipliers mu;
         mu.y = s_y; mu.rhoc = a.rhoc; mu.half_rhoc = a.half_rhoc;
@@ -816,138 +1018,17 @@ __global__ void __launch_bounds__(BLOCK, MINB) dual_solve_kernel(const __grid_co
 #pragma unroll
             for (int k = 0; k < NV; ++k) srec[sub * NV + k] = acc[k];
         }
+        if (threadIdx.x == 0) s_claim[(it + 1) & 1] = next_c;
         __syncthreads();
         parity ^= 1;
-        if (sub != 0) continue;
-        if (lane < NV) {
+        if (sub == 0 && lane < NV) {
             double s = srec[lane];
 #pragma unroll
             for (int w = 1; w < kGroupWarps; ++w) s = addx(s, srec[w * NV + lane]);
-            a.grouprecs[(unsigned long long) gl * a.nvp + lane] = s;
+            slot_put(sa.grouptags + 2ull * ((unsigned long long) lane * ngroups + gl), s, sa.tag0 | my_gen);
         }
-        __syncwarp();
-        NB_TR(if (lane == 0 && my_gen < kTraceGens) { const unsigned long long t = nb_gtime(); unsigned long long *r = sa.trace + 16 * my_gen;
+        NB_TR(if (sub == 0 && lane == 0 && my_gen < kTraceGens) { const unsigned long long t = nb_gtime(); unsigned long long *r = sa.trace + 16 * my_gen;
                   atomicMax(r + 3, ~t); atomicMax(r + 4, t); atomicAdd(r + 8, t - tr_s0); atomicAdd(r + 9, 1ull); })
-
-        // virtual-shard sum (monotonic ticket: every generation adds exactly P arrivals)
-        const unsigned vs_local = gl / a.segs_per_vshard;
-        {
-            unsigned t = 0;
-            __threadfence();
-            if (lane == 0) t = atomicAdd(&st->vtickets[vs_local], 1u);
-            t = __shfl_sync(0xffffffffu, t, 0);
-            __threadfence();
-            if ((t + 1u) % a.segs_per_vshard != 0u) continue;
-        }
-#pragma unroll
-        for (int k = 0; k < NV; ++k) acc[k] = 0.0;
-        {
-            const double *base = a.grouprecs + (unsigned long long) vs_local * a.segs_per_vshard * a.nvp;
-#pragma unroll 4
-            for (unsigned r = lane; r < a.segs_per_vshard; r += 32)      // loads of 4 rounds in flight, adds in order
-#pragma unroll
-                for (int k = 0; k < NV; ++k) acc[k] = addx(acc[k], __ldcg(base + (unsigned long long) r * a.nvp + k));
-        }
-        warp_fold<NV>(acc);
-        if (lane == 0) {
-            double *rec = a.vsums + (unsigned long long) vs_local * a.nvp;
-#pragma unroll
-            for (int k = 0; k < NV; ++k) rec[k] = acc[k];
-        }
-        {
-            unsigned t = 0;
-            __threadfence();
-            if (lane == 0) t = atomicAdd(&st->vtickets[kVirtualShards], 1u);
-            t = __shfl_sync(0xffffffffu, t, 0);
-            __threadfence();
-            if ((t + 1u) % a.local_vshards != 0u) continue;
-        }
-
-        // ---- this warp completed generation my_gen on this rank: total sums (exchange if sharded) ----
-        double total = 0.0;               // lane k < NV holds sum k
-        int timed_out = 0;
-        NB_TR(if (lane == 0 && my_gen < kTraceGens) sa.trace[16 * my_gen + 5] = nb_gtime();)
-        if (a.box[0] == nullptr) {
-            if (lane < NV) {
-                total = __ldcg(a.vsums + lane);
-                for (unsigned v = 1; v < a.local_vshards; ++v) total = addx(total, __ldcg(a.vsums + (unsigned long long) v * a.nvp + lane));
-            }
-        } else {
-            total = box_exchange(a.box, a.rank, a.world, a.seq + my_gen, a.vsums, a.nvp, a.local_vshards,
-                                 a.seg0 / a.segs_per_vshard, NV, lane, &timed_out);     // one tag per generation
-        }
-
-        NB_TR(if (lane == 0 && my_gen < kTraceGens) sa.trace[16 * my_gen + 6] = nb_gtime();)
-        // ---- the dual optimiser's turn (one lane; the machine is staged through shared memory) ----
-        {
-            const double *src = reinterpret_cast<const double *>(&st->mach);
-            double *dst = reinterpret_cast<double *>(&s_mach);
-            for (int i = lane; i < (int) (sizeof(DualMachine) / sizeof(double)); i += 32) dst[i] = __ldcg(src + i);
-        }
-        __syncwarp();
-        const int final_pass = *reinterpret_cast<volatile int *>(&st->final_pass);
-        // F and grad F from the sums, constants added in the reference's order (mma.c:75-78, :135)
-        double gci = 0.0;
-        if (lane >= 3 && lane < 3 + a.m) gci = addx(sa.cval[lane - 3], total);      // g_i(y)
-        int finished = 0, next_store = 0, next_final = 0;
-        if (!final_pass) {
-            double val = sa.fval;
-            for (int i = 0; i < a.m; ++i) val = addx(val, mulx(s_y[i], sa.cval[i]));
-            val = addx(val, __shfl_sync(0xffffffffu, total, 0));
-            __shared__ double s_grad[kMaxParamM];
-            if (lane >= 3 && lane < 3 + a.m) s_grad[lane - 3] = -gci;
-            __syncwarp();
-            if (lane == 0) {
-                const double elapsed = (double) (clock64() - t_start) * 5e-10;     // ~2 GHz; only feeds maxtime
-                finished = timed_out ? 1 : (s_mach.feed(-val, s_grad, elapsed) ? 1 : 0);
-                if (timed_out) s_mach.ret = kRetFailure;
-            }
-            finished = __shfl_sync(0xffffffffu, finished, 0);
-            if (finished && !timed_out) { next_store = 1; next_final = 1; }          // one more pass at the solution
-        }
-        __syncwarp();
-        NB_TR(if (lane == 0 && my_gen < kTraceGens) sa.trace[16 * my_gen + 7] = nb_gtime();)
-        if (final_pass || timed_out) {
-            // publish the result of the solve: raw sums of the final pass, multipliers, counts
-            if (lane < NV) sa.res_host[lane] = total;
-            if (lane < a.m) sa.res_host[24 + lane] = s_mach.y[lane];
-            if (lane == 0) {
-                sa.res_host[24 + kMaxParamM] = (double) s_mach.nevals;
-                sa.res_host[24 + kMaxParamM + 1] = (double) s_mach.ret;
-                sa.res_host[24 + kMaxParamM + 2] = (double) my_gen;
-            }
-            __threadfence_system();
-            __syncwarp();
-            if (lane == 0) {
-                *a.flag_host = a.seq;
-                __threadfence_system();
-                *reinterpret_cast<volatile int *>(&st->done) = 1;
-                __threadfence();
-            }
-            continue;      // the next wait sees done and leaves
-        }
-        // publish generation my_gen + 1
-        {
-            const double *trial = next_final ? s_mach.y : s_mach.ycur;
-            if (lane < a.m) st->y[lane] = trial[lane];
-            if (lane == 0) {
-                double u = a.rho;
-                for (int i = 0; i < a.m; ++i) u = addx(u, mulx(a.rhoc[i], trial[i]));
-                st->u_ccsaq = u;
-                st->store = next_store;
-                st->final_pass = next_final;
-            }
-            double *dstm = reinterpret_cast<double *>(&st->mach);
-            const double *srcm = reinterpret_cast<const double *>(&s_mach);
-            for (int i = lane; i < (int) (sizeof(DualMachine) / sizeof(double)); i += 32) dstm[i] = srcm[i];
-            __threadfence();
-            __syncwarp();
-            if (lane == 0) {
-                NB_TR(if (my_gen + 1 < kTraceGens) sa.trace[16 * (my_gen + 1)] = nb_gtime();)
-                *reinterpret_cast<volatile unsigned long long *>(&st->gen) = my_gen + 1;
-                __threadfence();
-            }
-        }
     }
 }
 

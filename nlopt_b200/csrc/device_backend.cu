@@ -191,6 +191,7 @@ void DeviceBackend::free_state()
     owned_.clear();
     if (xfull_dev_) cudaFree(xfull_dev_);
     solve_state_ = nullptr;
+    grouptags_ = nullptr;
     res_host_ = nullptr;
     if (h_x_) BlockCache::get().give(true, (size_t) geo_.n * sizeof(double), h_x_);
     for (int b = 0; b < 2; ++b) {
@@ -285,6 +286,7 @@ bool DeviceBackend::alloc_workspace()
 {
     if (partials_) { release_small(partials_); partials_ = nullptr; }
     if (grouprecs_) { release_small(grouprecs_); grouprecs_ = nullptr; }
+    if (grouptags_) { release_small(grouptags_); grouptags_ = nullptr; }
     if (vsums_) { release_small(vsums_); vsums_ = nullptr; }
     {
         const int maxm = pick_maxm((int) m_);
@@ -710,6 +712,15 @@ bool DeviceBackend::dual_solve(double *y, const double *lo, const double *hi, co
     SolveArgs sa;
     fill_dual_args(sa.d, y, sc, 0, (int) m_);
     sa.st = static_cast<SolveState *>(solve_state_);
+    if (!grouptags_ || solve_launch_id_ >= (1ull << 23)) {       // tags are (launch id, generation): start from a clean slate
+        const size_t bytes = (size_t) geo_.nseg_local * nvp_ * 2 * sizeof(double);
+        if (!grouptags_ && !small_dev((void **) &grouptags_, bytes)) return false;
+        NB_CUDA(cudaMemsetAsync(grouptags_, 0, bytes, stream_));
+        NB_CUDA(cudaMemsetAsync(solve_state_, 0, sizeof(SolveState), stream_));
+        solve_launch_id_ = 0;
+    }
+    sa.grouptags = grouptags_;
+    sa.tag0 = ++solve_launch_id_ << 40;
     sa.fval = sc.fval;
     for (unsigned i = 0; i < (unsigned) kMaxParamM; ++i) {
         sa.cval[i] = i < m_ ? ((variant_ == kMMA && std::isnan(sc.fcval[i])) ? 0.0 : sc.fcval[i]) : 0.0;
@@ -733,12 +744,12 @@ bool DeviceBackend::dual_solve(double *y, const double *lo, const double *hi, co
     int per_sm = 0;
     NB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, 256, 0));
     if (per_sm < 1) return fail("dual_solve_kernel does not fit on an SM");
-    long long grid = (long long) per_sm * sm_count_;
-    if (grid > (long long) geo_.nseg_local) grid = geo_.nseg_local;
-    if (grid < 1) grid = 1;
+    long long grid = (long long) per_sm * sm_count_;          // all co-resident: sweepers + the folder CTA (the last one)
+    if (grid > (long long) geo_.nseg_local + 1) grid = (long long) geo_.nseg_local + 1;
+    if (grid < 2) return fail("dual_solve_kernel needs two co-resident CTAs");
 
-    // the head of the state (claim counter, generation, flags, tickets) starts from zero every launch
-    NB_CUDA(cudaMemsetAsync(solve_state_, 0, offsetof(SolveState, u_ccsaq), stream_));
+    // the head of the state (claim counter, done flag) starts from zero every launch
+    NB_CUDA(cudaMemsetAsync(solve_state_, 0, offsetof(SolveState, pub), stream_));
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (time_kernels_) {
         if (ev_used_ + 2 > ev_pool_.size()) {
@@ -779,7 +790,8 @@ bool DeviceBackend::dual_solve(double *y, const double *lo, const double *hi, co
             for (int g = 1; g < kTraceGens && h[16 * g]; ++g) {
                 const unsigned long long *r = &h[16 * g];
                 const unsigned long long p = r[0];
-                std::fprintf(f, "  gen %d seen[%lld..%lld] recs[%lld..%lld] rank_done %lld totals %lld machine %lld next_pub %lld | mean_group_sweep %llu ns x %llu\n", g,
+                std::fprintf(f, "  gen %d phase0 %lld phase3 %lld phase7 %lld polls_t0 %llu t0_at_barrier %lld seen[%lld..%lld] recs[%lld..%lld] rank_done %lld totals %lld machine %lld next_pub %lld | mean_group_sweep %llu ns x %llu\n", g,
+                             (long long) (r[10] - p), (long long) (r[11] - p), (long long) (r[12] - p), r[13], (long long) (r[14] - p),
                              (long long) (~r[1] - p), (long long) (r[2] - p), (long long) (~r[3] - p), (long long) (r[4] - p),
                              (long long) (r[5] - p), (long long) (r[6] - p), (long long) (r[7] - p),
                              (long long) (h[16 * (g + 1)] ? h[16 * (g + 1)] - p : 0), r[9] ? r[8] / r[9] : 0ull, r[9]);

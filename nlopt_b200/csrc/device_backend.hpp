@@ -84,6 +84,8 @@ private:
     int sm_count_ = 148, ctas_per_sm_ = 0;
     void *solve_state_ = nullptr;     // SolveState (device) of the persistent dual-solve kernel
     double *res_host_ = nullptr;      // its mapped pinned result record
+    double *grouptags_ = nullptr;     // its tagged group-record slots {value, tag}, [local groups][nvp]
+    unsigned long long solve_launch_id_ = 0;   // tag = launch id << 40 | generation: never matches a stale slot
     bool fused_solve_ok_ = true;
     int kernel_cfg_ = -1;         // -1: measured default for (variant, m)          // index into the launch-geometry table of device_backend.cu
 

@@ -98,14 +98,21 @@ struct DualMachine {
     // (result code in ret, multipliers in y, best value in fmin).
     NB_HD bool feed(double F, const double *grad, double elapsed)
     {
+        if (feed_pre(F, grad, elapsed)) return true;
+        step();
+        return false;
+    }
+
+    // feed() without the closing step(): a warp runs step_term(i) on m lanes side by side and then
+    // step_sum() on one (same operations in the same order => same bits as step()).
+    NB_HD bool feed_pre(double F, const double *grad, double elapsed)
+    {
         if (awaiting_first) {                            // mma.c:218
             awaiting_first = 0;
             for (int i = 0; i < m; ++i) { g[i] = grad[i]; ycur[i] = y[i]; }
             fbase = fmin = fcur = F;
             nevals = 1;
-            if (outer_top(elapsed)) return true;
-            step();
-            return false;
+            return outer_top(elapsed);
         }
         fcur = F;                                        // mma.c:297
         ++nevals;
@@ -122,8 +129,42 @@ struct DualMachine {
             const double a = 10 * rho, b = 1.1 * (rho + (fcur - gval) / wval);
             rho = a < b ? a : b;
         }
-        step();
         return false;
+    }
+
+    // Term i of the MMA dual evaluation with zero constraints on the m dual variables (mma.c:59-137, m = 0):
+    // ycur_i <- argmin of the separable approximant around y; false: sigma_i == 0, no contribution.
+    NB_HD bool step_term(int i, double *gterm, double *wterm)
+    {
+        const double s = sigma[i];
+        if (s == 0) { ycur[i] = y[i]; return false; }
+        double u = g[i];
+        const double v = fabs(g[i]) * s + 0.5 * rho;
+        const double s2 = s * s;
+        u *= s2;
+        const double r = u / (v * s);
+        double dy = (u / v) / (-1 - sqrt(fabs(1 - r * r)));
+        double yc = y[i] + dy;
+        if (yc > hi[i]) yc = hi[i];
+        else if (yc < lo[i]) yc = lo[i];
+        if (yc > y[i] + 0.9 * s) yc = y[i] + 0.9 * s;
+        else if (yc < y[i] - 0.9 * s) yc = y[i] - 0.9 * s;
+        ycur[i] = yc;
+        dy = yc - y[i];
+        const double dy2 = dy * dy, dinv = 1.0 / (s2 - dy2), c = s2 * dy;
+        *gterm = (g[i] * c + (fabs(g[i]) * s + 0.5 * rho) * dy2) * dinv;
+        *wterm = 0.5 * dy2 * dinv;
+        return true;
+    }
+
+    // gval / wval as at mma.c:123-125: the terms added in index order
+    NB_HD void step_sum(const double *gterm, const double *wterm, const int *has)
+    {
+        double gs = fbase, ws = 0;
+        for (int i = 0; i < m; ++i)
+            if (has[i]) { gs += gterm[i]; ws += wterm[i]; }
+        gval = gs;
+        wval = ws;
     }
 
 private:
@@ -164,30 +205,12 @@ private:
         return false;
     }
 
-    // One MMA dual evaluation with zero constraints on the m dual variables (mma.c:59-137, m = 0):
-    // ycur <- argmin of the separable approximant around y; gval/wval as at mma.c:123-125.
     NB_HD void step()
     {
         double gs = fbase, ws = 0;
         for (int i = 0; i < m; ++i) {
-            const double s = sigma[i];
-            if (s == 0) { ycur[i] = y[i]; continue; }
-            double u = g[i];
-            const double v = fabs(g[i]) * s + 0.5 * rho;
-            const double s2 = s * s;
-            u *= s2;
-            const double r = u / (v * s);
-            double dy = (u / v) / (-1 - sqrt(fabs(1 - r * r)));
-            double yc = y[i] + dy;
-            if (yc > hi[i]) yc = hi[i];
-            else if (yc < lo[i]) yc = lo[i];
-            if (yc > y[i] + 0.9 * s) yc = y[i] + 0.9 * s;
-            else if (yc < y[i] - 0.9 * s) yc = y[i] - 0.9 * s;
-            ycur[i] = yc;
-            dy = yc - y[i];
-            const double dy2 = dy * dy, dinv = 1.0 / (s2 - dy2), c = s2 * dy;
-            gs += (g[i] * c + (fabs(g[i]) * s + 0.5 * rho) * dy2) * dinv;
-            ws += 0.5 * dy2 * dinv;
+            double gt, wt;
+            if (step_term(i, &gt, &wt)) { gs += gt; ws += wt; }
         }
         gval = gs;
         wval = ws;

@@ -46,7 +46,7 @@ def run(n, alg="ccsaq", extra=()):
                     "--no-cpu", "--no-e2e", *extra], env=env, check=True, stdout=subprocess.DEVNULL)
     cols = {k: [] for k in ("seen_lo", "seen_hi", "rec_lo", "rec_hi", "rank_done", "totals", "machine", "next_pub", "sweep")}
     head = ""
-    pat = re.compile(r"gen \d+ seen\[(-?\d+)\.\.(-?\d+)\] recs\[(-?\d+)\.\.(-?\d+)\] rank_done (-?\d+) totals (-?\d+) machine (-?\d+) next_pub (-?\d+) \| mean_group_sweep (\d+)")
+    pat = re.compile(r"gen \d+ .*?seen\[(-?\d+)\.\.(-?\d+)\] recs\[(-?\d+)\.\.(-?\d+)\] rank_done (-?\d+) totals (-?\d+) machine (-?\d+) next_pub (-?\d+) \| mean_group_sweep (\d+)")
     for line in open(out):
         if line.startswith("solve"):
             head = line.strip()
@@ -57,7 +57,7 @@ def run(n, alg="ccsaq", extra=()):
     print(head)
     print(f"n={n} {alg}: {len(cols['sweep'])} generations; medians in ns after the generation was published:")
     for k, v in cols.items():
-        print(f"  {k:10s} {statistics.median(v):9.0f}")
+        print(f"  {k:10s} {statistics.median(v) if v else -1:9.0f}")
 
 
 if __name__ == "__main__":
