@@ -54,6 +54,15 @@ public:
     virtual bool eval_objective(Slot slot, bool want_grad, double *value) = 0;
     virtual bool eval_constraint(Slot slot, unsigned ic, unsigned row0, bool want_grad, double *values) = 0;
 
+    // Called once after the objective and all constraints of one point have been evaluated.  A backend may have
+    // returned rank-local partial values from eval_objective / eval_constraint (device callbacks on several
+    // ranks); this turns them into the global values with ONE exchange.  Default: values are final already.
+    virtual bool finish_evals(double *fvalue, double *cvalues)
+    {
+        (void) fvalue; (void) cvalues;
+        return true;
+    }
+
     // One dual evaluation for multipliers y[m] (mma.c:59-137 / ccsa_quadratic.c:79-148).
     // In the MMA flavour a NaN sc.fcval[i] switches constraint i off (mma.c:78,103,126).
     // materialize == true also stores x*(y) into xcur.

@@ -21,10 +21,24 @@ struct FuncSpec {
     void *data = nullptr;
 };
 
+// The augmented-Lagrangian objective of NLOPT_AUGLAG* (src/algs/auglag/auglag.c:25-65), evaluated by the backend:
+//   L(x) = f(x) + rho/2 sum_k (h_k(x) + lambda_k/rho)^2 + rho/2 sum_k max(0, c_k(x) + mu_k/rho)^2
+// and, where a gradient is wanted, grad L = grad f + sum_k coef_k grad(h_k | c_k) accumulated in the reference's
+// order.  The caller owns the multipliers and changes them (and rho) between sub-optimisations.
+struct PenaltySpec {
+    std::vector<FuncSpec> eq, ineq;          // constraint objects folded into the objective
+    double rho = 1.0;
+    const double *lambda = nullptr;          // one per scalar equality constraint
+    const double *mu = nullptr;              // one per scalar inequality constraint
+    int *nevals_p = nullptr;                 // the outer object's evaluation counter (auglag.c:38)
+    const int *force_stop = nullptr;         // the outer object's force-stop flag (auglag.c:39)
+};
+
 struct BackendConfig {
     Variant variant = kMMA;
     unsigned n = 0;                          // global problem size
     FuncSpec objective;
+    const PenaltySpec *penalty = nullptr;    // non-null: `objective` is f of the augmented Lagrangian above
     std::vector<FuncSpec> constraints;       // inequality constraint objects, in registration order
     const double *lb = nullptr, *ub = nullptr;   // host, n entries
     bool lb_uniform = false, ub_uniform = false; // all entries equal lb[0] / ub[0]: fill on the device, no H2D

@@ -93,10 +93,11 @@ int ccsa_minimize(Variant variant, Backend &be, const std::vector<double> &tol, 
     // ---- first evaluation at the starting point, with gradients (mma.c:218-233) ----
     double fbase, fcur;
     if (!be.eval_objective(kBase, true, &fbase)) return L.fail("objective evaluation");
-    fcur = *minf = fbase;
     ++*stop.nevals_p;
     if (L.forced()) return R_FORCED;
     if ((ret = L.eval_constraints(kBase, true, c.data())) != R_SUCCESS) return ret;
+    if (!be.finish_evals(&fbase, c.data())) return L.fail("function value exchange");
+    fcur = *minf = fbase;
     bool feasible = true;
     double infeas = 0;
     for (unsigned i = 0; i < m; ++i) {
@@ -213,6 +214,7 @@ int ccsa_minimize(Variant variant, Backend &be, const std::vector<double> &tol, 
             ++inner_nevals;
             if (L.forced()) return R_FORCED;
             if ((ret = L.eval_constraints(kCandidate, prm.inner_gradients != 0, c_cur.data())) != R_SUCCESS) return ret;
+            if (!be.finish_evals(&fcur, c_cur.data())) return L.fail("function value exchange");
             if (stats) stats->seconds_eval += wall_seconds() - t_eval0;
             bool feasible_cur = true, inner_done = g0 >= fcur, new_infeasible = false;
             double infeas_cur = 0;
@@ -242,9 +244,11 @@ int ccsa_minimize(Variant variant, Backend &be, const std::vector<double> &tol, 
                 if (!prm.inner_gradients) {
                     // gradients are needed now; evaluation count is left alone (mma.c:339-370)
                     if (!be.eval_objective(kCandidate, true, &fcur)) return L.fail("objective evaluation");
+                    if (!be.finish_evals(&fcur, nullptr)) return L.fail("function value exchange");
                     if (L.forced()) return R_FORCED;
                     if (is_mma) inner_done = g0 >= fcur;          // mma.c:346 (absent in ccsa_quadratic.c)
                     if ((ret = L.eval_constraints(kCandidate, true, c_cur.data())) != R_SUCCESS) return ret;
+                    if (!be.finish_evals(nullptr, c_cur.data())) return L.fail("function value exchange");
                     classify(false);
                 }
                 fbase = *minf = fcur;

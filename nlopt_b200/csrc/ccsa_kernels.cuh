@@ -806,15 +806,22 @@ __device__ __noinline__ void solve_folder(const SolveArgs &sa)
             slot_put(st->pub + 2 * (kMaxParamM + 1), __longlong_as_double(0ll), sa.tag0 | 1ull);
         }
     }
+    for (int i = threadIdx.x; i < kVirtualShards * kGroupWarps * NV; i += 32 * kGroupWarps) s_w[i] = 0.0;
+    const unsigned fw_all = (a.segs_per_vshard + 31u) / 32u;
+    const unsigned fw_per = fw_all < (unsigned) kGroupWarps ? fw_all : (unsigned) kGroupWarps;      // non-empty fold warps per shard
+    const unsigned nitems = a.local_vshards * fw_per;
     __syncthreads();
     if (s_exit) return;
     const long long t_start = clock64();
     for (unsigned long long gen = 1;; ++gen) {
         const unsigned long long tag = sa.tag0 | gen;
-        // ---- shard sums, canonical order (see fold_shard_records): all 256 threads take one shard after the
-        // other -- shards complete roughly in index order, so when the last record of the generation lands only
-        // ceil(P / 256) polls of the last shard are still outstanding ----
-        for (unsigned v = 0; v < a.local_vshards; ++v) {
+        // ---- shard sums, canonical order (see fold_shard_records).  Work item (v, w) = fold warp w of local
+        // shard v: chains t = 32 w + lane over records t, t + 256, ...  Items are dealt round-robin to the 8
+        // physical warps in (v, w) order -- shards complete roughly in index order, and when P <= 32 (small n, or
+        // one shard per rank with 8 GPUs) all shards are polled side by side.  Empty fold warps contribute the
+        // +0.0 parked in s_w at start-up.
+        for (unsigned item = sub; item < nitems; item += kGroupWarps) {
+            const unsigned v = item / fw_per, w = item % fw_per;
             double acc[NV];
 #pragma unroll
             for (int k = 0; k < NV; ++k) acc[k] = 0.0;
@@ -822,7 +829,7 @@ __device__ __noinline__ void solve_folder(const SolveArgs &sa)
             const double *base = sa.grouptags + 2ull * (unsigned long long) v * a.segs_per_vshard;
             // warp-uniform control flow: a warp polls until all of its lanes have their record (measured: a warp
             // whose lanes left the poll loop at different times took ~9 us per shard instead of < 1 us)
-            for (unsigned r0 = 32u * sub; r0 < a.segs_per_vshard; r0 += 32 * kGroupWarps) {
+            for (unsigned r0 = 32u * w; r0 < a.segs_per_vshard; r0 += 32 * kGroupWarps) {
                 const unsigned r = r0 + lane;
                 const bool has = r < a.segs_per_vshard;
                 const double *rec = base + 2ull * (has ? r : 0u);
@@ -831,7 +838,6 @@ __device__ __noinline__ void solve_folder(const SolveArgs &sa)
                     bool all = true;
 #pragma unroll
                     for (int k = 0; k < NV; ++k) all = slot_peek(rec + 2ull * k * ngroups, tag, &val[k]) && all;
-                    NB_TR(if (threadIdx.x == 0 && gen < kTraceGens) atomicAdd(&sa.trace[16 * gen + 13], 1ull);)
                     if (__all_sync(0xffffffffu, all || !has)) break;
                     __nanosleep(20);
                 }
@@ -840,11 +846,10 @@ __device__ __noinline__ void solve_folder(const SolveArgs &sa)
                     for (int k = 0; k < NV; ++k) acc[k] = addx(acc[k], val[k]);
                 }
             }
-            NB_TR(if (threadIdx.x == 0 && gen < kTraceGens && (v == 0 || v == 3 || v == 7)) sa.trace[16 * gen + (v == 0 ? 10 : v == 3 ? 11 : 12)] = nb_gtime();)
             warp_fold<NV>(acc);
             if (lane == 0) {
 #pragma unroll
-                for (int k = 0; k < NV; ++k) s_w[(v * kGroupWarps + sub) * NV + k] = acc[k];
+                for (int k = 0; k < NV; ++k) s_w[(v * kGroupWarps + w) * NV + k] = acc[k];
             }
         }
         NB_TR(if (threadIdx.x == 0 && gen < kTraceGens) sa.trace[16 * gen + 14] = nb_gtime();)
@@ -1029,6 +1034,27 @@ __global__ void __launch_bounds__(BLOCK, MINB) dual_solve_kernel(const __grid_co
         }
         NB_TR(if (sub == 0 && lane == 0 && my_gen < kTraceGens) { const unsigned long long t = nb_gtime(); unsigned long long *r = sa.trace + 16 * my_gen;
                   atomicMax(r + 3, ~t); atomicMax(r + 4, t); atomicAdd(r + 8, t - tr_s0); atomicAdd(r + 9, 1ull); })
+    }
+}
+
+// Gradient of the augmented-Lagrangian objective (auglag.c:47-48, :59-60): g_j += coef_k * row_k[j] for the
+// K penalty rows in index order, separate multiply and add like the reference's loop (=> bit-identical gradient).
+// Rows with coef == 0 flagged by `skip` are left out entirely (an inactive inequality adds nothing, auglag.c:57).
+constexpr int kPenaltyRowsPerLaunch = 16;
+struct PenaltyCoefs {
+    double c[kPenaltyRowsPerLaunch];
+    int row[kPenaltyRowsPerLaunch];       // index of the row in the scratch block
+    int count;
+};
+__global__ void __launch_bounds__(kBlock) penalty_axpy_kernel(double *__restrict__ g, const double *__restrict__ rows,
+                                                               unsigned long long ld, unsigned long long n_local,
+                                                               const __grid_constant__ PenaltyCoefs pc)
+{
+    const unsigned long long stride = (unsigned long long) gridDim.x * blockDim.x;
+    for (unsigned long long j = (unsigned long long) blockIdx.x * blockDim.x + threadIdx.x; j < n_local; j += stride) {
+        double v = g[j];
+        for (int k = 0; k < pc.count; ++k) v = addx(v, mulx(pc.c[k], rows[(unsigned long long) pc.row[k] * ld + j]));
+        g[j] = v;
     }
 }
 

@@ -185,6 +185,8 @@ void DeviceBackend::free_state()
     if (stream_) cudaStreamSynchronize(stream_);
     if (copy_stream_) cudaStreamSynchronize(copy_stream_);
     if (pool_) BlockCache::get().give(false, pool_bytes_, pool_);
+    if (pen_rows_) BlockCache::get().give(false, (size_t) pen_total_ * geo_.ld * sizeof(double), pen_rows_);
+    pen_rows_ = nullptr;
     if (w_dev_) cudaFree(w_dev_);
     if (xtol_abs_dev_) cudaFree(xtol_abs_dev_);
     for (const Owned &o : owned_) BlockCache::get().give(o.pinned, o.bytes, o.p);   // every small buffer
@@ -333,9 +335,20 @@ bool DeviceBackend::setup(const BackendConfig &cfg)
         m_ += c.m;
         if (c.m > max_cdim_) max_cdim_ = c.m;
     }
+    pen_total_ = 0;
+    if (cfg.penalty)
+        for (int pass = 0; pass < 2; ++pass)
+            for (const FuncSpec &c : (pass == 0 ? cfg.penalty->eq : cfg.penalty->ineq)) {
+                pen_total_ += c.m;
+                if (c.m > max_cdim_) max_cdim_ = c.m;
+            }
     if (cfg.stats) stats_ = cfg.stats;
     if (!alloc_state()) return false;
     const size_t nl = geo_.n_local, j0 = geo_.j0;
+    if (pen_total_) {
+        NB_CUDA(cached_malloc(&pen_rows_, (size_t) pen_total_ * geo_.ld * sizeof(double)));
+        NB_CUDA(cudaMemsetAsync(pen_rows_, 0, (size_t) pen_total_ * geo_.ld * sizeof(double), stream_));
+    }
     // bounds and start point
     if (cfg.lb_uniform) {
         fill_kernel<<<grid_for(nl), kBlock, 0, stream_>>>(lb_, cfg.lb[0], nl);
@@ -353,6 +366,9 @@ bool DeviceBackend::setup(const BackendConfig &cfg)
     }
     bool any_host_cb = cfg.objective.f != nullptr;
     for (const FuncSpec &c : cfg.constraints) any_host_cb = any_host_cb || c.f || c.mf;
+    if (cfg.penalty)
+        for (int pass = 0; pass < 2; ++pass)
+            for (const FuncSpec &c : (pass == 0 ? cfg.penalty->eq : cfg.penalty->ineq)) any_host_cb = any_host_cb || c.f || c.mf;
     if (any_host_cb) {
         NB_CUDA(cached_host_alloc(&h_x_, (size_t) geo_.n * sizeof(double)));
         h_grad_cap_ = (size_t) max_cdim_ * geo_.n;
@@ -456,6 +472,104 @@ bool DeviceBackend::host_x_for(Slot slot)
 bool DeviceBackend::push_grad_rows(Slot slot, int row0, unsigned rows, bool is_objective, const double *host_grad)
 {
     double *dst = is_objective ? (slot == kBase ? g_ : gcur_) : (slot == kBase ? G_ : Gcur_) + (size_t) row0 * geo_.ld;
+    return push_rows_to(dst, rows, host_grad);
+}
+
+bool DeviceBackend::eval_objective(Slot slot, bool want_grad, double *value)
+{
+    return cfg_.penalty ? eval_penalty_objective(slot, want_grad, value) : eval_user_objective(slot, want_grad, value);
+}
+
+// The augmented-Lagrangian objective (PenaltySpec, backend_factory.hpp; auglag.c:25-65).  The constraint gradients
+// go to scratch rows in HBM (uploaded through the same pinned staging pipeline as everything else, or written by
+// device callbacks); one kernel then adds the active ones to grad f.  Only the m' + p' values visit the host.
+bool DeviceBackend::eval_penalty_objective(Slot slot, bool want_grad, double *value)
+{
+    const PenaltySpec &ps = *cfg_.penalty;
+    double L = 0;
+    if (!eval_user_objective(slot, want_grad, &L)) return false;
+    if (!finish_evals(&L, nullptr)) return false;
+    if (ps.nevals_p) ++*ps.nevals_p;
+    *value = L;
+    if (ps.force_stop && *ps.force_stop) return true;               // auglag.c:39
+    std::vector<double> vals(pen_total_ ? pen_total_ : 1);
+    double *xs = slot == kBase ? x_ : xcur_view();
+    Comm &comm = Comm::instance();
+    std::vector<char> partial(pen_total_ ? pen_total_ : 1, 0);
+    unsigned row = 0;
+    bool any_partial = false;
+    for (int pass = 0; pass < 2; ++pass)
+        for (const FuncSpec &fs : (pass == 0 ? ps.eq : ps.ineq)) {
+            if (fs.df) {
+                const double t0 = wall_seconds();
+                vals[row] = fs.df((unsigned) geo_.n_local, geo_.j0, xs, want_grad ? pen_rows_ + (size_t) row * geo_.ld : nullptr, fs.data, stream_);
+                cb_seconds_ += wall_seconds() - t0;
+                if (comm.active()) { partial[row] = 1; any_partial = true; }
+            } else {
+                if (!host_x_for(slot)) return false;
+                double *grad = want_grad ? staging(fs.m) : nullptr;
+                const double t0 = wall_seconds();
+                if (fs.f) vals[row] = fs.f((unsigned) geo_.n, h_x_, grad, fs.data);        // nlopt_eval_constraint, stop.c:178-184
+                else fs.mf(fs.m, &vals[row], (unsigned) geo_.n, h_x_, grad, fs.data);
+                cb_seconds_ += wall_seconds() - t0;
+                if (want_grad && !push_rows_to(pen_rows_ + (size_t) row * geo_.ld, fs.m, grad)) return false;
+            }
+            row += fs.m;
+            if (ps.force_stop && *ps.force_stop) return true;
+        }
+    if (any_partial) {                 // shard-local values of device callbacks: one all-reduce for all of them
+        std::vector<double> buf(pen_total_);
+        for (unsigned k = 0; k < pen_total_; ++k) buf[k] = partial[k] ? vals[k] : 0.0;
+        double *tmp = nullptr;
+        NB_CUDA(cached_malloc(&tmp, pen_total_ * sizeof(double)));
+        NB_CUDA(cudaMemcpyAsync(tmp, buf.data(), pen_total_ * sizeof(double), cudaMemcpyHostToDevice, stream_));
+        if (comm.all_reduce_sum(tmp, pen_total_, stream_, &err_)) return false;
+        NB_CUDA(cudaMemcpyAsync(buf.data(), tmp, pen_total_ * sizeof(double), cudaMemcpyDeviceToHost, stream_));
+        NB_CUDA(cudaStreamSynchronize(stream_));
+        BlockCache::get().give(false, pen_total_ * sizeof(double), tmp);
+        for (unsigned k = 0; k < pen_total_; ++k)
+            if (partial[k]) vals[k] = buf[k];
+    }
+    // values -> L and the coefficients of the gradient rows, in the reference's order (auglag.c:41-62)
+    PenaltyCoefs pc;
+    pc.count = 0;
+    double *gdst = slot == kBase ? g_ : gcur_;
+    auto flush = [&]() -> bool {
+        if (pc.count && want_grad) {
+            penalty_axpy_kernel<<<grid_for(geo_.n_local), kBlock, 0, stream_>>>(gdst, pen_rows_, geo_.ld, geo_.n_local, pc);
+            ++stats_->kernel_launches;
+            NB_CUDA(cudaGetLastError());
+        }
+        pc.count = 0;
+        return true;
+    };
+    unsigned neq = 0;
+    for (const FuncSpec &fs : ps.eq) neq += fs.m;
+    for (unsigned k = 0; k < pen_total_; ++k) {
+        double coef = 0;
+        bool active = true;
+        if (k < neq) {
+            const double h = vals[k] + ps.lambda[k] / ps.rho;
+            L += 0.5 * ps.rho * h * h;
+            coef = ps.rho * h;
+        } else {
+            const double fc = vals[k] + ps.mu[k - neq] / ps.rho;
+            active = fc > 0;
+            if (active) { L += 0.5 * ps.rho * fc * fc; coef = ps.rho * fc; }
+        }
+        if (active) {
+            pc.c[pc.count] = coef;
+            pc.row[pc.count] = (int) k;
+            if (++pc.count == kPenaltyRowsPerLaunch && !flush()) return false;
+        }
+    }
+    if (!flush()) return false;
+    *value = L;
+    return true;
+}
+
+bool DeviceBackend::push_rows_to(double *dst, unsigned rows, const double *host_grad)
+{
     const int b = host_grad == h_grad_[0] ? 0 : 1;
     NB_CUDA(cudaMemcpy2DAsync(dst, geo_.ld * sizeof(double), host_grad + geo_.j0, (size_t) geo_.n * sizeof(double),
                               geo_.n_local * sizeof(double), rows, cudaMemcpyHostToDevice, copy_stream_));
@@ -465,7 +579,7 @@ bool DeviceBackend::push_grad_rows(Slot slot, int row0, unsigned rows, bool is_o
     return true;
 }
 
-bool DeviceBackend::eval_objective(Slot slot, bool want_grad, double *value)
+bool DeviceBackend::eval_user_objective(Slot slot, bool want_grad, double *value)
 {
     const FuncSpec &fs = cfg_.objective;
     if (fs.df) {
@@ -474,12 +588,9 @@ bool DeviceBackend::eval_objective(Slot slot, bool want_grad, double *value)
         const double t0 = wall_seconds();
         double v = fs.df((unsigned) geo_.n_local, geo_.j0, xs, gs, fs.data, stream_);
         cb_seconds_ += wall_seconds() - t0;
-        Comm &comm = Comm::instance();
-        if (comm.active()) {           // shard contributions add up
-            NB_CUDA(cudaMemcpyAsync(scalar_dev_, &v, sizeof(double), cudaMemcpyHostToDevice, stream_));
-            if (comm.all_reduce_sum(scalar_dev_, 1, stream_, &err_)) return false;
-            NB_CUDA(cudaMemcpyAsync(&v, scalar_dev_, sizeof(double), cudaMemcpyDeviceToHost, stream_));
-            NB_CUDA(cudaStreamSynchronize(stream_));
+        if (Comm::instance().active()) {           // shard contributions add up: settled in finish_evals()
+            pend_val_[0] = v;
+            pend_mask_ |= 1ull;
         }
         *value = v;
         return true;
@@ -503,12 +614,9 @@ bool DeviceBackend::eval_constraint(Slot slot, unsigned ic, unsigned row0, bool 
         const double t0 = wall_seconds();
         double v = fs.df((unsigned) geo_.n_local, geo_.j0, xs, gs, fs.data, stream_);
         cb_seconds_ += wall_seconds() - t0;
-        Comm &comm = Comm::instance();
-        if (comm.active()) {
-            NB_CUDA(cudaMemcpyAsync(scalar_dev_, &v, sizeof(double), cudaMemcpyHostToDevice, stream_));
-            if (comm.all_reduce_sum(scalar_dev_, 1, stream_, &err_)) return false;
-            NB_CUDA(cudaMemcpyAsync(&v, scalar_dev_, sizeof(double), cudaMemcpyDeviceToHost, stream_));
-            NB_CUDA(cudaStreamSynchronize(stream_));
+        if (Comm::instance().active()) {
+            pend_val_[1 + row0] = v;
+            pend_mask_ |= 1ull << (1 + row0);
         }
         values[0] = v;
         return true;
@@ -520,6 +628,26 @@ bool DeviceBackend::eval_constraint(Slot slot, unsigned ic, unsigned row0, bool 
     else fs.mf(fs.m, values, (unsigned) geo_.n, h_x_, grad, fs.data);
     cb_seconds_ += wall_seconds() - t0;
     if (want_grad) return push_grad_rows(slot, (int) row0, fs.m, false, grad);
+    return true;
+}
+
+// Device callbacks on several ranks return shard-local values; one all-reduce settles every value of the point
+// (1 + m doubles; entries from host callbacks are global already and are not touched).
+bool DeviceBackend::finish_evals(double *fvalue, double *cvalues)
+{
+    if (!pend_mask_) return true;
+    Comm &comm = Comm::instance();
+    double buf[1 + kMaxParamM];
+    for (unsigned i = 0; i <= m_; ++i) buf[i] = ((pend_mask_ >> i) & 1ull) ? pend_val_[i] : 0.0;
+    const size_t cnt = 1 + (size_t) m_;
+    NB_CUDA(cudaMemcpyAsync(scalar_dev_, buf, cnt * sizeof(double), cudaMemcpyHostToDevice, stream_));
+    if (comm.all_reduce_sum(scalar_dev_, cnt, stream_, &err_)) return false;
+    NB_CUDA(cudaMemcpyAsync(buf, scalar_dev_, cnt * sizeof(double), cudaMemcpyDeviceToHost, stream_));
+    NB_CUDA(cudaStreamSynchronize(stream_));
+    if (fvalue && (pend_mask_ & 1ull)) { *fvalue = buf[0]; pend_mask_ &= ~1ull; }
+    if (cvalues)
+        for (unsigned i = 0; i < m_; ++i)
+            if ((pend_mask_ >> (1 + i)) & 1ull) { cvalues[i] = buf[1 + i]; pend_mask_ &= ~(1ull << (1 + i)); }
     return true;
 }
 

@@ -31,6 +31,10 @@ public:
     bool init_sigma(double sigma_min) override;
     bool eval_objective(Slot slot, bool want_grad, double *value) override;
     bool eval_constraint(Slot slot, unsigned ic, unsigned row0, bool want_grad, double *values) override;
+    bool finish_evals(double *fvalue, double *cvalues) override;
+    bool eval_user_objective(Slot slot, bool want_grad, double *value);
+    bool push_rows_to(double *dst, unsigned rows, const double *host_grad);
+    bool eval_penalty_objective(Slot slot, bool want_grad, double *value);
     bool dual_eval(const double *y, const DualScalars &sc, bool materialize, DualSums *out) override;
     bool supports_dual_solve() const override;
     bool dual_solve(double *y, const double *lo, const double *hi, const double *stop6, const DualScalars &sc, DualSums *out,
@@ -112,7 +116,11 @@ private:
     int h_grad_next_ = 0;
     cudaEvent_t h_grad_done_[2] = {nullptr, nullptr};
     double *xfull_dev_ = nullptr;                    // multi-rank host callbacks: gathered x
+    double *pen_rows_ = nullptr;                     // augmented-Lagrangian objective: gradient rows of the folded constraints
+    unsigned pen_total_ = 0;                         // their number (scalar constraints)
     double *scalar_dev_ = nullptr;                   // multi-rank device callbacks: value all-reduce
+    double pend_val_[1 + 32] = {};                   // shard-local values waiting for finish_evals()
+    unsigned long long pend_mask_ = 0;
     size_t shard_cap_ = 0;                           // largest padded shard length over all ranks
     unsigned long long x_epoch_ = 1, h_x_epoch_ = 0; // which (slot, epoch) h_x_ currently mirrors
     int h_x_slot_ = -1;

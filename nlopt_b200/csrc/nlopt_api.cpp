@@ -3,6 +3,7 @@
 // Same names, arguments, return codes and side effects as the reference's
 // src/api/options.c, src/api/general.c and the MMA/CCSAQ slice of src/api/optimize.c
 // (cited per function).  The object is a C++ struct of our own; only two algorithms run.
+#include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -162,6 +163,7 @@ double flipped(unsigned n, const double *x, double *grad, void *p)
 }
 
 nlopt_result run_ccsa(nlopt_opt opt, double *x_host, double *x_dev, double *minf);
+nlopt_result run_auglag(nlopt_opt opt, double *x_host, double *minf);
 
 }  // namespace
 
@@ -707,7 +709,15 @@ static nlopt_result optimize_common(nlopt_opt opt, double *x_host, double *x_dev
         opt->stopval = -opt->stopval;
         opt->maximize = 0;
     }
-    nlopt_result ret = run_ccsa(opt, x_host, x_dev, opt_f);
+    nlopt_result ret;
+    if (is_auglag(opt->algorithm)) {
+        if (!x_host || opt->df) {
+            set_err(opt, "NLOPT_AUGLAG* takes host x and host callbacks in this library");
+            ret = NLOPT_INVALID_ARGS;
+        } else
+            ret = run_auglag(opt, x_host, opt_f);
+    } else
+        ret = run_ccsa(opt, x_host, x_dev, opt_f);
     if (maximize) {
         opt->maximize = maximize;
         opt->stopval = -opt->stopval;
@@ -810,6 +820,7 @@ nlopt_result run_ccsa(nlopt_opt opt, double *x_host, double *x_dev, double *minf
     cfg.objective.f = opt->f;
     cfg.objective.df = opt->df;
     cfg.objective.data = opt->f_data;
+    cfg.penalty = opt->penalty;
     std::vector<double> tol;
     for (const auto &c : opt->fc) {
         nb200::FuncSpec s;
@@ -878,6 +889,275 @@ nlopt_result run_ccsa(nlopt_opt opt, double *x_host, double *x_dev, double *minf
     delete be;
     opt->stats.seconds_total = nb200::wall_seconds() - t0;
     return (nlopt_result) ret;
+}
+
+// ---- NLOPT_AUGLAG / AUGLAG_EQ / LD_AUGLAG / LD_AUGLAG_EQ (optimize.c:907-939, src/algs/auglag/auglag.c:69-300) ----
+// The outer loop (multiplier and penalty updates: scalars) runs here; the sub-problems go to LD_MMA / LD_CCSAQ on
+// the device, whose objective is the augmented Lagrangian evaluated by the backend (PenaltySpec).
+bool rel_stop_host(double vold, double vnew, double reltol, double abstol)      // stop.c:81-86
+{
+    if (nb200::nl_isinf(vold)) return false;
+    const double d = std::fabs(vnew - vold);
+    return d < abstol || d < reltol * (std::fabs(vnew) + std::fabs(vold)) * 0.5 || (reltol > 0 && vnew == vold);
+}
+
+bool stop_x_host(const nlopt_opt opt, const double *x, const double *oldx)      // nlopt_stop_x, stop.c:98-108
+{
+    const unsigned n = opt->n;
+    const double *w = opt->has_x_weights ? opt->x_weights.data() : nullptr;
+    double dn = 0, xn = 0;
+    if (w) {
+        for (unsigned i = 0; i < n; ++i) dn += w[i] * std::fabs(x[i] - oldx[i]);
+        for (unsigned i = 0; i < n; ++i) xn += w[i] * std::fabs(x[i]);
+    } else {
+        for (unsigned i = 0; i < n; ++i) dn += std::fabs(x[i] - oldx[i]);
+        for (unsigned i = 0; i < n; ++i) xn += std::fabs(x[i]);
+    }
+    if (dn < opt->xtol_rel * xn) return true;
+    if (!opt->has_xtol_abs) return false;
+    for (unsigned i = 0; i < n; ++i)
+        if (std::fabs(x[i] - oldx[i]) >= opt->xtol_abs[i]) return false;
+    return true;
+}
+
+// nlopt_eval_constraint without gradient (stop.c:178-184)
+void eval_values(const nb200::ConstraintRec &c, unsigned n, const double *x, double *out)
+{
+    if (c.f) out[0] = c.f(n, x, nullptr, c.f_data);
+    else c.mf(c.m, out, n, x, nullptr, c.f_data);
+}
+
+nlopt_result optimize_limited(nlopt_opt sub, double *x, double *minf, int maxeval, double maxtime)   // optimize.c:1087-1113
+{
+    const int save_maxeval = sub->maxeval;
+    const double save_maxtime = sub->maxtime;
+    if (save_maxeval <= 0 || (maxeval > 0 && maxeval < save_maxeval)) sub->maxeval = maxeval;
+    if (save_maxtime <= 0 || (maxtime > 0 && maxtime < save_maxtime)) sub->maxtime = maxtime;
+    const nlopt_result ret = nlopt_optimize(sub, x, minf);
+    sub->maxeval = save_maxeval;
+    sub->maxtime = save_maxtime;
+    return ret;
+}
+
+nlopt_result run_auglag(nlopt_opt opt, double *x, double *minf)
+{
+    const unsigned n = opt->n;
+    const nlopt_algorithm alg = opt->algorithm;
+    if (opt->maximize) { set_err(opt, "NULL args to nlopt_optimize_"); return NLOPT_INVALID_ARGS; }
+    for (const auto *list : {&opt->fc, &opt->h})
+        for (const auto &c : *list)
+            if (c.df) { set_err(opt, "NLOPT_AUGLAG* takes host callbacks in this library"); return NLOPT_INVALID_ARGS; }
+    for (unsigned i = 0; i < n; ++i)                 /* optimize.c:547-551 */
+        if (opt->lb[i] > opt->ub[i] || x[i] < opt->lb[i] || x[i] > opt->ub[i]) {
+            set_err(opt, "bounds %d fail %g <= %g <= %g", (int) i, opt->lb[i], x[i], opt->ub[i]);
+            return NLOPT_INVALID_ARGS;
+        }
+    if ((alg == NLOPT_AUGLAG || alg == NLOPT_AUGLAG_EQ) && !opt->local_opt) {
+        set_err(opt, "local optimizer must be specified for AUGLAG");
+        return NLOPT_INVALID_ARGS;
+    }
+    nlopt_opt sub = opt->local_opt;
+    const bool own_sub = !sub;
+    if (!sub) {                                      /* optimize.c:919-928 */
+        if (alg == NLOPT_LN_AUGLAG || alg == NLOPT_LN_AUGLAG_EQ) {
+            set_err(opt, "the default derivative-free local optimizer is not part of this library; set LD_MMA or LD_CCSAQ with nlopt_set_local_optimizer");
+            return NLOPT_INVALID_ARGS;
+        }
+        sub = nlopt_create(NLOPT_LD_MMA, n);
+        if (!sub) { set_err(opt, "failed to create local_opt"); return NLOPT_FAILURE; }
+        nlopt_set_ftol_rel(sub, opt->ftol_rel);
+        nlopt_set_ftol_abs(sub, opt->ftol_abs);
+        nlopt_set_xtol_rel(sub, opt->xtol_rel);
+        if (opt->has_xtol_abs) nlopt_set_xtol_abs(sub, opt->xtol_abs.data());
+        nlopt_set_maxeval(sub, -1);
+    }
+    struct Cleanup {
+        nlopt_opt opt, sub;
+        bool own;
+        ~Cleanup()
+        {
+            sub->penalty = nullptr;
+            opt->force_stop_child = nullptr;
+            if (own) nlopt_destroy(sub);
+        }
+    } cleanup{opt, sub, own_sub};
+    if (sub->algorithm != NLOPT_LD_MMA && sub->algorithm != NLOPT_LD_CCSAQ) {
+        set_err(opt, "local optimizer %s is not part of this library (only LD_MMA and LD_CCSAQ are built)",
+                nlopt_algorithm_to_string(sub->algorithm));
+        return NLOPT_INVALID_ARGS;
+    }
+    if (opt->has_dx) nlopt_set_initial_step(sub, opt->dx.data());
+    opt->force_stop_child = sub;
+
+    const bool sub_has_fc = alg == NLOPT_AUGLAG_EQ || alg == NLOPT_LN_AUGLAG_EQ || alg == NLOPT_LD_AUGLAG_EQ;
+    const std::vector<nb200::ConstraintRec> none;
+    const std::vector<nb200::ConstraintRec> &pen_fc = sub_has_fc ? none : opt->fc;     /* auglag.c:98-101 */
+    const std::vector<nb200::ConstraintRec> &sub_fc = sub_has_fc ? opt->fc : none;
+    unsigned mm = 0, pp = 0;
+    for (const auto &c : pen_fc) mm += c.m;
+    for (const auto &c : opt->h) pp += c.m;
+
+    nb200::PenaltySpec pen;
+    std::vector<double> lambda(pp ? pp : 1, 0.0), mu(mm ? mm : 1, 0.0);
+    auto to_spec = [](const nb200::ConstraintRec &c) {
+        nb200::FuncSpec s;
+        s.m = c.m; s.f = c.f; s.mf = c.mf; s.data = c.f_data;
+        return s;
+    };
+    for (const auto &c : opt->h) pen.eq.push_back(to_spec(c));
+    for (const auto &c : pen_fc) pen.ineq.push_back(to_spec(c));
+    pen.lambda = lambda.data();
+    pen.mu = mu.data();
+    opt->numevals = 0;
+    pen.nevals_p = &opt->numevals;
+    pen.force_stop = &opt->force_stop;
+
+    /* configure the sub-optimiser (auglag.c:107-137).  Its objective is f + penalties: f goes in as its plain
+       objective, the rest as the penalty spec */
+    sub->f = opt->f;
+    sub->f_data = opt->f_data;
+    sub->df = nullptr;
+    sub->pre = nullptr;
+    sub->maximize = 0;
+    nlopt_set_lower_bounds(sub, opt->lb.data());
+    nlopt_set_upper_bounds(sub, opt->ub.data());
+    sub->lb_uniform = opt->lb_uniform;
+    sub->ub_uniform = opt->ub_uniform;
+    nlopt_set_stopval(sub, (mm == 0 && pp == 0) ? opt->stopval : -kInf);
+    if (mm != 0 || pp != 0)
+        if (sub->xtol_rel <= 0 && sub->ftol_rel <= 0) nlopt_set_xtol_rel(sub, opt->xtol_rel > 0 ? opt->xtol_rel : 1e-8);
+    {   /* the sub-optimiser borrows the callbacks: its munge hooks must not touch the user's data */
+        const nlopt_munge md = sub->munge_on_destroy, mc = sub->munge_on_copy;
+        sub->munge_on_destroy = sub->munge_on_copy = nullptr;
+        nlopt_remove_inequality_constraints(sub);
+        nlopt_remove_equality_constraints(sub);
+        sub->munge_on_destroy = md;
+        sub->munge_on_copy = mc;
+    }
+    for (const auto &c : sub_fc) {
+        nlopt_result r = c.f ? nlopt_add_inequality_constraint(sub, c.f, c.f_data, c.tol[0])
+                             : nlopt_add_inequality_mconstraint(sub, c.m, c.mf, c.f_data, c.tol.data());
+        if (r < 0) return r;
+    }
+    sub->penalty = &pen;
+
+    const double t_start = nb200::wall_seconds();
+    auto forced = [&] { return opt->force_stop != 0; };
+    std::vector<double> xcur(x, x + n), vals;
+    unsigned maxdim = 1;
+    for (const auto &c : pen_fc) maxdim = c.m > maxdim ? c.m : maxdim;
+    for (const auto &c : opt->h) maxdim = c.m > maxdim ? c.m : maxdim;
+    vals.resize(maxdim);
+
+    /* magic parameters from Birgin & Martinez (auglag.c:85-87) */
+    const double tau = 0.5, gam = 10, lam_min = -1e20, lam_max = 1e20, mu_max = 1e20;
+    double ICM = HUGE_VAL, minf_penalty = HUGE_VAL, penalty = 0, fcur = 0;
+    int feasible = 0, minf_feasible = 0;
+    nlopt_result ret = NLOPT_SUCCESS;
+    *minf = HUGE_VAL;
+
+    if (pp > 0 || mm > 0) {                          /* starting rho, auglag.c:155-190 */
+        double con2 = 0;
+        ++opt->numevals;
+        fcur = opt->f(n, xcur.data(), nullptr, opt->f_data);
+        if (forced()) return NLOPT_FORCED_STOP;
+        penalty = 0;
+        feasible = 1;
+        for (const auto &c : opt->h) {
+            eval_values(c, n, xcur.data(), vals.data());
+            if (forced()) return NLOPT_FORCED_STOP;
+            for (unsigned k = 0; k < c.m; ++k) {
+                const double hi = vals[k];
+                penalty += std::fabs(hi);
+                feasible = feasible && std::fabs(hi) <= c.tol[k];
+                con2 += hi * hi;
+            }
+        }
+        for (const auto &c : pen_fc) {
+            eval_values(c, n, xcur.data(), vals.data());
+            if (forced()) return NLOPT_FORCED_STOP;
+            for (unsigned k = 0; k < c.m; ++k) {
+                const double fci = vals[k];
+                penalty += fci > 0 ? fci : 0;
+                feasible = feasible && fci <= c.tol[k];
+                if (fci > 0) con2 += fci * fci;
+            }
+        }
+        *minf = fcur;
+        minf_penalty = penalty;
+        minf_feasible = feasible;
+        const double r0 = 2 * std::fabs(*minf) / con2;
+        pen.rho = con2 > 0 ? std::max(1e-6, std::min(10.0, r0)) : 10;
+    } else
+        pen.rho = 1;
+    const int verbose = (int) nlopt_get_param(opt, "verbosity", 0);
+    int iters = 0;
+
+    do {                                             /* auglag.c:204-296 */
+        const double prev_ICM = ICM;
+        ret = optimize_limited(sub, xcur.data(), &fcur, opt->maxeval - opt->numevals,
+                               opt->maxtime - (nb200::wall_seconds() - t_start));
+        if (ret < 0) {
+            if (sub->has_errmsg) set_err(opt, "%s", sub->errmsg.c_str());
+            break;
+        }
+        ++opt->numevals;
+        fcur = opt->f(n, xcur.data(), nullptr, opt->f_data);
+        if (forced()) return NLOPT_FORCED_STOP;
+        ICM = 0;
+        penalty = 0;
+        feasible = 1;
+        unsigned ii = 0;
+        for (const auto &c : opt->h) {
+            eval_values(c, n, xcur.data(), vals.data());
+            if (forced()) return NLOPT_FORCED_STOP;
+            for (unsigned k = 0; k < c.m; ++k) {
+                const double hi = vals[k];
+                const double newlam = lambda[ii] + pen.rho * hi;
+                penalty += std::fabs(hi);
+                feasible = feasible && std::fabs(hi) <= c.tol[k];
+                ICM = std::max(ICM, std::fabs(hi));
+                lambda[ii++] = std::min(std::max(lam_min, newlam), lam_max);
+            }
+        }
+        ii = 0;
+        for (const auto &c : pen_fc) {
+            eval_values(c, n, xcur.data(), vals.data());
+            if (forced()) return NLOPT_FORCED_STOP;
+            for (unsigned k = 0; k < c.m; ++k) {
+                const double fci = vals[k];
+                const double newmu = mu[ii] + pen.rho * fci;
+                penalty += fci > 0 ? fci : 0;
+                feasible = feasible && fci <= c.tol[k];
+                ICM = std::max(ICM, std::fabs(std::max(fci, -mu[ii] / pen.rho)));
+                mu[ii++] = std::min(std::max(0.0, newmu), mu_max);
+            }
+        }
+        if (ICM > tau * prev_ICM) pen.rho *= gam;
+        ++iters;
+        if (verbose)
+            std::printf("auglag %d: ICM=%g (%sfeasible), rho=%g, fcur=%g\n", iters, ICM, feasible ? "" : "not ", pen.rho, fcur);
+
+        if ((feasible && (!minf_feasible || penalty < minf_penalty || fcur < *minf)) || (!minf_feasible && penalty < minf_penalty)) {
+            ret = NLOPT_SUCCESS;
+            if (feasible) {
+                if (fcur < opt->stopval) ret = NLOPT_STOPVAL_REACHED;
+                else if (rel_stop_host(*minf, fcur, opt->ftol_rel, opt->ftol_abs)) ret = NLOPT_FTOL_REACHED;
+                else if (stop_x_host(opt, xcur.data(), x)) ret = NLOPT_XTOL_REACHED;
+            }
+            *minf = fcur;
+            minf_penalty = penalty;
+            minf_feasible = feasible;
+            std::memcpy(x, xcur.data(), sizeof(double) * n);
+            if (ret != NLOPT_SUCCESS) break;
+        }
+        if (forced()) { ret = NLOPT_FORCED_STOP; break; }
+        if (opt->maxeval > 0 && opt->numevals >= opt->maxeval) { ret = NLOPT_MAXEVAL_REACHED; break; }
+        if (opt->maxtime > 0 && nb200::wall_seconds() - t_start >= opt->maxtime) { ret = NLOPT_MAXTIME_REACHED; break; }
+        if (ICM == 0) { ret = NLOPT_FTOL_REACHED; break; }
+    } while (true);
+    opt->stats = sub->stats;
+    return ret;
 }
 
 }  // namespace

@@ -10,6 +10,8 @@
 
 namespace nb200 {
 
+struct PenaltySpec;     // backend_factory.hpp
+
 // one registered constraint object (reference: nlopt_constraint, src/util/nlopt-util.h:119-126)
 struct ConstraintRec {
     unsigned m = 1;                 // output dimension
@@ -55,6 +57,8 @@ struct nlopt_opt_s {
     nlopt_opt_s *force_stop_child = nullptr;
 
     nlopt_opt_s *local_opt = nullptr;
+    const nb200::PenaltySpec *penalty = nullptr;  // set on the sub-optimiser while NLOPT_AUGLAG* drives it: its objective
+                                                  // is the augmented Lagrangian built around f (never copied)
     unsigned stochastic_population = 0, vector_storage = 0;
 
     bool has_errmsg = false;

@@ -51,10 +51,38 @@ public:
     bool eval_objective(Slot slot, bool want_grad, double *value) override
     {
         if (!cfg.objective.f) { err = "host test backend needs a host objective"; return false; }
+        const double *xs = (slot == kBase ? x : xcur).data();
+        double *gs = want_grad ? (slot == kBase ? g : gcur).data() : nullptr;
         const double t0 = now_s();
-        *value = cfg.objective.f(n_, (slot == kBase ? x : xcur).data(),
-                                 want_grad ? (slot == kBase ? g : gcur).data() : nullptr, cfg.objective.data);
+        double L = cfg.objective.f(n_, xs, gs, cfg.objective.data);
         cb += now_s() - t0;
+        *value = L;
+        if (!cfg.penalty) return true;
+        // the augmented-Lagrangian objective (PenaltySpec): plain host loops standing in for the device kernel
+        const PenaltySpec &ps = *cfg.penalty;
+        if (ps.nevals_p) ++*ps.nevals_p;
+        if (ps.force_stop && *ps.force_stop) return true;
+        unsigned maxdim = 1;
+        for (const FuncSpec &fs : ps.eq) maxdim = fs.m > maxdim ? fs.m : maxdim;
+        for (const FuncSpec &fs : ps.ineq) maxdim = fs.m > maxdim ? fs.m : maxdim;
+        std::vector<double> vals(maxdim), rows(want_grad ? (size_t) maxdim * n_ : 1);
+        unsigned ii = 0;
+        for (int pass = 0; pass < 2; ++pass) {
+            ii = 0;
+            for (const FuncSpec &fs : (pass == 0 ? ps.eq : ps.ineq)) {
+                if (fs.f) vals[0] = fs.f(n_, xs, want_grad ? rows.data() : nullptr, fs.data);
+                else fs.mf(fs.m, vals.data(), n_, xs, want_grad ? rows.data() : nullptr, fs.data);
+                if (ps.force_stop && *ps.force_stop) return true;
+                for (unsigned k = 0; k < fs.m; ++k, ++ii) {
+                    const double v = vals[k] + (pass == 0 ? ps.lambda[ii] : ps.mu[ii]) / ps.rho;
+                    if (pass == 1 && !(v > 0)) continue;
+                    L += 0.5 * ps.rho * v * v;
+                    if (want_grad)
+                        for (unsigned j = 0; j < n_; ++j) gs[j] += (ps.rho * v) * rows[(size_t) k * n_ + j];
+                }
+            }
+        }
+        *value = L;
         return true;
     }
     bool eval_constraint(Slot slot, unsigned ic, unsigned row0, bool want_grad, double *values) override

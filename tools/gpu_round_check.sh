@@ -5,7 +5,10 @@ timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
 b() { echo "== bench $*"; timeout 300 python bench.py --steps 8 --warmup 3 --no-cpu "$@" 2>/dev/null | python -c "$P"; }
 b --no-e2e
 b --alg mma --no-e2e
+for tc in 2 3 4 6; do b --no-e2e --param b200_target_chunks=$tc; done
+b --alg mma --no-e2e --param b200_target_chunks=3
 b --n 1000000 --no-e2e
 b --n 1250000 --no-e2e
 b --n 100000 --no-e2e
+b --n 10000 --no-e2e
 for t in "$@"; do timeout 200 python tools/trace_solve.py run $t ccsaq; done
