@@ -170,3 +170,60 @@ def test_auglag_large_n_gradient_assembly(built, reflib):
     assert a["ret"] == b["ret"] and a["numevals"] == b["numevals"]
     assert abs(a["minf"] - b["minf"]) <= 1e-7 * max(1.0, abs(b["minf"]))
     assert np.max(np.abs(a["x"] - b["x"])) <= 1e-6
+
+
+def test_auglag_maximize_stopval_and_forced_stop(hosttest_lib, reflib):
+    """Option surface around the outer loop: maximisation (sign flip, optimize.c:1014-1024), stopval on a feasible
+    point (auglag.c:272), nlopt_force_stop from inside a callback (auglag.c:39, :218) -- same outcome as the reference."""
+    n = 12
+    lb, ub, x0 = np.full(n, -2.0), np.full(n, 2.0), np.full(n, 0.3)
+
+    def neg_obj(x, grad):
+        v = lin_obj(x, grad)
+        if grad.size:
+            grad[:] = -grad
+        return -v
+
+    res = {}
+    for name, lib in (("ours", hosttest_lib), ("ref", reflib)):
+        o = nl.opt(nl.LD_AUGLAG, n, library=lib)
+        o.set_lower_bounds(lb); o.set_upper_bounds(ub)
+        o.set_max_objective(neg_obj)
+        o.add_equality_constraint(circle_eq, 1e-8)
+        o.set_xtol_rel(1e-6); o.set_maxeval(2000)
+        x = o.optimize(x0.copy())
+        res[name] = (o.last_optimize_result(), o.get_numevals(), o.last_optimum_value(), x)
+    assert res["ours"][0] == res["ref"][0] and res["ours"][1] == res["ref"][1]
+    assert abs(res["ours"][2] - res["ref"][2]) <= 1e-9 and np.max(np.abs(res["ours"][3] - res["ref"][3])) <= 1e-7
+
+    for name, lib in (("ours", hosttest_lib), ("ref", reflib)):
+        o = nl.opt(nl.LD_AUGLAG, n, library=lib)
+        o.set_lower_bounds(lb); o.set_upper_bounds(ub)
+        o.set_min_objective(lin_obj)
+        o.add_inequality_constraint(halfspace, 1e-8)
+        o.set_stopval(1.0); o.set_xtol_rel(1e-9); o.set_maxeval(2000)      # any feasible point with f < 1 ends the run
+        x = o.optimize(x0.copy())
+        res[name] = (o.last_optimize_result(), o.get_numevals(), o.last_optimum_value(), x)
+    assert res["ours"][0] == res["ref"][0] == nl.STOPVAL_REACHED and res["ours"][1] == res["ref"][1]
+    assert abs(res["ours"][2] - res["ref"][2]) <= 1e-9
+
+    for name, lib in (("ours", hosttest_lib), ("ref", reflib)):
+        o = nl.opt(nl.LD_AUGLAG, n, library=lib)
+        calls = [0]
+
+        def stopping_obj(x, grad, o=o, calls=calls):
+            calls[0] += 1
+            if calls[0] == 9:
+                o.force_stop()
+            return lin_obj(x, grad)
+
+        o.set_lower_bounds(lb); o.set_upper_bounds(ub)
+        o.set_min_objective(stopping_obj)
+        o.add_equality_constraint(circle_eq, 1e-8)
+        o.set_xtol_rel(1e-9); o.set_maxeval(500)
+        try:
+            o.optimize(x0.copy())
+        except Exception:
+            pass
+        res[name] = (o.last_optimize_result(), calls[0])
+    assert res["ours"] == res["ref"] and res["ours"][0] == nl.FORCED_STOP
