@@ -5,10 +5,15 @@
  * (reference: src/api/nlopt.h:60-301, soname libnlopt.so.1), so code compiled
  * against the reference header -- including the reference's header-only C++
  * wrapper nlopt.hpp and test/t_tutorial.cxx -- links against libnlopt_b200.so
- * unmodified.  Only NLOPT_LD_MMA and NLOPT_LD_CCSAQ are executable:
- * nlopt_optimize() on any other algorithm id returns NLOPT_INVALID_ARGS with
- * a message.  All O(n) work of those two algorithms runs in CUDA kernels on
- * sm_100a; there is no CPU fallback (no device => NLOPT_FAILURE + message).
+ * unmodified.  Executable algorithms: NLOPT_LD_MMA and NLOPT_LD_CCSAQ
+ * (src/algs/mma/mma.c, ccsa_quadratic.c) and the augmented-Lagrangian family
+ * that wraps them (NLOPT_AUGLAG, NLOPT_AUGLAG_EQ, NLOPT_LD_AUGLAG,
+ * NLOPT_LD_AUGLAG_EQ, and the LN_ variants when an LD_MMA / LD_CCSAQ local
+ * optimizer is set; src/algs/auglag/auglag.c).  nlopt_optimize() on any
+ * other algorithm id returns NLOPT_INVALID_ARGS with a message.  All O(n)
+ * work of MMA / CCSAQ and the gradient of the augmented Lagrangian run in
+ * CUDA kernels on sm_100a; there is no CPU fallback (no device =>
+ * NLOPT_FAILURE + message).
  *
  * The `nlopt_b200_*` symbols are additive extensions (device-resident
  * callbacks, kernel-level access to the dual evaluation, multi-GPU sharding,
@@ -49,9 +54,9 @@ typedef enum {
     NLOPT_LD_MMA = 24,              /* <- built here */
     NLOPT_LN_COBYLA = 25, NLOPT_LN_NEWUOA = 26, NLOPT_LN_NEWUOA_BOUND = 27,
     NLOPT_LN_NELDERMEAD = 28, NLOPT_LN_SBPLX = 29,
-    NLOPT_LN_AUGLAG = 30, NLOPT_LD_AUGLAG = 31, NLOPT_LN_AUGLAG_EQ = 32, NLOPT_LD_AUGLAG_EQ = 33,
+    NLOPT_LN_AUGLAG = 30, NLOPT_LD_AUGLAG = 31, NLOPT_LN_AUGLAG_EQ = 32, NLOPT_LD_AUGLAG_EQ = 33,   /* <- built here (over MMA/CCSAQ) */
     NLOPT_LN_BOBYQA = 34, NLOPT_GN_ISRES = 35,
-    NLOPT_AUGLAG = 36, NLOPT_AUGLAG_EQ = 37, NLOPT_G_MLSL = 38, NLOPT_G_MLSL_LDS = 39,
+    NLOPT_AUGLAG = 36, NLOPT_AUGLAG_EQ = 37,  /* <- built here */  NLOPT_G_MLSL = 38, NLOPT_G_MLSL_LDS = 39,
     NLOPT_LD_SLSQP = 40,
     NLOPT_LD_CCSAQ = 41,            /* <- built here */
     NLOPT_GN_ESCH = 42, NLOPT_GN_AGS = 43,
