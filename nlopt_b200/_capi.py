@@ -116,6 +116,20 @@ _STD = {
     "nlopt_get_initial_step": (C.c_int, [C.c_void_p, c_double_p, c_double_p]),
     "nlopt_set_munge": (None, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "nlopt_munge_data": (None, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    # deprecated one-call API (reference nlopt.h:305-343)
+    "nlopt_minimize": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_void_p, c_double_p, c_double_p, c_double_p, c_double_p,
+                                 C.c_double, C.c_double, C.c_double, C.c_double, c_double_p, C.c_int, C.c_double]),
+    "nlopt_minimize_constrained": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_ssize_t,
+                                             c_double_p, c_double_p, c_double_p, c_double_p, C.c_double, C.c_double, C.c_double,
+                                             C.c_double, c_double_p, C.c_int, C.c_double]),
+    "nlopt_minimize_econstrained": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_ssize_t,
+                                              C.c_int, C.c_void_p, C.c_void_p, C.c_ssize_t, c_double_p, c_double_p, c_double_p,
+                                              c_double_p, C.c_double, C.c_double, C.c_double, C.c_double, c_double_p, C.c_double,
+                                              C.c_double, C.c_int, C.c_double]),
+    "nlopt_get_local_search_algorithm": (None, [C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "nlopt_set_local_search_algorithm": (None, [C.c_int, C.c_int, C.c_int]),
+    "nlopt_get_stochastic_population": (C.c_int, []),
+    "nlopt_set_stochastic_population": (None, [C.c_int]),
 }
 
 # additive extensions, include/nlopt_b200.h

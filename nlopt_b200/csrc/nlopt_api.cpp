@@ -19,6 +19,13 @@ using nb200::ConstraintRec;
 using nb200::NamedParam;
 
 namespace {
+/* process-wide defaults of the deprecated API (deprecated.c:27-29, :48) */
+nlopt_algorithm g_local_deriv = NLOPT_LD_MMA, g_local_nonderiv = NLOPT_LN_COBYLA;
+int g_local_maxeval = -1;
+int g_stochastic_population = 0;
+}  // namespace
+
+namespace {
 
 const double kInf = HUGE_VAL;
 
@@ -733,6 +740,72 @@ nlopt_result nlopt_optimize(nlopt_opt opt, double *x, double *opt_f)
     return optimize_common(opt, x, nullptr, opt_f);
 }
 
+/* ------------------------------------------------------------------ deprecated API (deprecated.c) */
+
+void nlopt_get_local_search_algorithm(nlopt_algorithm *deriv, nlopt_algorithm *nonderiv, int *maxeval)
+{
+    *deriv = g_local_deriv;
+    *nonderiv = g_local_nonderiv;
+    *maxeval = g_local_maxeval;
+}
+
+void nlopt_set_local_search_algorithm(nlopt_algorithm deriv, nlopt_algorithm nonderiv, int maxeval)
+{
+    g_local_deriv = deriv;
+    g_local_nonderiv = nonderiv;
+    g_local_maxeval = maxeval;
+}
+
+int nlopt_get_stochastic_population(void) { return g_stochastic_population; }
+void nlopt_set_stochastic_population(int pop) { g_stochastic_population = pop <= 0 ? 0 : pop; }
+
+nlopt_result nlopt_minimize_econstrained(nlopt_algorithm algorithm, int n, nlopt_func_old f, void *f_data, int m,
+                                         nlopt_func_old fc, void *fc_data, ptrdiff_t fc_datum_size, int p, nlopt_func_old h,
+                                         void *h_data, ptrdiff_t h_datum_size, const double *lb, const double *ub, double *x,
+                                         double *minf, double minf_max, double ftol_rel, double ftol_abs, double xtol_rel,
+                                         const double *xtol_abs, double htol_rel, double htol_abs, int maxeval, double maxtime)
+{
+    (void) htol_rel;                     /* unused in the reference as well (deprecated.c:97) */
+    if (n < 0 || m < 0 || p < 0) return NLOPT_INVALID_ARGS;
+    nlopt_opt opt = nlopt_create(algorithm, (unsigned) n);
+    if (!opt) return NLOPT_INVALID_ARGS;
+    /* the old callback type differs from nlopt_func only in the signedness of n */
+    nlopt_result ret = nlopt_set_min_objective(opt, reinterpret_cast<nlopt_func>(f), f_data);
+    for (int i = 0; ret == NLOPT_SUCCESS && i < m; ++i)
+        ret = nlopt_add_inequality_constraint(opt, reinterpret_cast<nlopt_func>(fc), static_cast<char *>(fc_data) + i * fc_datum_size, 0.0);
+    for (int i = 0; ret == NLOPT_SUCCESS && i < p; ++i)
+        ret = nlopt_add_equality_constraint(opt, reinterpret_cast<nlopt_func>(h), static_cast<char *>(h_data) + i * h_datum_size, htol_abs);
+    if (ret == NLOPT_SUCCESS) ret = nlopt_set_lower_bounds(opt, lb);
+    if (ret == NLOPT_SUCCESS) ret = nlopt_set_upper_bounds(opt, ub);
+    if (ret == NLOPT_SUCCESS) ret = nlopt_set_stopval(opt, minf_max);
+    if (ret == NLOPT_SUCCESS) ret = nlopt_set_ftol_rel(opt, ftol_rel);
+    if (ret == NLOPT_SUCCESS) ret = nlopt_set_ftol_abs(opt, ftol_abs);
+    if (ret == NLOPT_SUCCESS) ret = nlopt_set_xtol_rel(opt, xtol_rel);
+    if (ret == NLOPT_SUCCESS && xtol_abs) ret = nlopt_set_xtol_abs(opt, xtol_abs);
+    if (ret == NLOPT_SUCCESS) ret = nlopt_set_maxeval(opt, maxeval);
+    if (ret == NLOPT_SUCCESS) ret = nlopt_set_maxtime(opt, maxtime);
+    if (ret == NLOPT_SUCCESS) ret = nlopt_optimize(opt, x, minf);
+    nlopt_destroy(opt);
+    return ret;
+}
+
+nlopt_result nlopt_minimize_constrained(nlopt_algorithm algorithm, int n, nlopt_func_old f, void *f_data, int m,
+                                        nlopt_func_old fc, void *fc_data, ptrdiff_t fc_datum_size, const double *lb,
+                                        const double *ub, double *x, double *minf, double minf_max, double ftol_rel,
+                                        double ftol_abs, double xtol_rel, const double *xtol_abs, int maxeval, double maxtime)
+{
+    return nlopt_minimize_econstrained(algorithm, n, f, f_data, m, fc, fc_data, fc_datum_size, 0, nullptr, nullptr, 0, lb, ub,
+                                       x, minf, minf_max, ftol_rel, ftol_abs, xtol_rel, xtol_abs, ftol_rel, ftol_abs, maxeval, maxtime);
+}
+
+nlopt_result nlopt_minimize(nlopt_algorithm algorithm, int n, nlopt_func_old f, void *f_data, const double *lb,
+                            const double *ub, double *x, double *minf, double minf_max, double ftol_rel, double ftol_abs,
+                            double xtol_rel, const double *xtol_abs, int maxeval, double maxtime)
+{
+    return nlopt_minimize_constrained(algorithm, n, f, f_data, 0, nullptr, nullptr, 0, lb, ub, x, minf, minf_max, ftol_rel,
+                                      ftol_abs, xtol_rel, xtol_abs, maxeval, maxtime);
+}
+
 nlopt_result nlopt_b200_optimize_device(nlopt_opt opt, double *x_dev, double *opt_f)
 {
     return optimize_common(opt, nullptr, x_dev, opt_f);
@@ -795,7 +868,7 @@ nlopt_result run_ccsa(nlopt_opt opt, double *x_host, double *x_dev, double *minf
     /* the dual optimiser's configuration, optimize.c:817-826.  Precedence: named parameter >
        local optimiser (if one was set) > library default; only MMA exists here for the dual. */
     const nlopt_opt lo = opt->local_opt;
-    const int dual_alg = (int) nlopt_get_param(opt, "dual_algorithm", lo ? (double) lo->algorithm : (double) NLOPT_LD_MMA);
+    const int dual_alg = (int) nlopt_get_param(opt, "dual_algorithm", lo ? (double) lo->algorithm : (double) g_local_deriv);
     if (dual_alg != NLOPT_LD_MMA) {
         set_err(opt, "dual_algorithm %d is not part of this library (the dual problem is solved by LD_MMA)", dual_alg);
         return NLOPT_INVALID_ARGS;
@@ -963,13 +1036,13 @@ nlopt_result run_auglag(nlopt_opt opt, double *x, double *minf)
             set_err(opt, "the default derivative-free local optimizer is not part of this library; set LD_MMA or LD_CCSAQ with nlopt_set_local_optimizer");
             return NLOPT_INVALID_ARGS;
         }
-        sub = nlopt_create(NLOPT_LD_MMA, n);
+        sub = nlopt_create(g_local_deriv, n);          /* nlopt_local_search_alg_deriv: LD_MMA unless changed */
         if (!sub) { set_err(opt, "failed to create local_opt"); return NLOPT_FAILURE; }
         nlopt_set_ftol_rel(sub, opt->ftol_rel);
         nlopt_set_ftol_abs(sub, opt->ftol_abs);
         nlopt_set_xtol_rel(sub, opt->xtol_rel);
         if (opt->has_xtol_abs) nlopt_set_xtol_abs(sub, opt->xtol_abs.data());
-        nlopt_set_maxeval(sub, -1);
+        nlopt_set_maxeval(sub, g_local_maxeval);
     }
     struct Cleanup {
         nlopt_opt opt, sub;

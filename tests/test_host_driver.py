@@ -242,3 +242,52 @@ def test_reference_cpp_functor_links_and_runs(hosttest_lib):
     exe = refsrc.compile_reference_test("cpp_functor.cxx", hosttest_lib.path, out, False)
     r = subprocess.run([exe], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
+
+
+def test_deprecated_one_call_api_matches_reference(hosttest_lib, reflib):
+    """nlopt_minimize_constrained / nlopt_minimize_econstrained / nlopt_minimize and the process-wide local-search
+    settings (reference src/api/deprecated.c, nlopt.h:305-343): same results as the reference through the same call."""
+    import ctypes as C
+    OLD = C.CFUNCTYPE(C.c_double, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_void_p)
+
+    class CD(C.Structure):
+        _fields_ = [("a", C.c_double), ("b", C.c_double)]
+
+    def f_old(n, x, grad, _d):
+        if grad:
+            grad[0], grad[1] = 0.0, 0.5 / np.sqrt(x[1])
+        return float(np.sqrt(x[1]))
+
+    def c_old(n, x, grad, d):
+        cd = CD.from_address(d)
+        t = cd.a * x[0] + cd.b
+        if grad:
+            grad[0], grad[1] = 3 * cd.a * t * t, -1.0
+        return float(t ** 3 - x[1])
+
+    fo, co = OLD(f_old), OLD(c_old)
+    data = (CD * 2)(CD(2.0, 0.0), CD(-1.0, 1.0))
+    out = {}
+    for name, lib in (("ours", hosttest_lib), ("ref", reflib)):
+        L = lib.dll
+        L.nlopt_minimize_constrained.restype = C.c_int
+        L.nlopt_minimize_constrained.argtypes = [C.c_int, C.c_int, OLD, C.c_void_p, C.c_int, OLD, C.c_void_p, C.c_ssize_t,
+                                                 C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                                 C.POINTER(C.c_double), C.c_double, C.c_double, C.c_double, C.c_double,
+                                                 C.POINTER(C.c_double), C.c_int, C.c_double]
+        lb, ub = (C.c_double * 2)(-np.inf, 1e-6), (C.c_double * 2)(np.inf, np.inf)
+        x, minf = (C.c_double * 2)(1.234, 5.678), C.c_double(0)
+        ret = L.nlopt_minimize_constrained(nl.LD_MMA, 2, fo, None, 2, co, C.cast(data, C.c_void_p), C.sizeof(CD), lb, ub, x, C.byref(minf),
+                                           -1e300, 0.0, 0.0, 1e-6, None, 500, 0.0)
+        out[name] = (ret, minf.value, x[0], x[1])
+        L.nlopt_get_local_search_algorithm.argtypes = [C.POINTER(C.c_int)] * 3
+        d, nd, me = C.c_int(), C.c_int(), C.c_int()
+        L.nlopt_get_local_search_algorithm(C.byref(d), C.byref(nd), C.byref(me))
+        assert (d.value, nd.value, me.value) == (nl.LD_MMA, nl.LN_COBYLA, -1)
+        L.nlopt_set_stochastic_population(7)
+        assert L.nlopt_get_stochastic_population() == 7
+        L.nlopt_set_stochastic_population(-3)
+        assert L.nlopt_get_stochastic_population() == 0
+    assert out["ours"][0] == out["ref"][0] == nl.XTOL_REACHED
+    assert abs(out["ours"][1] - out["ref"][1]) <= 1e-6 and abs(out["ours"][1] - P.TUT_FSTAR) <= 1e-3
+    assert abs(out["ours"][2] - out["ref"][2]) <= 1e-5 and abs(out["ours"][3] - out["ref"][3]) <= 1e-5
