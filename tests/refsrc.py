@@ -45,3 +45,17 @@ def compile_reference_test(name, libpath, outdir, use_our_header):
            f"-L{libdir}", f"-l:{libfile}", f"-Wl,-rpath,{libdir}"]
     subprocess.check_call(cmd)
     return exe
+
+
+def compile_reference_testopt(libpath, outdir):
+    """The reference's benchmark driver test/testopt.c (+ testfuncs.c and, as test/CMakeLists.txt:26 does, the two
+    util sources whose symbols it uses directly) compiled unmodified against `libpath`."""
+    os.makedirs(outdir, exist_ok=True)
+    libdir, libfile = os.path.split(libpath)
+    exe = os.path.join(outdir, "testopt_" + os.path.splitext(libfile)[0])
+    cmd = ["gcc", "-O1", "-DHAVE_GETOPT", "-DHAVE_GETOPT_H", f"-I{REF}/src/api", f"-I{REF}/src/util",
+           f"-I{os.path.join(ROOT, 'oracle', 'ref_config')}", os.path.join(REF, "test", "testopt.c"),
+           os.path.join(REF, "test", "testfuncs.c"), os.path.join(REF, "src", "util", "timer.c"),
+           os.path.join(REF, "src", "util", "mt19937ar.c"), "-o", exe, f"-L{libdir}", f"-l:{libfile}", f"-Wl,-rpath,{libdir}", "-lm"]
+    subprocess.check_call(cmd)
+    return exe

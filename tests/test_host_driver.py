@@ -291,3 +291,28 @@ def test_deprecated_one_call_api_matches_reference(hosttest_lib, reflib):
     assert out["ours"][0] == out["ref"][0] == nl.XTOL_REACHED
     assert abs(out["ours"][1] - out["ref"][1]) <= 1e-6 and abs(out["ours"][1] - P.TUT_FSTAR) <= 1e-3
     assert abs(out["ours"][2] - out["ref"][2]) <= 1e-5 and abs(out["ours"][3] - out["ref"][3]) <= 1e-5
+
+
+@pytest.mark.skipif(not refsrc.available(), reason="reference tree not mounted")
+@pytest.mark.parametrize("alg", [24, 41])
+@pytest.mark.parametrize("obj", [0, 1])
+def test_reference_testopt_runs_against_our_library(hosttest_lib, reflib, alg, obj):
+    """ctest's `testopt_algo24_obj{0,1}` (test/CMakeLists.txt:39-60): the reference's own benchmark driver, compiled
+    unmodified against our library, must behave like the same driver linked with the reference: identical printed
+    optimum for a short run from the deterministic start (-c), success and the same optimum to 1e-3 for a long one."""
+    out = os.path.join(ROOT, "tests", "_build")
+    ours = refsrc.compile_reference_testopt(hosttest_lib.path, out)
+    ref = refsrc.compile_reference_testopt(reflib.path, out)
+
+    def run(exe, evals):
+        r = subprocess.run([exe, "-c", "-e", str(evals), "-a", str(alg), "-o", str(obj)], stdout=subprocess.PIPE,
+                           stderr=subprocess.STDOUT, text=True, timeout=120)
+        assert r.returncode == 0, r.stdout
+        lines = [l for l in r.stdout.splitlines() if l.startswith(("return code", "Found minimum", "Minimum at"))]
+        return lines
+
+    assert run(ours, 25) == run(ref, 25)
+    a, b = run(ours, 3000), run(ref, 3000)
+    fa = float(a[1].split("f = ")[1].split()[0])
+    fb = float(b[1].split("f = ")[1].split()[0])
+    assert a[0] == b[0] and abs(fa - fb) <= 1e-3 * max(1.0, abs(fb))
