@@ -225,7 +225,7 @@ def test_local_optimizer_supplies_dual_tolerances(hosttest_lib, reflib):
 
 @pytest.mark.skipif(not refsrc.available(), reason="/root/reference not mounted")
 @pytest.mark.parametrize("use_our_header", [False, True])
-@pytest.mark.parametrize("arg", [None, "24", "41"])
+@pytest.mark.parametrize("arg", [None, "24", "41", "31"])      # 31 = LD_AUGLAG over the default MMA (ctest t_tutorial_31)
 def test_reference_t_tutorial_links_and_passes(hosttest_lib, use_our_header, arg):
     """BASELINE config 1: the reference's own test/t_tutorial.cxx, unmodified, compiled against the
     reference-generated nlopt.hpp and linked with OUR object API + CCSA driver."""
