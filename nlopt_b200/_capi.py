@@ -198,7 +198,10 @@ _default = None
 
 
 def default_library() -> Library:
+    """The product library; NLOPT_B200_LIBRARY_PATH points the module at another library exporting the NLopt C ABI
+    (tests: the CPU-backed build of the host logic, or the reference itself)."""
     global _default
     if _default is None:
-        _default = Library()
+        alt = os.environ.get("NLOPT_B200_LIBRARY_PATH")
+        _default = Library(alt, extensions=False) if alt else Library()
     return _default

@@ -316,3 +316,15 @@ def test_reference_testopt_runs_against_our_library(hosttest_lib, reflib, alg, o
     fa = float(a[1].split("f = ")[1].split()[0])
     fb = float(b[1].split("f = ")[1].split()[0])
     assert a[0] == b[0] and abs(fa - fb) <= 1e-3 * max(1.0, abs(fb))
+
+
+@pytest.mark.skipif(not refsrc.available(), reason="reference tree not mounted")
+@pytest.mark.parametrize("arg", [None, "24", "41", "31"])
+def test_reference_t_python_runs_on_the_shim(hosttest_lib, arg):
+    """The reference's own test/t_python.py (ctest t_python*), unmodified, with `import nlopt` resolved by
+    nlopt_b200/shim and the library pointed at the CPU-backed build of our host logic."""
+    env = dict(os.environ, PYTHONPATH=os.path.join(ROOT, "nlopt_b200", "shim"), NLOPT_B200_LIBRARY_PATH=hosttest_lib.path)
+    r = subprocess.run([os.sys.executable, os.path.join(refsrc.REF, "test", "t_python.py")] + ([arg] if arg else []),
+                       capture_output=True, text=True, env=env, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "minimum value: 0.5443" in r.stdout
