@@ -1,0 +1,105 @@
+"""Randomised (fixed seeds) comparison of the product's host logic with the unmodified reference on small problems
+that mix the corner cases of the CCSA loop: fixed variables (lb == ub), infinite bounds, infeasible starts (capped
+multipliers), vector constraints, maximisation, non-default parameters.  Short runs (<= 18 evaluations) so that the
+rounding-level differences between the two summation orders cannot be amplified yet:
+same return code, same evaluation count, f to 1e-6 relative and x to 1e-5 (measured differences are <= 1e-7: the
+dual problem is solved to ftol_rel = 1e-14, but its flat maximum turns last-bit differences of the sums into
+~1e-8 differences of y and x)."""
+import numpy as np
+import pytest
+
+import nlopt_b200 as nl
+
+
+def make_problem(seed):
+    rng = np.random.default_rng(seed)
+    n = int(rng.integers(2, 24))
+    m_scalar = int(rng.integers(0, 4))
+    vec_dim = int(rng.integers(0, 3))                    # one vector constraint of this dimension (0: none)
+    A = rng.normal(size=(n, n)) / np.sqrt(n)
+    Q = A @ A.T + 0.2 * np.eye(n)                        # convex quadratic objective
+    b = rng.normal(size=n)
+    W = rng.normal(size=(m_scalar + vec_dim, n))
+    off = rng.normal(size=m_scalar + vec_dim) * 0.3 + (0.4 if rng.random() < 0.5 else -0.4)   # some start infeasible
+    curv = rng.random(m_scalar + vec_dim) * 0.5
+    lb = -1.0 - rng.random(n)
+    ub = 1.0 + rng.random(n)
+    for j in rng.choice(n, size=max(1, n // 6), replace=False):
+        k = rng.integers(0, 4)
+        if k == 0:
+            lb[j] = ub[j] = 0.25                           # fixed variable: sigma = 0
+        elif k == 1:
+            lb[j] = -np.inf
+        elif k == 2:
+            ub[j] = np.inf
+        else:
+            lb[j], ub[j] = -np.inf, np.inf
+    x0 = np.clip(rng.normal(size=n) * 0.5, np.where(np.isinf(lb), -3, lb), np.where(np.isinf(ub), 3, ub))
+
+    def f(x, grad):
+        if grad.size:
+            grad[:] = Q @ x + b
+        return float(0.5 * x @ Q @ x + b @ x)
+
+    def con(i):
+        def c(x, grad):
+            if grad.size:
+                grad[:] = W[i] + 2 * curv[i] * x
+            return float(W[i] @ x + curv[i] * (x @ x) - off[i] - 1.0)
+        return c
+
+    def vcon(result, x, grad):
+        for k in range(vec_dim):
+            i = m_scalar + k
+            result[k] = W[i] @ x + curv[i] * (x @ x) - off[i] - 1.0
+            if grad.size:
+                grad[k, :] = W[i] + 2 * curv[i] * x
+
+    opts = {}
+    r = rng.random()
+    if r < 0.15:
+        opts["inner_maxeval"] = 2
+    elif r < 0.3:
+        opts["always_improve"] = 0
+    elif r < 0.45:
+        opts["inner_gradients"] = 0
+    elif r < 0.6:
+        opts["rho_init"] = 5.0
+    elif r < 0.7:
+        opts["sigma_min"] = 0.05
+    return dict(n=n, f=f, cons=[con(i) for i in range(m_scalar)], vec=(vcon, vec_dim) if vec_dim else None, lb=lb, ub=ub,
+                x0=x0, opts=opts, maximize=bool(rng.random() < 0.15), alg=nl.LD_MMA if rng.random() < 0.5 else nl.LD_CCSAQ,
+                maxeval=int(rng.integers(6, 19)))
+
+
+def run(lib, p):
+    o = nl.opt(p["alg"], p["n"], library=lib)
+    o.set_lower_bounds(p["lb"]); o.set_upper_bounds(p["ub"])
+    if p["maximize"]:
+        o.set_max_objective(lambda x, g: -p["f"](x, g) if g.size == 0 else _neg(p["f"], x, g))
+    else:
+        o.set_min_objective(p["f"])
+    for c in p["cons"]:
+        o.add_inequality_constraint(c, 1e-8)
+    if p["vec"]:
+        o.add_inequality_mconstraint(p["vec"][0], [1e-8] * p["vec"][1])
+    for k, v in p["opts"].items():
+        o.set_param(k, v)
+    o.set_maxeval(p["maxeval"])
+    x = o.optimize(p["x0"].copy())
+    return o.last_optimize_result(), o.get_numevals(), o.last_optimum_value(), x
+
+
+def _neg(f, x, g):
+    v = f(x, g)
+    g[:] = -g
+    return -v
+
+
+@pytest.mark.parametrize("seed", range(48))
+def test_random_small_problems_match_reference(hosttest_lib, reflib, seed):
+    p = make_problem(1000 + seed)
+    a, b = run(hosttest_lib, p), run(reflib, p)
+    assert a[0] == b[0] and a[1] == b[1], (a[:3], b[:3])
+    assert abs(a[2] - b[2]) <= 1e-6 * max(1.0, abs(b[2])), (a[2], b[2])
+    assert np.max(np.abs(a[3] - b[3])) <= 1e-5
