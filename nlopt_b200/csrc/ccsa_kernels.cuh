@@ -1,11 +1,13 @@
 // ccsa_kernels.cuh -- the CUDA kernels of the MMA/CCSAQ hot path (sm_100a).
 //
-//   dual_eval_kernel  : one dual evaluation  y -> x*(y), val, g0, w, g_1..g_m over this rank's shard
-//                       (reference: static dual_func, src/algs/mma/mma.c:59-137 and
-//                        src/algs/mma/ccsa_quadratic.c:79-148)
-//   sigma_init_kernel : mma.c:202-210
-//   end_outer_kernel  : nlopt_stop_x norms (src/util/stop.c:98-108) + sigma update (mma.c:431-442,
-//                       ccsa_quadratic.c:577-590) + xprev/xprevprev rotation (mma.c:264-265), one pass
+//   dual_eval_kernel     : one dual evaluation  y -> x*(y), val, g0, w, g_1..g_m over this rank's shard
+//                          (reference: static dual_func, src/algs/mma/mma.c:59-137 and
+//                           src/algs/mma/ccsa_quadratic.c:79-148); dual_eval_tma_kernel: same, operands staged by TMA
+//   dual_solve_kernel    : a whole dual solve (mma.c:275-288) in one persistent cooperative launch -- the default path
+//   sigma_init_kernel    : mma.c:202-210
+//   end_outer_kernel     : nlopt_stop_x norms (src/util/stop.c:98-108) + sigma update (mma.c:431-442,
+//                          ccsa_quadratic.c:577-590) + xprev/xprevprev rotation (mma.c:264-265), one pass
+//   penalty_axpy_kernel  : gradient of the augmented-Lagrangian objective (src/algs/auglag/auglag.c:47-48, :59-60)
 //
 // Arithmetic contract: every per-variable expression is evaluated with the reference's operation
 // order using __dmul_rn/__dadd_rn/__dsub_rn/__ddiv_rn/__dsqrt_rn, which nvcc never contracts into
@@ -13,13 +15,14 @@
 // therefore bit-identical to the reference; only the ORDER of the n-term sums differs (fixed
 // tree, see below), which is the documented parity tolerance.
 //
-// Reduction contract (deterministic and independent of the number of GPUs): the global index
-// space is cut into S = 8*P segments whose boundaries depend on n only.  One CTA reduces one
-// segment with a fixed thread->element map and a fixed shuffle/shared-memory tree and stores
-// m+3 partials.  The last CTA to finish a "virtual shard" (P consecutive segments; 8 of them,
-// each rank owns 8/world) folds that shard's partials in a fixed order; the last virtual shard
-// to finish folds the rank's shard sums in index order and publishes them -- to mapped host
-// memory when the rank is alone, else to the exchange buffer that the all-gather reads.
+// Reduction contract (deterministic and independent of the grid and of the number of GPUs): the global
+// index space is cut into S = 8*P groups whose boundaries depend on n only (geometry.hpp).  A group is
+// reduced with a fixed lane->element map and a fixed shuffle / shared-memory tree into one record of m+3
+// sums.  The P records of a "virtual shard" (8 shards; each rank owns 8/world) are folded in the canonical
+// shard order (fold_shard_records), the rank's shard sums in index order, and the 8 shard sums of all ranks
+// in index order.  Who does the folding differs by kernel -- the warp that completes a shard (atomic
+// ticket) in the one-evaluation kernels, a dedicated folder CTA polling tagged records in the solve
+// kernel -- the operations and their order do not, so every path gives the same bits.
 #pragma once
 
 #include <cuda_runtime.h>
