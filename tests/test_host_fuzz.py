@@ -103,3 +103,33 @@ def test_random_small_problems_match_reference(hosttest_lib, reflib, seed):
     assert a[0] == b[0] and a[1] == b[1], (a[:3], b[:3])
     assert abs(a[2] - b[2]) <= 1e-6 * max(1.0, abs(b[2])), (a[2], b[2])
     assert np.max(np.abs(a[3] - b[3])) <= 1e-5
+
+
+@pytest.mark.parametrize("seed", range(16))
+@pytest.mark.parametrize("stop", ["xtol_rel", "ftol_rel", "xtol_abs"])
+def test_random_small_problems_converge_to_the_reference_optimum(hosttest_lib, reflib, seed, stop):
+    """The same generator run to convergence under each stopping rule (stop.c:81-108): the result class must be a
+    success in both libraries and the optimum must agree (which rule fires first may legitimately differ at ties)."""
+    p = make_problem(5000 + seed)
+    out = []
+    for lib in (hosttest_lib, reflib):
+        o = nl.opt(p["alg"], p["n"], library=lib)
+        o.set_lower_bounds(p["lb"]); o.set_upper_bounds(p["ub"])
+        o.set_min_objective(p["f"])
+        for c in p["cons"]:
+            o.add_inequality_constraint(c, 1e-8)
+        if p["vec"]:
+            o.add_inequality_mconstraint(p["vec"][0], [1e-8] * p["vec"][1])
+        if stop == "xtol_rel":
+            o.set_xtol_rel(1e-9)
+        elif stop == "ftol_rel":
+            o.set_ftol_rel(1e-12)
+        else:
+            o.set_xtol_abs(np.full(p["n"], 1e-9))
+        o.set_maxeval(4000)
+        x = o.optimize(p["x0"].copy())
+        out.append((o.last_optimize_result(), o.last_optimum_value(), x))
+    (ra, fa, xa), (rb, fb, xb) = out
+    assert ra > 0 and rb > 0
+    if ra != nl.MAXEVAL_REACHED and rb != nl.MAXEVAL_REACHED:
+        assert abs(fa - fb) <= 1e-5 * max(1.0, abs(fb)), (ra, rb, fa, fb)       # slow CCSAQ tails stop a few 1e-6 apart
