@@ -328,3 +328,29 @@ def test_reference_t_python_runs_on_the_shim(hosttest_lib, arg):
                        capture_output=True, text=True, env=env, timeout=120)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "minimum value: 0.5443" in r.stdout
+
+
+def test_distinct_objects_on_distinct_threads(hosttest_lib):
+    """SURVEY.md 8(b) threading contract: an nlopt_opt must not be shared, but distinct objects may run on distinct
+    threads.  Eight threads, each with its own object and problem size; results must equal the sequential ones."""
+    import threading
+
+    def solve(n):
+        f, c = P.quad_problem(n)
+        r = run(hosttest_lib, nl.LD_MMA if n % 2 else nl.LD_CCSAQ, n, f, [c], [0.0], np.full(n, -1.0), np.full(n, 1.0),
+                np.full(n, -0.5), xtol_rel=1e-7, maxeval=80)
+        return r["ret"], r["numevals"], r["minf"], r["x"].tobytes()
+
+    sizes = [40 + 7 * k for k in range(8)]
+    want = [solve(n) for n in sizes]
+    got = [None] * len(sizes)
+
+    def worker(i):
+        got[i] = solve(sizes[i])
+
+    ts = [threading.Thread(target=worker, args=(i,)) for i in range(len(sizes))]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert got == want
