@@ -95,6 +95,10 @@ public:
     // copy the accepted point to host memory (or a device pointer in device mode)
     virtual bool fetch_x(double *x_out) = 0;
 
+    // Collective OR of a rank-local decision (time limits): with one rank, the identity.  Every rank of a sharded
+    // run calls it at the same points of the loop.
+    virtual bool agree_any(bool local) { return local; }
+
     // implementation knobs (e.g. "time_kernels"); unknown keys return false
     virtual bool configure(const char *key, long long value) { (void) key; (void) value; return false; }
 

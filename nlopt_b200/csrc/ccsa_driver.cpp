@@ -38,7 +38,13 @@ struct Loop {
 
     bool forced() const { return stop.force_stop && *stop.force_stop; }
     bool evals_out() const { return stop.maxeval > 0 && *stop.nevals_p >= stop.maxeval; }
-    bool timed_out() const { return stop.maxtime > 0 && wall_seconds() - start >= stop.maxtime; }
+    // Several ranks: every rank must take the same branch, or one returns MAXTIME while its peers wait in the next
+    // exchange.  The backend turns the local clock test into a collective one (any rank over the limit => all stop).
+    bool timed_out() const
+    {
+        if (!(stop.maxtime > 0)) return false;
+        return be.agree_any(wall_seconds() - start >= stop.maxtime);
+    }
     // MMA only: a NaN constraint value means "constraint switched off" (mma.c:141-143)
     bool off(double c) const { return variant == kMMA && std::isnan(c); }
 
@@ -78,7 +84,7 @@ int ccsa_minimize(Variant variant, Backend &be, const std::vector<double> &tol, 
                   const StopCriteria &stop, const CcsaParams &prm, DriverStats *stats, std::string *errmsg)
 {
     const unsigned m = be.m();
-    Loop L{variant, be, tol, stop, prm, stats, errmsg, wall_seconds(), m};
+    Loop L{variant, be, tol, stop, prm, stats, errmsg, stop.start >= 0 ? stop.start : wall_seconds(), m};
     const bool is_mma = variant == kMMA;
     const char *tag = is_mma ? "MMA" : "CCSA";
 

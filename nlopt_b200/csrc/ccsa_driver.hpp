@@ -16,6 +16,8 @@ struct StopCriteria {
     bool has_xtol_abs = false;
     int maxeval = 0;
     double maxtime = 0;
+    double start = -1;         // wall_seconds() when nlopt_optimize was entered (optimize.c:1001: stop.start is
+                               // taken before any algorithm setup); < 0: the driver takes it itself
     const int *force_stop = nullptr;
     int *nevals_p = nullptr;
 };

@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <vector>
 
 #include "../../include/nlopt_b200.h"
 
@@ -94,7 +95,13 @@ int Comm::init(const unsigned char id[128], int r, int w, int dev, std::string *
     const char *ex = std::getenv("NLOPT_B200_EXCHANGE");
     force_nccl_ = ex && std::strcmp(ex, "nccl") == 0;
     std::string perr;
-    if (setup_p2p(&perr) != 0) {
+    const int prc = setup_p2p(&perr);
+    if (prc == -2) {             // a bootstrap collective itself failed: the communicator is unusable
+        teardown_p2p();
+        if (err) *err = "mailbox bootstrap: " + perr;
+        return -1;
+    }
+    if (prc != 0) {              // agreed by ALL ranks (see setup_p2p): everyone takes the NCCL path
         std::fprintf(stderr, "nlopt_b200: peer mailboxes unavailable (%s); using NCCL all-gather per dual evaluation\n",
                      perr.c_str());
         teardown_p2p();
@@ -103,38 +110,65 @@ int Comm::init(const unsigned char id[128], int r, int w, int dev, std::string *
 }
 
 // Allocate this rank's mailbox, all-gather the CUDA IPC handles over NCCL, map every peer's mailbox.
+// The outcome is COLLECTIVE: a local failure (allocation, IPC export, IPC import of some peer) does not
+// return early -- every rank still takes part in both collectives below, and the mailbox path is enabled
+// only if the closing all-reduce shows that all ranks succeeded.  (A per-rank decision would leave some ranks
+// launching the mailbox kernel while others wait in ncclAllGather: a deadlock.)
 int Comm::setup_p2p(std::string *err)
 {
     p2p_ready = false;
-    if (cudaMalloc(&box_local_, kBoxDoubles * sizeof(double)) != cudaSuccess) { *err = "cudaMalloc mailbox"; return -1; }
-    cudaMemset(box_local_, 0, kBoxDoubles * sizeof(double));
+    bool ok = true;
+    std::string why;
+    auto note = [&](const char *what, cudaError_t ce) {
+        if (ok) why = std::string(what) + ": " + cudaGetErrorString(ce);
+        ok = false;
+        cudaGetLastError();
+    };
+    cudaError_t ce;
+    if ((ce = cudaMalloc(&box_local_, kBoxDoubles * sizeof(double))) != cudaSuccess) { box_local_ = nullptr; note("cudaMalloc mailbox", ce); }
+    if (box_local_) cudaMemset(box_local_, 0, kBoxDoubles * sizeof(double));
     cudaIpcMemHandle_t mine;
-    if (cudaIpcGetMemHandle(&mine, box_local_) != cudaSuccess) { *err = "cudaIpcGetMemHandle"; cudaGetLastError(); return -1; }
+    std::memset(&mine, 0, sizeof mine);
+    if (ok && (ce = cudaIpcGetMemHandle(&mine, box_local_)) != cudaSuccess) note("cudaIpcGetMemHandle", ce);
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle is 64 bytes");
+    const size_t per = sizeof(cudaIpcMemHandle_t) / sizeof(double) + 1;      // handle + "this rank is fine so far"
     double *stage = nullptr;
-    const size_t per = sizeof(cudaIpcMemHandle_t) / sizeof(double);
-    if (cudaMalloc(&stage, (size_t) world * sizeof(cudaIpcMemHandle_t)) != cudaSuccess) { *err = "cudaMalloc stage"; return -1; }
-    cudaMemcpy(stage + (size_t) rank * per, &mine, sizeof mine, cudaMemcpyHostToDevice);
-    std::string e2;
-    if (all_gather_inplace(stage, per, 0, &e2) != 0) { *err = e2; cudaFree(stage); return -1; }
-    cudaStreamSynchronize(0);
-    cudaIpcMemHandle_t all[8];
-    cudaMemcpy(all, stage, (size_t) world * sizeof(cudaIpcMemHandle_t), cudaMemcpyDeviceToHost);
-    cudaFree(stage);
-    for (int r = 0; r < world; ++r) {
-        if (r == rank) { box_peer[r] = box_local_; continue; }
-        void *p = nullptr;
-        cudaError_t ce = cudaIpcOpenMemHandle(&p, all[r], cudaIpcMemLazyEnablePeerAccess);
-        if (ce != cudaSuccess) { *err = std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(ce); cudaGetLastError(); return -1; }
-        box_peer[r] = (double *) p;
+    if (cudaMalloc(&stage, (size_t) world * per * sizeof(double)) != cudaSuccess) {
+        // without even this buffer the rank cannot join a collective at all: nothing sensible is left to do
+        *err = "cudaMalloc of the bootstrap buffer failed";
+        return -2;
     }
-    // nobody may start writing before everyone has mapped and zeroed: one tiny all-reduce as a barrier
-    double *one = nullptr;
-    cudaMalloc(&one, sizeof(double));
-    cudaMemset(one, 0, sizeof(double));
-    all_reduce_sum(one, 1, 0, &e2);
+    double rec[sizeof(cudaIpcMemHandle_t) / sizeof(double) + 1];
+    std::memcpy(rec, &mine, sizeof mine);
+    rec[per - 1] = ok ? 1.0 : 0.0;
+    cudaMemcpy(stage + (size_t) rank * per, rec, per * sizeof(double), cudaMemcpyHostToDevice);
+    std::string e2;
+    if (all_gather_inplace(stage, per, 0, &e2) != 0) { *err = e2; cudaFree(stage); return -2; }
     cudaStreamSynchronize(0);
-    cudaFree(one);
+    std::vector<double> all((size_t) world * per);
+    cudaMemcpy(all.data(), stage, all.size() * sizeof(double), cudaMemcpyDeviceToHost);
+    bool everyone = ok;
+    for (int r = 0; r < world; ++r) everyone = everyone && all[(size_t) r * per + per - 1] == 1.0;
+    if (everyone)
+        for (int r = 0; r < world; ++r) {
+            if (r == rank) { box_peer[r] = box_local_; continue; }
+            cudaIpcMemHandle_t h;
+            std::memcpy(&h, &all[(size_t) r * per], sizeof h);
+            void *p = nullptr;
+            if ((ce = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess)) != cudaSuccess) { note("cudaIpcOpenMemHandle", ce); break; }
+            box_peer[r] = (double *) p;
+        }
+    // closing collective: (a) nobody may start writing before everyone has mapped and zeroed, (b) the verdict
+    double bad = ok ? 0.0 : 1.0;
+    cudaMemcpy(stage, &bad, sizeof bad, cudaMemcpyHostToDevice);
+    if (all_reduce_sum(stage, 1, 0, &e2) != 0) { *err = e2; cudaFree(stage); return -2; }
+    cudaStreamSynchronize(0);
+    cudaMemcpy(&bad, stage, sizeof bad, cudaMemcpyDeviceToHost);
+    cudaFree(stage);
+    if (bad != 0.0) {
+        *err = ok ? "a peer rank could not set up its mailbox" : why;
+        return -1;
+    }
     p2p_ready = true;
     return 0;
 }

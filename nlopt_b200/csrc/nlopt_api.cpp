@@ -941,6 +941,7 @@ nlopt_result run_ccsa(nlopt_opt opt, double *x_host, double *x_dev, double *minf
     st.nevals_p = &opt->numevals;
     st.maxeval = opt->maxeval;
     st.maxtime = opt->maxtime;
+    st.start = t0;                                   /* the clock started before the device state was built */
     st.force_stop = &opt->force_stop;
 
     nb200::DriverStats ds;

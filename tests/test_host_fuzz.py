@@ -184,8 +184,6 @@ def test_non_finite_callback_values_are_handled_like_the_reference(hosttest_lib,
 
 
 @pytest.mark.gpu
-@pytest.mark.skipif(not __import__("os").environ.get("NLOPT_B200_EXTRA_GPU_TESTS"),
-                    reason="written after the round's GPU budget was spent: enable with NLOPT_B200_EXTRA_GPU_TESTS=1 once validated on a GPU")
 @pytest.mark.parametrize("seed", range(48))
 def test_random_small_problems_on_gpu_match_reference(built, reflib, seed):
     """The fixed-seed generator above through the product library (CUDA path)."""
