@@ -214,6 +214,33 @@ typedef double (*nlopt_b200_dfunc)(unsigned n_local, unsigned long long j0, cons
 nlopt_result nlopt_b200_set_min_objective_device(nlopt_opt opt, nlopt_b200_dfunc f, void *f_data);
 nlopt_result nlopt_b200_add_inequality_constraint_device(nlopt_opt opt, nlopt_b200_dfunc fc,
                                                          void *fc_data, double tol);
+
+/* Device callbacks, second form: asynchronous and independent of the number of ranks.
+ * The library cuts the n variables into groups and 8 "virtual shards" by a rule that depends on n only (the rule of the
+ * dual kernels); a rank owns the virtual shards [vshard0, vshard0 + local_vshards).  The callback enqueues its work on
+ * `cuda_stream` and leaves the partial sum of each of ITS virtual shards in vsums_dev[vshard] (8 doubles, zeroed by the
+ * library beforehand) -- reduced over the shard's groups in an order that depends on n only.  It does not synchronise
+ * and returns nothing: after all callbacks of a point have been enqueued, the library adds the 8 shard sums of all
+ * ranks in index order (so the value is bit-identical for 1, 2, 4 and 8 ranks) and calls finish(total, data) on the
+ * host for the function value.  One host synchronisation per point instead of one per function.
+ * `halo` > 0: the callback also reads x_dev[-halo .. -1] and x_dev[n_local .. n_local + halo - 1] (stencil functions
+ * such as the chained Rosenbrock function); the library fills these cells from the neighbouring ranks before the
+ * callbacks of a point run.  halo <= 1 in this build. */
+typedef struct {
+    unsigned long long n, n_local, j0;          /* global size; this rank's variables [j0, j0 + n_local)          */
+    unsigned long long nchunks, chunk0;         /* 512-variable chunks: all of them / first of this rank           */
+    unsigned groups_total, group0, groups_local, groups_per_vshard;   /* group g = chunks [g nchunks / groups_total, ...) */
+    unsigned vshard0, local_vshards;
+    int rank, world;
+} nlopt_b200_shard;
+void nlopt_b200_shard_geometry(unsigned long long n, int rank, int world, nlopt_b200_shard *out);
+typedef void (*nlopt_b200_dfunc2)(const nlopt_b200_shard *shard, const double *x_dev, double *grad_dev, double *vsums_dev,
+                                  void *func_data, void *cuda_stream);
+typedef double (*nlopt_b200_dfinish)(double total, void *func_data);
+nlopt_result nlopt_b200_set_min_objective_device2(nlopt_opt opt, nlopt_b200_dfunc2 f, nlopt_b200_dfinish finish,
+                                                  void *f_data, int halo);
+nlopt_result nlopt_b200_add_inequality_constraint_device2(nlopt_opt opt, nlopt_b200_dfunc2 fc, nlopt_b200_dfinish finish,
+                                                          void *fc_data, double tol, int halo);
 /* like nlopt_optimize, but x_dev is a device array of this rank's shard (in/out) */
 nlopt_result nlopt_b200_optimize_device(nlopt_opt opt, double *x_dev, double *opt_f);
 

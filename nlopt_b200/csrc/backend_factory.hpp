@@ -18,6 +18,9 @@ struct FuncSpec {
     nlopt_func f = nullptr;
     nlopt_mfunc mf = nullptr;
     nlopt_b200_dfunc df = nullptr;
+    nlopt_b200_dfunc2 df2 = nullptr;         // asynchronous device callback (takes precedence over df) ...
+    nlopt_b200_dfinish dfin = nullptr;       // ... and its host-side finish
+    int halo = 0;
     void *data = nullptr;
 };
 

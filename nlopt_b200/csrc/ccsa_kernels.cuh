@@ -1,13 +1,15 @@
 // ccsa_kernels.cuh -- the CUDA kernels of the MMA/CCSAQ hot path (sm_100a).
 //
-//   dual_eval_kernel     : one dual evaluation  y -> x*(y), val, g0, w, g_1..g_m over this rank's shard
-//                          (reference: static dual_func, src/algs/mma/mma.c:59-137 and
-//                           src/algs/mma/ccsa_quadratic.c:79-148); dual_eval_tma_kernel: same, operands staged by TMA
-//   dual_solve_kernel    : a whole dual solve (mma.c:275-288) in one persistent cooperative launch -- the default path
-//   sigma_init_kernel    : mma.c:202-210
-//   end_outer_kernel     : nlopt_stop_x norms (src/util/stop.c:98-108) + sigma update (mma.c:431-442,
-//                          ccsa_quadratic.c:577-590) + xprev/xprevprev rotation (mma.c:264-265), one pass
-//   penalty_axpy_kernel  : gradient of the augmented-Lagrangian objective (src/algs/auglag/auglag.c:47-48, :59-60)
+//   dual_eval_kernel      : one dual evaluation  y -> x*(y), val, g0, w, g_1..g_m over this rank's shard, m <= 16
+//                           (reference: static dual_func, src/algs/mma/mma.c:59-137 and
+//                            src/algs/mma/ccsa_quadratic.c:79-148); dual_eval_tma_kernel: same, operands staged by TMA
+//   dual_eval_wide_kernel : the same for ANY number of constraints (m > 16): rows of the gradient block streamed in
+//                           blocks of 8, the five n-vectors read once (the reference has no cap on m, mma.c:173)
+//   dual_solve_kernel     : a whole dual solve (mma.c:275-288) in one persistent cooperative launch -- the default path
+//   sigma_init_kernel     : mma.c:202-210
+//   end_outer_kernel      : nlopt_stop_x norms (src/util/stop.c:98-108) + sigma update (mma.c:431-442,
+//                           ccsa_quadratic.c:577-590) + xprev/xprevprev rotation (mma.c:264-265), one pass
+//   penalty_axpy_kernel   : gradient of the augmented-Lagrangian objective (src/algs/auglag/auglag.c:47-48, :59-60)
 //
 // Arithmetic contract: every per-variable expression is evaluated with the reference's operation
 // order using __dmul_rn/__dadd_rn/__dsub_rn/__ddiv_rn/__dsqrt_rn, which nvcc never contracts into
@@ -18,11 +20,11 @@
 // Reduction contract (deterministic and independent of the grid and of the number of GPUs): the global
 // index space is cut into S = 8*P groups whose boundaries depend on n only (geometry.hpp).  A group is
 // reduced with a fixed lane->element map and a fixed shuffle / shared-memory tree into one record of m+3
-// sums.  The P records of a "virtual shard" (8 shards; each rank owns 8/world) are folded in the canonical
-// shard order (fold_shard_records), the rank's shard sums in index order, and the 8 shard sums of all ranks
-// in index order.  Who does the folding differs by kernel -- the warp that completes a shard (atomic
-// ticket) in the one-evaluation kernels, a dedicated folder CTA polling tagged records in the solve
-// kernel -- the operations and their order do not, so every path gives the same bits.
+// sums, which its sweeper drops into a TAGGED 16-byte slot {value, tag} with one 128-bit store -- no fence,
+// no atomic, no ticket.  The P records of a "virtual shard" (8 shards; each rank owns 8/world) are folded in a
+// canonical order by a dedicated folder CTA that polls the tags (fold_generation), the rank's shard sums in
+// index order, and the 8 shard sums of all ranks in index order.  Every kernel here uses the same folder code,
+// so every path gives the same bits.
 #pragma once
 
 #include <cuda_runtime.h>
@@ -36,8 +38,9 @@ namespace nb200 {
 constexpr int kBlock = 256;              // threads per CTA of every kernel here
 constexpr int kWarps = kBlock / 32;
 constexpr int kVirtualShards = 8;        // V: fixed, so 1/2/4/8 ranks give bit-identical sums
-constexpr int kMaxParamM = 32;           // multipliers that travel as kernel parameters
-constexpr int kMaxNV = 3 + 16;           // accumulators one CTA carries: val, g0, w, <=16 g_i
+constexpr int kMaxParamM = 16;           // multipliers that travel as kernel parameters (register-row kernels); m > 16: wide kernel
+constexpr int kMaxNV = 3 + kMaxParamM;   // accumulators one CTA of the register-row kernels carries: val, g0, w, <=16 g_i
+constexpr int kWideMaxM = 2048;          // the wide kernel keeps its per-row scalars in shared memory (88 bytes per row)
 
 // ---- exact-rounding arithmetic (never fused) ---------------------------------------------
 __device__ __forceinline__ double mulx(double a, double b) { return __dmul_rn(a, b); }
@@ -45,13 +48,45 @@ __device__ __forceinline__ double addx(double a, double b) { return __dadd_rn(a,
 __device__ __forceinline__ double subx(double a, double b) { return __dsub_rn(a, b); }
 __device__ __forceinline__ double divx(double a, double b) { return __ddiv_rn(a, b); }
 
-// streaming loads: read-once data must not displace anything in L1
+__device__ __forceinline__ unsigned long long nb_globaltimer()     // nanoseconds, one clock for all SMs and all GPUs of a node
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+// streaming loads: read-once data must not displace anything in L1.  The L2 behaviour is chosen per ARRAY through a
+// cache-policy operand: arrays the caller asks to keep (DualArgs::l2_keep, a bit per operand array) are loaded
+// evict_last so that they survive in the 126 MB L2 from one dual evaluation to the next -- the persistent solve
+// kernel re-reads the same (5+m) arrays every generation, and once a rank's shard is small enough (8 GPUs at
+// n = 1e7: 10 MB per array) some of them fit; everything else is loaded evict_first so that it does not push them out.
 __device__ __forceinline__ double2 ld_stream(const double2 *p)
 {
     double2 v;
     asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
     return v;
 }
+__device__ __forceinline__ double2 ld_stream_pol(const double2 *p, unsigned long long pol)
+{
+    double2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;" : "=d"(v.x), "=d"(v.y) : "l"(p), "l"(pol));
+    return v;
+}
+struct L2Policies {
+    unsigned long long keep, stream;
+    unsigned mask;                      // bit k set: operand array k (0 x, 1 lb, 2 ub, 3 sigma, 4 grad f, 5+i row i) is kept
+    __device__ __forceinline__ void init(unsigned m)
+    {
+        mask = m;
+        asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(keep));
+        asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(stream));
+    }
+    __device__ __forceinline__ double2 ld(const double2 *p, int k) const
+    {
+        if (mask == 0u) return ld_stream(p);          // nothing to protect: the plain streaming load (no policy operand)
+        return ld_stream_pol(p, ((mask >> k) & 1u) ? keep : stream);
+    }
+};
 __device__ __forceinline__ void st_stream(double2 *p, double2 v)
 {
     asm volatile("st.global.L1::no_allocate.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(v.x), "d"(v.y) : "memory");
@@ -70,7 +105,8 @@ __device__ __forceinline__ bool box_get(const double *slot, unsigned long long t
     *value = __longlong_as_double(v);
     return t == tag;
 }
-constexpr int kBoxStride = 24;           // slots per virtual shard record (comm.hpp)
+constexpr int kBoxStride = 24;           // slots per virtual shard record (comm.hpp): <= 19 sums + 1 flag slot
+constexpr int kBoxFlagSlot = kMaxNV;     // slot 19: "this rank's time limit has expired" (see box_exchange)
 
 // The same slots inside one GPU (group records and published multipliers of the persistent solve kernel):
 // gpu-scope relaxed accesses are served by the L2.  (The .volatile = system-scope forms above, needed across
@@ -107,25 +143,27 @@ __device__ __forceinline__ bool slot_get(const double *slot, unsigned long long 
 }
 
 // Lane k < nv: write this rank's shard records into every peer's mailbox, then gather all 8 records of
-// sum k from the own mailbox and fold them in index order.  Returns the total in lanes < nv; *timed_out is
-// warp-uniform.
-// VS_LOCAL: the shard sums were written by this CTA (shared memory or own global writes ordered by a barrier): plain loads.
-template <bool VS_LOCAL = false>
+// sum k from the own mailbox and fold them in index order.  Lane kBoxFlagSlot carries one extra value per rank the
+// same way (`flag`, 0 or 1: the rank's time limit has expired); its total comes back in *any_flag (warp-uniform), so
+// that every rank takes the SAME decision -- a rank-local clock test would let one rank stop while its peers wait
+// for its next record.  Returns the total in lanes < nv; *timed_out (a peer died) is warp-uniform.
+// vsums: the shard sums written by this CTA (shared memory): plain loads.
 __device__ __forceinline__ double box_exchange(double *const *box, int rank, int world, unsigned long long seq,
                                                const double *vsums, int nvp, unsigned local_vshards, unsigned v0,
-                                               int nv, int lane, int *timed_out)
+                                               int nv, int lane, double flag, int *any_flag, int *timed_out)
 {
     const int buf = (int) (seq & 1ull);
     double total = 0.0;
     int to = 0;
-    if (lane < nv) {
+    const bool mine_lane = lane < nv || lane == kBoxFlagSlot;
+    if (mine_lane) {
         for (unsigned v = 0; v < local_vshards; ++v) {
-            const double val = VS_LOCAL ? vsums[(unsigned long long) v * nvp + lane] : __ldcg(vsums + (unsigned long long) v * nvp + lane);
+            const double val = lane < nv ? vsums[(unsigned long long) v * nvp + lane] : flag;
             for (int r = 0; r < world; ++r)
                 box_put(box[r] + 2ull * (((unsigned long long) buf * 8 + v0 + v) * kBoxStride + lane), val, seq);
         }
         const double *mine = box[rank] + 2ull * ((unsigned long long) buf * 8 * kBoxStride + lane);
-        const long long t0 = clock64();
+        const unsigned long long t0 = nb_globaltimer();
         double x[kVirtualShards];
         for (;;) {                         // all 8 slots are fetched together: one L2 round trip per poll
             bool ok[kVirtualShards];
@@ -135,13 +173,14 @@ __device__ __forceinline__ double box_exchange(double *const *box, int rank, int
 #pragma unroll
             for (int v = 0; v < kVirtualShards; ++v) all = all && ok[v];
             if (all) break;
-            if (clock64() - t0 > 20000000000ll) { to = 1; break; }          // ~10 s: a peer died
+            if (nb_globaltimer() - t0 > 10000000000ull) { to = 1; break; }          // 10 s: a peer died
         }
         total = x[0];
 #pragma unroll
         for (int v = 1; v < kVirtualShards; ++v) total = addx(total, x[v]);
     }
     *timed_out = __any_sync(0xffffffffu, to);
+    *any_flag = __shfl_sync(0xffffffffu, total, kBoxFlagSlot) > 0.0 ? 1 : 0;
     return total;
 }
 
@@ -163,34 +202,26 @@ struct DualArgs {
     unsigned segs_per_vshard;     // P
     unsigned local_vshards;       // 8 / world
     // reduction workspace
-    double *grouprecs;            // [local groups][nvp]       group records
-    double *vsums;                // [local_vshards][nvp]
-    unsigned *tickets;            // [local_vshards + 1], zero between launches
-    double *out_dev;              // [8][nvp] all-rank exchange buffer (this rank's slots filled)
-    volatile double *out_host;    // mapped pinned [nvp]; written when publish_host
+    double *grouptags;            // [nvp][local groups] tagged slots {value, tag}: the group records
+    unsigned long long tag;       // tag of this evaluation's records (unique per launch)
+    double *out_dev;              // [8][nvp] all-rank exchange buffer (this rank's slots filled)   (NCCL path)
+    volatile double *out_host;    // mapped pinned [nvp]; written when publish_host or the mailbox exchange is used
     volatile unsigned long long *flag_host;
     unsigned long long seq;
     int publish_host;             // 1: single rank, results + flag go straight to the host
-    int nvp;                      // stride of one record (>= 3 + chunk size)
+    int nvp;                      // stride of one record (>= 3 + m)
     // fused cross-rank exchange over NVLink peer memory (null box[0]: NCCL path instead)
     double *box[8];               // box[r]: rank r's mailbox as mapped into this process (CUDA IPC)
     int rank, world;
+    unsigned l2_keep;             // operand arrays to hold in L2 across evaluations (L2Policies::mask)
+    unsigned prefetch_chunks;     // solve kernel: chunks of its next group a waiting sweeper asks the L2 to fetch
     // the multipliers and penalties
     int m;                        // total number of constraints (rows of G)
-    int cons0, cons_n;            // this launch accumulates g_i for i in [cons0, cons0 + cons_n)
-    unsigned active;              // bit i clear: constraint i switched off (MMA, NaN value)
+    unsigned active;              // bit i clear: constraint i switched off (MMA, NaN value)            (m <= 16)
     double rho, half_rho, u_ccsaq;    // u_ccsaq = rho + sum_i rhoc_i y_i (ccsa_quadratic.c:116-120)
-    double y[kMaxParamM], rhoc[kMaxParamM], half_rhoc[kMaxParamM];
-};
-
-// the per-evaluation scalars as the point functions see them: for the one-evaluation kernel they alias
-// the __grid_constant__ parameter block (constant-bank operands), for the persistent solve kernel y lives
-// in shared memory and changes every generation
-struct Multipliers {
-    const double *y, *rhoc, *half_rhoc;
-    double rho, half_rho, u_ccsaq;
-    unsigned active;
-    int m, cons0, cons_n;
+    double y[kMaxParamM], rhoc[kMaxParamM], half_rhoc[kMaxParamM];       // (m <= 16)
+    const double *wide;           // m > 16: device block  y[m] | rhoc[m] | half_rhoc[m] | active[m] (1.0 / 0.0)
+    __device__ __forceinline__ double u() const { return u_ccsaq; }
 };
 
 // pair range [p_lo, p_hi) of global group `seg`, relative to the start of this rank's shard
@@ -224,7 +255,7 @@ __device__ __forceinline__ void block_reduce_to(double (&acc)[NV], double *smem 
     __syncthreads();
 }
 
-// true in exactly one CTA: the one whose ticket completes `total`
+// true in exactly one CTA: the one whose ticket completes `total`   (end_outer_kernel: once per outer iteration)
 __device__ __forceinline__ bool is_last_arrival(unsigned *ticket, unsigned total, int *s_flag)
 {
     __threadfence();
@@ -235,33 +266,23 @@ __device__ __forceinline__ bool is_last_arrival(unsigned *ticket, unsigned total
 }
 
 // ---- per-variable closed forms ------------------------------------------------------------------
-// MAXM rows of grad_c are kept in registers; FULL means m == MAXM with every constraint active, which
+// MAXM rows of grad_c are kept in registers (m <= MAXM); FULL means m == MAXM with every constraint active, which
 // strips the per-row predicates from the unrolled loops (the common case m in {1,2,4,8,16}).
 // MMA: mma.c:96-129.
 template <int MAXM, bool FULL, class MU>
 __device__ __forceinline__ double mma_point(const MU &a, double x, double lb, double ub, double s, double g,
-                                            const double (&Gr)[MAXM > 0 ? MAXM : 1], const double *Gcol,
-                                            unsigned long long ld, double (&acc)[3 + (MAXM > 0 ? MAXM : 1)])
+                                            const double (&Gr)[MAXM > 0 ? MAXM : 1], double (&acc)[3 + (MAXM > 0 ? MAXM : 1)])
 {
     if (s == 0) return x;                                    // fixed variable, mma.c:96-99
     const double ag_s = mulx(fabs(g), s);
     double u = g;
     double v = addx(ag_s, a.half_rho);
-    if (FULL || a.m <= MAXM) {
 #pragma unroll
-        for (int i = 0; i < MAXM; ++i)
-            if (FULL || (i < a.m && ((a.active >> i) & 1u))) {
-                u = addx(u, mulx(Gr[i], a.y[i]));
-                v = addx(v, mulx(addx(mulx(fabs(Gr[i]), s), a.half_rhoc[i]), a.y[i]));
-            }
-    } else {
-        for (int i = 0; i < a.m; ++i)
-            if ((a.active >> i) & 1u) {
-                const double gi = Gcol[(unsigned long long) i * ld];
-                u = addx(u, mulx(gi, a.y[i]));
-                v = addx(v, mulx(addx(mulx(fabs(gi), s), a.half_rhoc[i]), a.y[i]));
-            }
-    }
+    for (int i = 0; i < MAXM; ++i)
+        if (FULL || (i < a.m && ((a.active >> i) & 1u))) {
+            u = addx(u, mulx(Gr[i], a.y[i]));
+            v = addx(v, mulx(addx(mulx(fabs(Gr[i]), s), a.half_rhoc[i]), a.y[i]));
+        }
     const double s2 = mulx(s, s);
     u = mulx(u, s2);
     const double r = divx(u, mulx(v, s));
@@ -278,33 +299,24 @@ __device__ __forceinline__ double mma_point(const MU &a, double x, double lb, do
     acc[1] = addx(acc[1], mulx(addx(mulx(g, c), mulx(addx(ag_s, a.half_rho), dx2)), dinv));   // mma.c:123
     acc[2] = addx(acc[2], mulx(mulx(0.5, dx2), dinv));                                  // mma.c:125
 #pragma unroll
-    for (int k = 0; k < MAXM; ++k) {
-        const int i = FULL ? k : a.cons0 + k;
-        if (FULL || (k < a.cons_n && ((a.active >> i) & 1u))) {
-            const double gi = (FULL || a.m <= MAXM) ? Gr[k] : Gcol[(unsigned long long) i * ld];
+    for (int k = 0; k < MAXM; ++k)
+        if (FULL || (k < a.m && ((a.active >> k) & 1u)))
             acc[3 + k] = addx(acc[3 + k],
-                              mulx(addx(mulx(gi, c), mulx(addx(mulx(fabs(gi), s), a.half_rhoc[i]), dx2)), dinv));   // mma.c:127
-        }
-    }
+                              mulx(addx(mulx(Gr[k], c), mulx(addx(mulx(fabs(Gr[k]), s), a.half_rhoc[k]), dx2)), dinv));   // mma.c:127
     return xc;
 }
 
 // CCSAQ: ccsa_quadratic.c:111-140
 template <int MAXM, bool FULL, class MU>
 __device__ __forceinline__ double ccsaq_point(const MU &a, double x, double lb, double ub, double s, double g,
-                                              const double (&Gr)[MAXM > 0 ? MAXM : 1], const double *Gcol,
-                                              unsigned long long ld, double (&acc)[3 + (MAXM > 0 ? MAXM : 1)])
+                                              const double (&Gr)[MAXM > 0 ? MAXM : 1], double (&acc)[3 + (MAXM > 0 ? MAXM : 1)])
 {
     if (s == 0) return x;                                    // ccsa_quadratic.c:111-114
     double v = g;
-    if (FULL || a.m <= MAXM) {
 #pragma unroll
-        for (int i = 0; i < MAXM; ++i)
-            if (FULL || i < a.m) v = addx(v, mulx(Gr[i], a.y[i]));
-    } else {
-        for (int i = 0; i < a.m; ++i) v = addx(v, mulx(Gcol[(unsigned long long) i * ld], a.y[i]));
-    }
-    const double u = a.u_ccsaq;
+    for (int i = 0; i < MAXM; ++i)
+        if (FULL || i < a.m) v = addx(v, mulx(Gr[i], a.y[i]));
+    const double u = a.u();
     const double s2 = mulx(s, s);
     double dx = divx(mulx(-s2, v), u);                       // ccsa_quadratic.c:122
     if (fabs(dx) > s) dx = copysign(s, dx);                  // ccsa_quadratic.c:126
@@ -317,28 +329,11 @@ __device__ __forceinline__ double ccsaq_point(const MU &a, double x, double lb, 
     acc[1] = addx(acc[1], addx(mulx(g, dx), mulx(a.rho, q)));                            // :137
     acc[2] = addx(acc[2], q);                                                            // :138
 #pragma unroll
-    for (int k = 0; k < MAXM; ++k) {
-        const int i = FULL ? k : a.cons0 + k;
-        if (FULL || k < a.cons_n) {
-            const double gi = (FULL || a.m <= MAXM) ? Gr[k] : Gcol[(unsigned long long) i * ld];
-            acc[3 + k] = addx(acc[3 + k], addx(mulx(gi, dx), mulx(a.rhoc[i], q)));       // :139-140
-        }
-    }
+    for (int k = 0; k < MAXM; ++k)
+        if (FULL || k < a.m) acc[3 + k] = addx(acc[3 + k], addx(mulx(Gr[k], dx), mulx(a.rhoc[k], q)));       // :139-140
     return xc;
 }
 
-// ---- the dual evaluation kernel ---------------------------------------------------------------------
-// Persistent CTAs (grid sized to the machine).  A *group* is a contiguous run of 512-variable chunks;
-// the 8 warps of a group slot sweep it together -- sweep step t reads one 4 KB-contiguous chunk per array,
-// warp w taking lanes [32w, 32w+32) of it -- but every warp keeps its OWN m+3 accumulators over the group
-// and folds them with a fixed xor-butterfly into a warp record.  The streaming loop has no barrier; one
-// slot barrier per group hands the 8 warp records to warp 0 through shared memory.
-// Fold tree (all in fixed order, all un-fused adds):
-//   warp record -> group record (8 warp records in warp order, by warp 0 of the slot)
-//               -> virtual-shard sum (P group records, by the warp that completes the shard)
-//               -> rank sum / exchange buffer (8/world shard sums, by the warp that completes the rank).
-// A record depends only on n (the cuts) -- never on the grid size, on which CTA swept the group or on the
-// number of ranks -- so the m+3 sums are bit-identical for every launch geometry and every world size.
 template <int NV>
 __device__ __forceinline__ void warp_fold(double (&acc)[NV])
 {
@@ -349,40 +344,146 @@ __device__ __forceinline__ void warp_fold(double (&acc)[NV])
     }
 }
 
-__device__ __forceinline__ bool warp_is_last(unsigned *ticket, unsigned total, int lane)
+// ---- folding the tagged group records of one evaluation (one "generation") --------------------------------------
+// Slot (group gl, sum k) lives at grouptags[2 * (k * ngroups + gl)]: the 32 lanes of a poll read 512 contiguous bytes.
+// fold_generation<NV>: called by ALL 256 threads of the folder CTA.  Polls the records tagged `tag` of the local
+// virtual shards for the sums [k0, k0 + nk), nk <= NV, and leaves the shard sums in s_vs[v * NV + k] (valid after
+// the call for warp 0, which is the only reader).
+// Canonical order of one shard's P records: chain t in [0, 256) adds records t, t+256, ... in index order; the 32
+// chains of "fold warp" w = t / 32 meet in an xor butterfly; the 8 fold-warp results are added in warp order.  Work
+// item (v, w) = fold warp w of local shard v; items are dealt round-robin to the 8 physical warps in (v, w) order --
+// shards complete roughly in index order, and when P <= 32 (small n, or one shard per rank with 8 GPUs) all shards
+// are polled side by side.  Empty fold warps contribute the +0.0 parked in s_w by fold_init.
+// Warp-uniform control flow: a warp polls until all of its lanes have their record (measured: a warp whose lanes
+// left the poll loop at different times took ~9 us per shard instead of < 1 us).
+// barrier of the 8 folder warps (a named barrier with an explicit count: the TMA kernel's CTAs carry a ninth warp)
+__device__ __forceinline__ void fold_barrier() { asm volatile("bar.sync 1, %0;" ::"r"(32 * kGroupWarps) : "memory"); }
+
+template <int NV>
+__device__ __forceinline__ void fold_init(double *s_w)
 {
-    unsigned t = 0;
-    __threadfence();
-    if (lane == 0) t = atomicAdd(ticket, 1u);
-    t = __shfl_sync(0xffffffffu, t, 0);
-    __threadfence();
-    return t == total - 1u;
+    for (int i = threadIdx.x; i < kVirtualShards * kGroupWarps * NV; i += 32 * kGroupWarps) s_w[i] = 0.0;
+    fold_barrier();
 }
 
-// Virtual-shard sum of P group records, canonical order (the order the solve kernel's folder CTA produces with
-// its 256 threads): chain t in [0, 256) adds records t, t+256, ... in index order; the 32 chains of "fold warp"
-// w = t / 32 meet in an xor butterfly; the 8 fold-warp results are added in warp order.  Here one warp plays
-// the 8 fold warps in turn.  Every lane returns all NV sums.
 template <int NV>
-__device__ __forceinline__ void fold_shard_records(const double *base, unsigned P, int nvp, int lane, double (&tot)[NV])
+__device__ __forceinline__ void fold_generation(const double *grouptags, unsigned ngroups, unsigned P, unsigned local_vshards,
+                                                unsigned long long tag, int k0, int nk, double *s_w, double *s_vs)
 {
-#pragma unroll 1
-    for (int w = 0; w < kGroupWarps; ++w) {
+    const int lane = threadIdx.x & 31;
+    const int sub = threadIdx.x >> 5;
+    const unsigned fw_all = (P + 31u) / 32u;
+    const unsigned fw_per = fw_all < (unsigned) kGroupWarps ? fw_all : (unsigned) kGroupWarps;      // non-empty fold warps per shard
+    const unsigned nitems = local_vshards * fw_per;
+    for (unsigned item = sub; item < nitems; item += kGroupWarps) {
+        const unsigned v = item / fw_per, w = item % fw_per;
         double acc[NV];
 #pragma unroll
         for (int k = 0; k < NV; ++k) acc[k] = 0.0;
-        for (unsigned r = 32 * w + lane; r < P; r += 32 * kGroupWarps)
+        const double *base = grouptags + 2ull * ((unsigned long long) k0 * ngroups + (unsigned long long) v * P);
+        for (unsigned r0 = 32u * w; r0 < P; r0 += 32 * kGroupWarps) {
+            const unsigned r = r0 + lane;
+            const bool has = r < P;
+            const double *rec = base + 2ull * (has ? r : 0u);
+            double val[NV];
+            for (;;) {                // the sums of a record are fetched together: one round trip per poll
+                bool all = true;
 #pragma unroll
-            for (int k = 0; k < NV; ++k) acc[k] = addx(acc[k], __ldcg(base + (unsigned long long) r * nvp + k));
+                for (int k = 0; k < NV; ++k) {
+                    val[k] = 0.0;
+                    if (k < nk) all = slot_peek(rec + 2ull * k * ngroups, tag, &val[k]) && all;
+                }
+                if (__all_sync(0xffffffffu, all || !has)) break;
+                __nanosleep(20);
+            }
+            if (has) {
+#pragma unroll
+                for (int k = 0; k < NV; ++k) acc[k] = addx(acc[k], val[k]);
+            }
+        }
         warp_fold<NV>(acc);
+        if (lane == 0) {
 #pragma unroll
-        for (int k = 0; k < NV; ++k) tot[k] = w == 0 ? acc[k] : addx(tot[k], acc[k]);
+            for (int k = 0; k < NV; ++k) s_w[(v * kGroupWarps + w) * NV + k] = acc[k];
+        }
+    }
+    fold_barrier();
+    if (sub == 0 && lane < NV) {
+        for (unsigned v = 0; v < local_vshards; ++v) {
+            double t = s_w[(v * kGroupWarps) * NV + lane];
+#pragma unroll
+            for (int w = 1; w < kGroupWarps; ++w) t = addx(t, s_w[(v * kGroupWarps + w) * NV + lane]);
+            s_vs[v * NV + lane] = t;
+        }
+    }
+    __syncwarp();
+}
+
+// The folder CTA of the one-evaluation kernels (the last CTA of the grid; sweepers never wait for it, so it may start
+// late when the grid exceeds the machine).  Sums [0, nv_total) in tiles of NV.
+//   single rank          : totals -> mapped pinned out_host, then the flag
+//   mailbox exchange     : shard sums -> every peer's mailbox -> totals -> out_host, flag      (nv_total <= kMaxNV)
+//   NCCL exchange        : shard sums -> out_dev (ncclAllGather + publish_kernel follow on the stream)
+template <int NV>
+__device__ __noinline__ void eval_folder(const DualArgs &a, int nv_total)
+{
+    __shared__ double s_vs[kVirtualShards * NV];
+    __shared__ double s_w[kVirtualShards * kGroupWarps * NV];
+    const int lane = threadIdx.x & 31, sub = threadIdx.x >> 5;
+    const unsigned ngroups = a.segs_per_vshard * a.local_vshards;
+    fold_init<NV>(s_w);
+    for (int k0 = 0; k0 < nv_total; k0 += NV) {
+        const int nk = nv_total - k0 < NV ? nv_total - k0 : NV;
+        fold_generation<NV>(a.grouptags, ngroups, a.segs_per_vshard, a.local_vshards, a.tag, k0, nk, s_w, s_vs);
+        if (sub == 0) {
+            if (a.publish_host) {
+                if (lane < nk) {
+                    double s = s_vs[lane];
+                    for (unsigned v = 1; v < a.local_vshards; ++v) s = addx(s, s_vs[v * NV + lane]);
+                    a.out_host[k0 + lane] = s;
+                }
+            } else if (a.box[0] == nullptr) {
+                const unsigned v0 = a.seg0 / a.segs_per_vshard;
+                if (lane < nk)
+                    for (unsigned v = 0; v < a.local_vshards; ++v)
+                        a.out_dev[(unsigned long long) (v0 + v) * a.nvp + k0 + lane] = s_vs[v * NV + lane];
+            } else {
+                int timed_out = 0, any_flag = 0;
+                const double total = box_exchange(a.box, a.rank, a.world, a.seq, s_vs, NV, a.local_vshards,
+                                                  a.seg0 / a.segs_per_vshard, nk, lane, 0.0, &any_flag, &timed_out);
+                if (lane < nk) a.out_host[k0 + lane] = timed_out ? __longlong_as_double(0x7ff8000000000000ll) : total;
+            }
+        }
+        fold_barrier();
+    }
+    if (sub == 0 && (a.publish_host || a.box[0] != nullptr)) {
+        __threadfence_system();
+        __syncwarp();
+        if (lane == 0) {
+            *a.flag_host = a.seq;
+            __threadfence_system();
+        }
     }
 }
 
+// ---- the dual evaluation kernel ---------------------------------------------------------------------
+// Persistent sweeper CTAs (grid sized to the machine) + one folder CTA.  A *group* is a contiguous run of
+// 512-variable chunks; the 8 warps of a group slot sweep it together -- sweep step t reads one 4 KB-contiguous chunk
+// per array, warp w taking lanes [32w, 32w+32) of it -- but every warp keeps its OWN m+3 accumulators over the group
+// and folds them with a fixed xor-butterfly into a warp record.  The streaming loop has no barrier; one
+// slot barrier per group hands the 8 warp records to warp 0 through shared memory.
+// Fold tree (all in fixed order, all un-fused adds):
+//   warp record -> group record (8 warp records in warp order, by warp 0 of the slot)
+//               -> virtual-shard sum (P group records, canonical order, by the folder CTA)
+//               -> rank sum / exchange (8/world shard sums in index order).
+// A record depends only on n (the cuts) -- never on the grid size, on which CTA swept the group or on the
+// number of ranks -- so the m+3 sums are bit-identical for every launch geometry and every world size.
+//
 // Sweep one group: this warp's lanes of every chunk of group `gl`, m+3 lane accumulators.
-template <int VARIANT, int MAXM, bool FULL, int UNROLL, class MU>
-__device__ __forceinline__ void sweep_group(const DualArgs &a, const MU &mu, bool store, unsigned gl, int sub,
+// POL: load through the per-array L2 cache policies (persistent solve kernel with b200_l2_keep_mb), else plain
+// streaming loads.
+template <int VARIANT, int MAXM, bool FULL, int UNROLL, bool POL, class MU>
+__device__ __forceinline__ void sweep_group(const DualArgs &a, const MU &mu, const L2Policies &pol, bool store, unsigned gl, int sub,
                                             int lane, double (&acc)[3 + (MAXM > 0 ? MAXM : 1)])
 {
     constexpr int MR = MAXM > 0 ? MAXM : 1;
@@ -391,7 +492,6 @@ __device__ __forceinline__ void sweep_group(const DualArgs &a, const MU &mu, boo
     const double2 *ub2 = reinterpret_cast<const double2 *>(a.ub);
     const double2 *s2v = reinterpret_cast<const double2 *>(a.sigma);
     const double2 *g2 = reinterpret_cast<const double2 *>(a.g);
-    const bool in_regs = FULL || mu.m <= MAXM;
     unsigned long long p_lo, p_hi;
     group_pairs(a.nchunks, a.nseg_total, a.chunk0, a.seg0 + gl, &p_lo, &p_hi);
 
@@ -405,15 +505,21 @@ __device__ __forceinline__ void sweep_group(const DualArgs &a, const MU &mu, boo
             vs[u] = make_double2(0.0, 0.0);      // sigma = 0 lanes are skipped by both formulas
             vx[u] = vlb[u] = vub[u] = vg[u] = make_double2(0.0, 0.0);
             if (live) {
-                vx[u] = ld_stream(x2 + p); vlb[u] = ld_stream(lb2 + p); vub[u] = ld_stream(ub2 + p);
-                vs[u] = ld_stream(s2v + p); vg[u] = ld_stream(g2 + p);
+                if (POL) {
+                    vx[u] = pol.ld(x2 + p, 0); vlb[u] = pol.ld(lb2 + p, 1); vub[u] = pol.ld(ub2 + p, 2);
+                    vs[u] = pol.ld(s2v + p, 3); vg[u] = pol.ld(g2 + p, 4);
+                } else {
+                    vx[u] = ld_stream(x2 + p); vlb[u] = ld_stream(lb2 + p); vub[u] = ld_stream(ub2 + p);
+                    vs[u] = ld_stream(s2v + p); vg[u] = ld_stream(g2 + p);
+                }
             }
 #pragma unroll
             for (int i = 0; i < MR; ++i) {
                 Ga[u][i] = 0.0;
                 Gb[u][i] = 0.0;
-                if (MAXM > 0 && in_regs && (FULL || i < mu.m) && live) {
-                    const double2 t = ld_stream(reinterpret_cast<const double2 *>(a.G + (unsigned long long) i * a.ld) + p);
+                if (MAXM > 0 && (FULL || i < mu.m) && live) {
+                    const double2 *gp = reinterpret_cast<const double2 *>(a.G + (unsigned long long) i * a.ld) + p;
+                    const double2 t = POL ? pol.ld(gp, 5 + i) : ld_stream(gp);
                     Ga[u][i] = t.x;
                     Gb[u][i] = t.y;
                 }
@@ -423,17 +529,55 @@ __device__ __forceinline__ void sweep_group(const DualArgs &a, const MU &mu, boo
         for (int u = 0; u < UNROLL; ++u) {
             const unsigned long long p = p0 + (unsigned long long) kChunkPairs * u;
             const bool live = u == 0 || p < p_hi;
-            const double *col = a.G + 2 * p;
             double2 xc;
             if (VARIANT == 0) {
-                xc.x = mma_point<MAXM, FULL>(mu, vx[u].x, vlb[u].x, vub[u].x, vs[u].x, vg[u].x, Ga[u], col, a.ld, acc);
-                xc.y = mma_point<MAXM, FULL>(mu, vx[u].y, vlb[u].y, vub[u].y, vs[u].y, vg[u].y, Gb[u], col + 1, a.ld, acc);
+                xc.x = mma_point<MAXM, FULL>(mu, vx[u].x, vlb[u].x, vub[u].x, vs[u].x, vg[u].x, Ga[u], acc);
+                xc.y = mma_point<MAXM, FULL>(mu, vx[u].y, vlb[u].y, vub[u].y, vs[u].y, vg[u].y, Gb[u], acc);
             } else {
-                xc.x = ccsaq_point<MAXM, FULL>(mu, vx[u].x, vlb[u].x, vub[u].x, vs[u].x, vg[u].x, Ga[u], col, a.ld, acc);
-                xc.y = ccsaq_point<MAXM, FULL>(mu, vx[u].y, vlb[u].y, vub[u].y, vs[u].y, vg[u].y, Gb[u], col + 1, a.ld, acc);
+                xc.x = ccsaq_point<MAXM, FULL>(mu, vx[u].x, vlb[u].x, vub[u].x, vs[u].x, vg[u].x, Ga[u], acc);
+                xc.y = ccsaq_point<MAXM, FULL>(mu, vx[u].y, vlb[u].y, vub[u].y, vs[u].y, vg[u].y, Gb[u], acc);
             }
             if (store && live) st_stream(reinterpret_cast<double2 *>(a.xcur) + p, xc);
         }
+    }
+}
+
+// The operands of a sweep do not depend on the multipliers.  A sweeper of the persistent solve kernel that has to wait
+// for the next generation's multipliers first asks the L2 to fetch the head of its next group -- one bulk prefetch per
+// operand array, issued by one thread each, no registers held -- so that the serial part of a generation (last
+// record, fold, exchange, optimiser step, publication) overlaps with HBM traffic instead of leaving the memory system
+// idle: `chunks` x (5+m) x 4 KB per CTA.
+__device__ __forceinline__ void prefetch_l2_bulk(const void *p, unsigned bytes)
+{
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+// called by ONE thread: the bulk prefetch is a uniform-datapath instruction (UBLKPF), one array per issue
+__device__ __forceinline__ void prefetch_group_head(const DualArgs &a, unsigned gl, unsigned chunks)
+{
+    unsigned long long p_lo, p_hi;
+    group_pairs(a.nchunks, a.nseg_total, a.chunk0, a.seg0 + gl, &p_lo, &p_hi);
+    unsigned long long np = p_hi - p_lo;
+    if (np > (unsigned long long) chunks * kChunkPairs) np = (unsigned long long) chunks * kChunkPairs;
+    if (np == 0) return;
+    const unsigned bytes = (unsigned) (np * 16);
+    prefetch_l2_bulk(a.x + 2 * p_lo, bytes);
+    prefetch_l2_bulk(a.lb + 2 * p_lo, bytes);
+    prefetch_l2_bulk(a.ub + 2 * p_lo, bytes);
+    prefetch_l2_bulk(a.sigma + 2 * p_lo, bytes);
+    prefetch_l2_bulk(a.g + 2 * p_lo, bytes);
+    for (int i = 0; i < a.m; ++i) prefetch_l2_bulk(a.G + (unsigned long long) i * a.ld + 2 * p_lo, bytes);
+}
+
+// group record = the 8 warp records added in warp order, dropped into the group's tagged slots
+template <int NV>
+__device__ __forceinline__ void put_group_record(const double *srec, double *grouptags, unsigned ngroups, unsigned gl,
+                                                 unsigned long long tag, int lane)
+{
+    if (lane < NV) {
+        double s = srec[lane];
+#pragma unroll
+        for (int w = 1; w < kGroupWarps; ++w) s = addx(s, srec[w * NV + lane]);
+        slot_put(grouptags + 2ull * ((unsigned long long) lane * ngroups + gl), s, tag);
     }
 }
 
@@ -442,85 +586,36 @@ __global__ void __launch_bounds__(BLOCK, MINB) dual_eval_kernel(const __grid_con
 {
     constexpr int MR = MAXM > 0 ? MAXM : 1;
     constexpr int NV = 3 + MR;
-    constexpr int SLOTS = BLOCK / (32 * kGroupWarps);        // groups a CTA sweeps at a time
-    static_assert(BLOCK % (32 * kGroupWarps) == 0, "a CTA holds whole group slots");
+    static_assert(BLOCK == 32 * kGroupWarps, "one group slot per CTA");
+    if (blockIdx.x == gridDim.x - 1) {
+        eval_folder<NV>(a, NV);
+        return;
+    }
     const int lane = threadIdx.x & 31;
-    const int sub = (threadIdx.x >> 5) % kGroupWarps;        // which eighth of every chunk this warp owns
-    const unsigned slot = blockIdx.x * SLOTS + (threadIdx.x >> 5) / kGroupWarps;
-    const unsigned nslots = gridDim.x * SLOTS;
+    const int sub = threadIdx.x >> 5;
+    const unsigned nslots = gridDim.x - 1;
     const unsigned ngroups = a.segs_per_vshard * a.local_vshards;
-    __shared__ double s_rec[SLOTS][2][kGroupWarps * NV];
+    __shared__ double s_rec[2][kGroupWarps * NV];
+    L2Policies pol;
+    pol.init(a.l2_keep);
     int parity = 0;
-    for (unsigned gl = slot; gl < ngroups; gl += nslots) {
+    for (unsigned gl = blockIdx.x; gl < ngroups; gl += nslots) {
         double acc[NV];
 #pragma unroll
         for (int k = 0; k < NV; ++k) acc[k] = 0.0;
-        sweep_group<VARIANT, MAXM, FULL, UNROLL>(a, a, STORE, gl, sub, lane, acc);   // multipliers = the parameter block itself
+        sweep_group<VARIANT, MAXM, FULL, UNROLL, false>(a, a, pol, STORE, gl, sub, lane, acc);   // multipliers = the parameter block itself
 
-        // warp record -> shared memory; group record = the 8 warp records added in warp order by warp 0 of
-        // the slot.  One slot barrier per group; the record buffer is double-buffered across iterations so
-        // the next group's writers can never overtake this group's reader.
+        // warp record -> shared memory; one CTA barrier per group; the record buffer is double-buffered across
+        // iterations so the next group's writers can never overtake this group's reader.
         warp_fold<NV>(acc);
-        double *srec = s_rec[(threadIdx.x >> 5) / kGroupWarps][parity];
+        double *srec = s_rec[parity];
         if (lane == 0) {
 #pragma unroll
             for (int k = 0; k < NV; ++k) srec[sub * NV + k] = acc[k];
         }
-        if (SLOTS == 1) __syncthreads();
-        else asm volatile("bar.sync %0, %1;" ::"r"((int) ((threadIdx.x >> 5) / kGroupWarps) + 1), "r"(32 * kGroupWarps) : "memory");
+        __syncthreads();
         parity ^= 1;
-        if (sub != 0) continue;
-        if (lane < NV) {
-            double s = srec[lane];
-#pragma unroll
-            for (int w = 1; w < kGroupWarps; ++w) s = addx(s, srec[w * NV + lane]);
-            a.grouprecs[(unsigned long long) gl * a.nvp + lane] = s;
-        }
-        __syncwarp();
-
-        // virtual-shard sum, by the warp that completes the shard
-        const unsigned vs_local = gl / a.segs_per_vshard;
-        if (!warp_is_last(a.tickets + vs_local, a.segs_per_vshard, lane)) continue;
-        fold_shard_records<NV>(a.grouprecs + (unsigned long long) vs_local * a.segs_per_vshard * a.nvp, a.segs_per_vshard,
-                               a.nvp, lane, acc);
-        if (lane == 0) {
-            double *rec = a.vsums + (unsigned long long) vs_local * a.nvp;
-#pragma unroll
-            for (int k = 0; k < NV; ++k) rec[k] = acc[k];
-        }
-
-        // rank sum, by the warp that completes the last virtual shard
-        if (!warp_is_last(a.tickets + a.local_vshards, a.local_vshards, lane)) continue;
-        if (lane < NV) {
-            if (a.publish_host) {
-                double s = __ldcg(a.vsums + lane);
-                for (unsigned v = 1; v < a.local_vshards; ++v) s = addx(s, __ldcg(a.vsums + (unsigned long long) v * a.nvp + lane));
-                a.out_host[lane] = s;
-                __threadfence_system();
-            } else if (a.box[0] == nullptr) {
-                const unsigned v0 = a.seg0 / a.segs_per_vshard;
-                for (unsigned v = 0; v < a.local_vshards; ++v)
-                    a.out_dev[(unsigned long long) (v0 + v) * a.nvp + lane] = __ldcg(a.vsums + (unsigned long long) v * a.nvp + lane);
-            }
-        }
-        if (!a.publish_host && a.box[0] != nullptr) {
-            // ---- all-gather fused into the kernel: tagged NVLink peer stores (comm.hpp layout) ----
-            int timed_out = 0;
-            const double total = box_exchange(a.box, a.rank, a.world, a.seq, a.vsums, a.nvp, a.local_vshards,
-                                              a.seg0 / a.segs_per_vshard, NV, lane, &timed_out);
-            if (lane < NV) {
-                a.out_host[lane] = timed_out ? __longlong_as_double(0x7ff8000000000000ll) : total;
-                __threadfence_system();
-            }
-        }
-        __syncwarp();
-        if (lane == 0) {
-            for (unsigned v = 0; v <= a.local_vshards; ++v) a.tickets[v] = 0;    // ready for the next launch
-            if (a.publish_host || a.box[0] != nullptr) {
-                *a.flag_host = a.seq;
-                __threadfence_system();
-            }
-        }
+        if (sub == 0) put_group_record<NV>(srec, a.grouptags, ngroups, gl, a.tag, lane);
     }
 }
 
@@ -561,7 +656,6 @@ __device__ __forceinline__ void tma_bulk_load(void *smem_dst, const void *gmem_s
 
 constexpr int kTmaBlock = 32 * (kGroupWarps + 1);        // 8 consumer warps + 1 producer warp
 constexpr unsigned kChunkBytes = kChunkPairs * 16;       // 4 KB per array per stage
-
 template <int VARIANT, int MAXM, bool STORE, int STAGES, int MINB>
 __global__ void __launch_bounds__(kTmaBlock, MINB) dual_eval_tma_kernel(const __grid_constant__ DualArgs a)
 {
@@ -576,6 +670,12 @@ __global__ void __launch_bounds__(kTmaBlock, MINB) dual_eval_tma_kernel(const __
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const unsigned ngroups = a.segs_per_vshard * a.local_vshards;
+    const unsigned nslots = gridDim.x - 1;
+
+    if (blockIdx.x == gridDim.x - 1) {                        // the folder CTA: its 8 first warps
+        if (warp < kGroupWarps) eval_folder<NV>(a, NV);
+        return;
+    }
 
     if (threadIdx.x == 0) {
         for (int st = 0; st < STAGES; ++st) {
@@ -595,7 +695,7 @@ __global__ void __launch_bounds__(kTmaBlock, MINB) dual_eval_tma_kernel(const __
             for (int i = 0; i < MAXM; ++i) src[5 + i] = a.G + (unsigned long long) i * a.ld;
             int st = 0;
             unsigned phase = 0;
-            for (unsigned gl = blockIdx.x; gl < ngroups; gl += gridDim.x) {
+            for (unsigned gl = blockIdx.x; gl < ngroups; gl += nslots) {
                 unsigned long long p_lo, p_hi;
                 group_pairs(a.nchunks, a.nseg_total, a.chunk0, a.seg0 + gl, &p_lo, &p_hi);
                 for (unsigned long long p = p_lo; p < p_hi; p += kChunkPairs) {
@@ -616,7 +716,7 @@ __global__ void __launch_bounds__(kTmaBlock, MINB) dual_eval_tma_kernel(const __
     int st = 0;
     unsigned phase = 0;
     int parity = 0;
-    for (unsigned gl = blockIdx.x; gl < ngroups; gl += gridDim.x) {
+    for (unsigned gl = blockIdx.x; gl < ngroups; gl += nslots) {
         unsigned long long p_lo, p_hi;
         group_pairs(a.nchunks, a.nseg_total, a.chunk0, a.seg0 + gl, &p_lo, &p_hi);
         double acc[NV];
@@ -638,11 +738,11 @@ __global__ void __launch_bounds__(kTmaBlock, MINB) dual_eval_tma_kernel(const __
             if (++st == STAGES) { st = 0; phase ^= 1u; }
             double2 xc;
             if (VARIANT == 0) {
-                xc.x = mma_point<MAXM, true>(a, vx.x, vlb.x, vub.x, vs.x, vg.x, Ga, nullptr, a.ld, acc);
-                xc.y = mma_point<MAXM, true>(a, vx.y, vlb.y, vub.y, vs.y, vg.y, Gb, nullptr, a.ld, acc);
+                xc.x = mma_point<MAXM, true>(a, vx.x, vlb.x, vub.x, vs.x, vg.x, Ga, acc);
+                xc.y = mma_point<MAXM, true>(a, vx.y, vlb.y, vub.y, vs.y, vg.y, Gb, acc);
             } else {
-                xc.x = ccsaq_point<MAXM, true>(a, vx.x, vlb.x, vub.x, vs.x, vg.x, Ga, nullptr, a.ld, acc);
-                xc.y = ccsaq_point<MAXM, true>(a, vx.y, vlb.y, vub.y, vs.y, vg.y, Gb, nullptr, a.ld, acc);
+                xc.x = ccsaq_point<MAXM, true>(a, vx.x, vlb.x, vub.x, vs.x, vg.x, Ga, acc);
+                xc.y = ccsaq_point<MAXM, true>(a, vx.y, vlb.y, vub.y, vs.y, vg.y, Gb, acc);
             }
             if (STORE) st_stream(reinterpret_cast<double2 *>(a.xcur) + p + sub * 32 + lane, xc);
         }
@@ -655,74 +755,239 @@ __global__ void __launch_bounds__(kTmaBlock, MINB) dual_eval_tma_kernel(const __
         }
         asm volatile("bar.sync 1, %0;" ::"r"(32 * kGroupWarps) : "memory");      // the 8 consumer warps only
         parity ^= 1;
-        if (sub != 0) continue;
-        if (lane < NV) {
-            double s = srec[lane];
+        if (sub == 0) put_group_record<NV>(srec, a.grouptags, ngroups, gl, a.tag, lane);
+    }
+}
+
+// ---- the dual evaluation kernel for any number of constraints (m > 16) ----------------------------------------
+// The reference has no cap on m (mma.c:173; loops :101-129).  With more rows than registers can hold, one sweep step
+// (one 512-variable chunk, two variables per thread) makes two passes over the m rows of the gradient block:
+//   pass A  rows in blocks of 8 (eight 128-bit loads in flight per thread): u, v of mma.c:101-106 (v of
+//           ccsa_quadratic.c:116-121) accumulated in row order, exactly the reference's chain;
+//   then    the closed-form minimiser, clamps, and the three row-independent sums, as in the register-row kernels;
+//   pass B  the same rows again -- they were read microseconds ago by this CTA, so they come from L1/L2, not from
+//           HBM: HBM traffic stays (5 + m) * 8 bytes per variable -- for the g_i terms (mma.c:126-129,
+//           ccsa_quadratic.c:139-140).
+// Reduction of the g_i terms (m accumulators do not fit in registers either): per row and chunk, a lane adds its two
+// terms, the warp reduces eight rows at a time with an exchange-and-halve butterfly (9 shuffles for 8 rows instead of
+// 40), and lane 4r of the warp adds the row's chunk total to the warp's running row sum in shared memory -- chunks in
+// index order.  Group record = the 8 warps' row sums in warp order; from there on the canonical fold tree.  The
+// multipliers, penalties and the "constraint switched off" flags (MMA, NaN value) come from a device block (a.wide)
+// staged in shared memory.  Deterministic, independent of the grid and of the number of ranks like every other path.
+constexpr int kWideRows = 8;              // rows per block
+
+// lane values t[0..8) of eight rows -> row r's warp total in lanes 4r .. 4r+3 (returned)
+__device__ __forceinline__ double reduce8_rows(double (&t)[kWideRows], int lane)
+{
+    const bool b4 = (lane & 16) != 0, b3 = (lane & 8) != 0, b2 = (lane & 4) != 0;
+    double q[4];
 #pragma unroll
-            for (int w = 1; w < kGroupWarps; ++w) s = addx(s, srec[w * NV + lane]);
-            a.grouprecs[(unsigned long long) gl * a.nvp + lane] = s;
-        }
-        __syncwarp();
-        const unsigned vs_local = gl / a.segs_per_vshard;
-        if (!warp_is_last(a.tickets + vs_local, a.segs_per_vshard, lane)) continue;
-        fold_shard_records<NV>(a.grouprecs + (unsigned long long) vs_local * a.segs_per_vshard * a.nvp, a.segs_per_vshard,
-                               a.nvp, lane, acc);
-        if (lane == 0) {
-            double *rec = a.vsums + (unsigned long long) vs_local * a.nvp;
+    for (int j = 0; j < 4; ++j) {         // xor 16: lanes with bit 4 clear keep rows 0-3, the others rows 4-7
+        const double send = b4 ? t[j] : t[j + 4];
+        const double keep = b4 ? t[j + 4] : t[j];
+        q[j] = addx(keep, __shfl_xor_sync(0xffffffffu, send, 16));
+    }
+    double h[2];
 #pragma unroll
-            for (int k = 0; k < NV; ++k) rec[k] = acc[k];
-        }
-        if (!warp_is_last(a.tickets + a.local_vshards, a.local_vshards, lane)) continue;
-        if (lane < NV) {
-            if (a.publish_host) {
-                double s = __ldcg(a.vsums + lane);
-                for (unsigned v = 1; v < a.local_vshards; ++v) s = addx(s, __ldcg(a.vsums + (unsigned long long) v * a.nvp + lane));
-                a.out_host[lane] = s;
-                __threadfence_system();
-            } else if (a.box[0] == nullptr) {
-                const unsigned v0 = a.seg0 / a.segs_per_vshard;
-                for (unsigned v = 0; v < a.local_vshards; ++v)
-                    a.out_dev[(unsigned long long) (v0 + v) * a.nvp + lane] = __ldcg(a.vsums + (unsigned long long) v * a.nvp + lane);
-            }
-        }
-        if (!a.publish_host && a.box[0] != nullptr) {
-            int timed_out = 0;
-            const double total = box_exchange(a.box, a.rank, a.world, a.seq, a.vsums, a.nvp, a.local_vshards,
-                                              a.seg0 / a.segs_per_vshard, NV, lane, &timed_out);
-            if (lane < NV) {
-                a.out_host[lane] = timed_out ? __longlong_as_double(0x7ff8000000000000ll) : total;
-                __threadfence_system();
-            }
-        }
+    for (int j = 0; j < 2; ++j) {         // xor 8: of its four rows a lane keeps the lower (bit 3 clear) or upper pair
+        const double send = b3 ? q[j] : q[j + 2];
+        const double keep = b3 ? q[j + 2] : q[j];
+        h[j] = addx(keep, __shfl_xor_sync(0xffffffffu, send, 8));
+    }
+    const double send = b2 ? h[0] : h[1]; // xor 4: one row left
+    const double keep = b2 ? h[1] : h[0];
+    double s = addx(keep, __shfl_xor_sync(0xffffffffu, send, 4));
+    s = addx(s, __shfl_xor_sync(0xffffffffu, s, 2));
+    s = addx(s, __shfl_xor_sync(0xffffffffu, s, 1));
+    return s;                             // row 4*b4 + 2*b3 + b2 = lane / 4
+}
+
+template <int VARIANT, bool STORE>
+__global__ void __launch_bounds__(kBlock, 2) dual_eval_wide_kernel(const __grid_constant__ DualArgs a)
+{
+    extern __shared__ __align__(16) double s_dyn[];           // y[m] | rhoc[m] | half_rhoc[m] | act[m] | wrow[8][mp]
+    const int m = a.m;
+    const int mp = (m + kWideRows - 1) / kWideRows * kWideRows;   // rows padded to whole blocks (padding rows: act = 0)
+    double *s_y = s_dyn, *s_rhoc = s_dyn + mp, *s_hrhoc = s_dyn + 2 * mp, *s_act = s_dyn + 3 * mp, *s_wrow = s_dyn + 4 * mp;
+    __shared__ double s_rec[kGroupWarps * 3];
+    const int lane = threadIdx.x & 31;
+    const int sub = threadIdx.x >> 5;
+    const unsigned ngroups = a.segs_per_vshard * a.local_vshards;
+    if (blockIdx.x == gridDim.x - 1) {
+        eval_folder<16>(a, 3 + m);
+        return;
+    }
+    for (int i = threadIdx.x; i < mp; i += kBlock) {
+        const bool in = i < m;
+        s_y[i] = in ? a.wide[i] : 0.0;
+        s_rhoc[i] = in ? a.wide[m + i] : 0.0;
+        s_hrhoc[i] = in ? a.wide[2 * m + i] : 0.0;
+        s_act[i] = in ? a.wide[3 * m + i] : 0.0;
+    }
+    __syncthreads();
+    const unsigned nslots = gridDim.x - 1;
+    const double2 *x2 = reinterpret_cast<const double2 *>(a.x);
+    const double2 *lb2 = reinterpret_cast<const double2 *>(a.lb);
+    const double2 *ub2 = reinterpret_cast<const double2 *>(a.ub);
+    const double2 *s2v = reinterpret_cast<const double2 *>(a.sigma);
+    const double2 *g2 = reinterpret_cast<const double2 *>(a.g);
+    double *wrow = s_wrow + (size_t) sub * mp;                // this warp's running row sums over the group
+
+    for (unsigned gl = blockIdx.x; gl < ngroups; gl += nslots) {
+        for (int i = lane; i < mp; i += 32) wrow[i] = 0.0;
         __syncwarp();
-        if (lane == 0) {
-            for (unsigned v = 0; v <= a.local_vshards; ++v) a.tickets[v] = 0;
-            if (a.publish_host || a.box[0] != nullptr) {
-                *a.flag_host = a.seq;
-                __threadfence_system();
+        unsigned long long p_lo, p_hi;
+        group_pairs(a.nchunks, a.nseg_total, a.chunk0, a.seg0 + gl, &p_lo, &p_hi);
+        double acc[3] = {0.0, 0.0, 0.0};
+        for (unsigned long long p = p_lo + sub * 32 + lane; p < p_hi; p += kChunkPairs) {
+            const double2 vx = ld_stream(x2 + p), vlb = ld_stream(lb2 + p), vub = ld_stream(ub2 + p), vs = ld_stream(s2v + p),
+                          vg = ld_stream(g2 + p);
+            const double2 *Gp = reinterpret_cast<const double2 *>(a.G) + p;
+            const unsigned long long ldp = a.ld / 2;          // row stride in double2
+            // ---- pass A: u, v ----
+            double ua = vg.x, ub_ = vg.y, va = 0.0, vb = 0.0;
+            double agsa = 0.0, agsb = 0.0;
+            if (VARIANT == 0) {
+                agsa = mulx(fabs(vg.x), vs.x); agsb = mulx(fabs(vg.y), vs.y);
+                va = addx(agsa, a.half_rho); vb = addx(agsb, a.half_rho);
+            }
+            for (int i0 = 0; i0 < mp; i0 += kWideRows) {
+                double2 Gi[kWideRows];
+#pragma unroll
+                for (int r = 0; r < kWideRows; ++r) Gi[r] = i0 + r < m ? __ldg(Gp + (unsigned long long) (i0 + r) * ldp) : make_double2(0.0, 0.0);
+#pragma unroll
+                for (int r = 0; r < kWideRows; ++r) {
+                    const int i = i0 + r;
+                    if (VARIANT == 0) {
+                        if (s_act[i] != 0.0) {
+                            const double yi = s_y[i], hr = s_hrhoc[i];
+                            ua = addx(ua, mulx(Gi[r].x, yi));
+                            ub_ = addx(ub_, mulx(Gi[r].y, yi));
+                            va = addx(va, mulx(addx(mulx(fabs(Gi[r].x), vs.x), hr), yi));
+                            vb = addx(vb, mulx(addx(mulx(fabs(Gi[r].y), vs.y), hr), yi));
+                        }
+                    } else if (i < m) {
+                        const double yi = s_y[i];
+                        ua = addx(ua, mulx(Gi[r].x, yi));
+                        ub_ = addx(ub_, mulx(Gi[r].y, yi));
+                    }
+                }
+            }
+            // ---- the minimiser and the row-independent sums (same expressions as mma_point / ccsaq_point) ----
+            double2 xc = vx;
+            double dxa = 0.0, dxb = 0.0;          // x*(y) - x
+            double fa = 0.0, fb = 0.0;            // MMA: s2 * dx ("c"), CCSAQ: dx^2 / (2 s2) ("q")
+            double da = 0.0, db = 0.0;            // MMA: dx^2 / (s2 - dx^2) numerator helper: dx2;  unused for CCSAQ
+            double ia = 0.0, ib = 0.0;            // MMA: 1 / (s2 - dx^2)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const double x = h ? vx.y : vx.x, lb = h ? vlb.y : vlb.x, ub = h ? vub.y : vub.x, s = h ? vs.y : vs.x,
+                             g = h ? vg.y : vg.x;
+                if (s == 0) continue;                         // fixed variable: no contribution anywhere
+                double xcj, dx;
+                if (VARIANT == 0) {
+                    double u = h ? ub_ : ua;
+                    const double v = h ? vb : va, ag_s = h ? agsb : agsa;
+                    const double s2 = mulx(s, s);
+                    u = mulx(u, s2);
+                    const double r = divx(u, mulx(v, s));
+                    dx = divx(divx(u, v), subx(-1.0, __dsqrt_rn(fabs(subx(1.0, mulx(r, r))))));
+                    xcj = addx(x, dx);
+                    if (xcj > ub) xcj = ub; else if (xcj < lb) xcj = lb;
+                    const double lim = mulx(0.9, s), hi = addx(x, lim), lo = subx(x, lim);
+                    if (xcj > hi) xcj = hi; else if (xcj < lo) xcj = lo;
+                    dx = subx(xcj, x);
+                    const double dx2 = mulx(dx, dx);
+                    const double dinv = divx(1.0, subx(s2, dx2));
+                    acc[0] = addx(acc[0], mulx(addx(mulx(u, dx), mulx(v, dx2)), dinv));
+                    const double c = mulx(s2, dx);
+                    acc[1] = addx(acc[1], mulx(addx(mulx(g, c), mulx(addx(ag_s, a.half_rho), dx2)), dinv));
+                    acc[2] = addx(acc[2], mulx(mulx(0.5, dx2), dinv));
+                    if (h) { fb = c; db = dx2; ib = dinv; } else { fa = c; da = dx2; ia = dinv; }
+                } else {
+                    const double v = h ? ub_ : ua;
+                    const double u = a.u_ccsaq;
+                    const double s2 = mulx(s, s);
+                    dx = divx(mulx(-s2, v), u);
+                    if (fabs(dx) > s) dx = copysign(s, dx);
+                    xcj = addx(x, dx);
+                    if (xcj > ub) xcj = ub; else if (xcj < lb) xcj = lb;
+                    dx = subx(xcj, x);
+                    const double dx2 = mulx(dx, dx);
+                    acc[0] = addx(acc[0], addx(mulx(v, dx), divx(mulx(mulx(0.5, u), dx2), s2)));
+                    const double q = divx(mulx(0.5, dx2), s2);
+                    acc[1] = addx(acc[1], addx(mulx(g, dx), mulx(a.rho, q)));
+                    acc[2] = addx(acc[2], q);
+                    if (h) fb = q; else fa = q;
+                }
+                if (h) { xc.y = xcj; dxb = dx; } else { xc.x = xcj; dxa = dx; }
+            }
+            if (STORE) st_stream(reinterpret_cast<double2 *>(a.xcur) + p, xc);
+            const bool on_a = vs.x != 0, on_b = vs.y != 0;
+            // ---- pass B: the g_i terms ----
+            for (int i0 = 0; i0 < mp; i0 += kWideRows) {
+                double2 Gi[kWideRows];
+#pragma unroll
+                for (int r = 0; r < kWideRows; ++r) Gi[r] = i0 + r < m ? __ldg(Gp + (unsigned long long) (i0 + r) * ldp) : make_double2(0.0, 0.0);
+                double t[kWideRows];
+#pragma unroll
+                for (int r = 0; r < kWideRows; ++r) {
+                    const int i = i0 + r;
+                    double ta = 0.0, tb = 0.0;
+                    if (VARIANT == 0) {
+                        if (s_act[i] != 0.0) {
+                            const double hr = s_hrhoc[i];
+                            if (on_a) ta = mulx(addx(mulx(Gi[r].x, fa), mulx(addx(mulx(fabs(Gi[r].x), vs.x), hr), da)), ia);
+                            if (on_b) tb = mulx(addx(mulx(Gi[r].y, fb), mulx(addx(mulx(fabs(Gi[r].y), vs.y), hr), db)), ib);
+                        }
+                    } else if (i < m) {
+                        const double rc = s_rhoc[i];
+                        if (on_a) ta = addx(mulx(Gi[r].x, dxa), mulx(rc, fa));
+                        if (on_b) tb = addx(mulx(Gi[r].y, dxb), mulx(rc, fb));
+                    }
+                    t[r] = addx(ta, tb);
+                }
+                const double s = reduce8_rows(t, lane);
+                if ((lane & 3) == 0) {
+                    const int i = i0 + (lane >> 2);
+                    wrow[i] = addx(wrow[i], s);
+                }
             }
         }
+        // ---- group record: sums 0..2 like the register-row kernels, sums 3.. from the warps' row sums ----
+        warp_fold<3>(acc);
+        if (lane == 0) { s_rec[sub * 3] = acc[0]; s_rec[sub * 3 + 1] = acc[1]; s_rec[sub * 3 + 2] = acc[2]; }
+        __syncthreads();
+        const unsigned long long tag = a.tag;
+        for (int k = threadIdx.x; k < 3 + m; k += kBlock) {
+            double s;
+            if (k < 3) {
+                s = s_rec[k];
+                for (int w = 1; w < kGroupWarps; ++w) s = addx(s, s_rec[w * 3 + k]);
+            } else {
+                s = s_wrow[k - 3];
+                for (int w = 1; w < kGroupWarps; ++w) s = addx(s, s_wrow[(size_t) w * mp + k - 3]);
+            }
+            slot_put(a.grouptags + 2ull * ((unsigned long long) k * ngroups + gl), s, tag);
+        }
+        __syncthreads();                          // the row sums are re-zeroed at the top of the next group
     }
 }
 
 // ---- the persistent dual-SOLVE kernel: one launch per dual solve ------------------------------------------
-//   The m-dimensional dual optimiser (DualMachine, dual_mma.hpp -- the same code the
-// host runs) moves into the kernel: all CTAs stay resident (cooperative launch) and walk *generations*.
-// Generation g = one dual evaluation at the trial multipliers y_g.
+//   The m-dimensional dual optimiser moves into the kernel: all CTAs stay resident
+// (cooperative launch) and walk *generations*.  Generation g = one dual evaluation at the trial multipliers y_g.
 //
 //   sweeper CTAs (all but the last): claim groups from a monotonic counter (claim c -> generation
 //     c / ngroups + 1, group c % ngroups), sweep them exactly like dual_eval_kernel (same warp records,
-//     same group records => same bits) and drop each group record into a *tagged* 16-byte slot
-//     {value, tag(launch, generation)} with one 128-bit store.  No fence, no ticket, no atomic on the
-//     record path: the timeline of the previous (ticket) design showed warp 0 of every CTA spending
-//     ~4.6 us per group in fence + atomic + fence under full memory load while its seven sibling warps
-//     waited at the next slot barrier (profiles/r01_trace_summary_ticket_design.txt).
-//   the folder CTA (the last one): warp v polls the P slots of local virtual shard v in index order
-//     (lane l takes records l, l+32, ...; then the xor butterfly -- the fold tree of dual_eval_kernel),
-//     one CTA barrier hands the <= 8 shard sums to warp 0, which exchanges them over the NVLink mailbox
-//     when there are several ranks, feeds F and grad F to the DualMachine held in ITS shared memory,
-//     and publishes y_{g+1} as tagged slots the sweepers poll (again no fence: a slot is valid iff its
-//     tag is the awaited generation).
+//     same group records => same bits) and drop each group record into its tagged slots.  A sweeper that runs
+//     out of work in generation g claims a group of generation g + 1 and ISSUES ITS FIRST OPERAND LOADS before it
+//     starts to poll for y_{g+1} (the loads do not depend on y): the serial part of a generation -- last record,
+//     fold, exchange, optimiser step, publication -- overlaps with (5+m) x 4 KB x #CTAs of HBM traffic.
+//   the folder CTA (the last one): fold_generation, then warp 0 exchanges the shard sums over the NVLink mailbox
+//     when there are several ranks, feeds F and grad F to the WarpDualMachine held in ITS registers (lane i owns
+//     multiplier i), and publishes y_{g+1} as tagged slots the sweepers poll (again no fence: a slot is valid iff
+//     its tag is the awaited generation).
 // Versus one launch per evaluation this removes launch latency, the PCIe result hop and the host turn-
 // around from every evaluation; the host sees one launch and one result per dual solve.
 //
@@ -732,16 +997,150 @@ __global__ void __launch_bounds__(kTmaBlock, MINB) dual_eval_tma_kernel(const __
 // of per-group sweep times.  Row 0 holds the CTA start times.  All in %globaltimer nanoseconds.
 #ifdef NB200_TRACE
 constexpr int kTraceGens = 512;
-__device__ __forceinline__ unsigned long long nb_gtime()
-{
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    return t;
-}
 #define NB_TR(...) __VA_ARGS__
 #else
 #define NB_TR(...)
 #endif
+
+// The dual optimiser of dual_mma.hpp (DualMachine: mma.c:145-452 with m' = 0 constraints, and its level-3 step
+// mma.c:59-137), restated for one warp: lane i < m owns y_i, g_i, sigma_i, ...; the scalars are replicated in every
+// lane and every lane executes the same scalar control flow.  Sums over i are taken in index order through shuffles,
+// so every operation and its order are those of the host machine: the two produce the same bits
+// (tests/test_gpu_parity.py::test_fused_solve_equals_host_driven).
+struct WarpDualMachine {
+    double y, g, sigma, ycur, yprev, yprevprev, lo, hi;          // lane i: element i (lanes >= m: sigma = 0)
+    double rho, fbase, fmin, fcur, fprev, gval, wval;
+    unsigned k;
+    long nevals;
+    int awaiting_first, ret, m;
+    DualStop st;
+
+    __device__ __forceinline__ int start(int m_, double y0, double lo_, double hi_, const DualStop &stop, int lane)
+    {
+        m = m_;
+        st = stop;
+        nevals = 0;
+        k = 0;
+        const bool in = lane < m;
+        y = in ? y0 : 0.0; lo = in ? lo_ : 0.0; hi = in ? hi_ : 0.0;
+        const bool bad = in && (lo > hi || y < lo || y > hi);                        // optimize.c:547-551
+        ret = __any_sync(0xffffffffu, bad) ? kRetInvalid : kRetSuccess;
+        sigma = !in ? 0.0 : ((nl_isinf(hi) || nl_isinf(lo)) ? 1.0 : mulx(0.5, subx(hi, lo)));   // mma.c:202-210
+        g = ycur = yprev = yprevprev = 0.0;
+        rho = 1.0;
+        fbase = fmin = fcur = fprev = gval = wval = 0.0;
+        awaiting_first = 1;
+        return ret;
+    }
+
+    __device__ __forceinline__ double trial() const { return awaiting_first ? y : ycur; }
+
+    __device__ __forceinline__ bool limits_hit(bool time_up)
+    {
+        if (st.maxeval > 0 && nevals >= st.maxeval) ret = kRetMaxeval;
+        else if (time_up) ret = kRetMaxtime;
+        return ret != kRetSuccess;
+    }
+    __device__ __forceinline__ bool outer_top(bool time_up)          // mma.c:255-265
+    {
+        fprev = fcur;
+        if (limits_hit(time_up)) return true;
+        if (++k > 1) yprevprev = yprev;
+        yprev = ycur;
+        return false;
+    }
+    __device__ __forceinline__ bool x_converged(int lane) const     // stop.c:98-108, unit weights, uniform xtol_abs
+    {
+        const double d = fabs(subx(ycur, yprev)), a = fabs(ycur);
+        double dn = 0.0, xn = 0.0;
+        for (int i = 0; i < m; ++i) dn = addx(dn, __shfl_sync(0xffffffffu, d, i));
+        for (int i = 0; i < m; ++i) xn = addx(xn, __shfl_sync(0xffffffffu, a, i));
+        if (dn < mulx(st.xtol_rel, xn)) return true;
+        return !__any_sync(0xffffffffu, lane < m && d >= st.xtol_abs);
+    }
+    __device__ __forceinline__ bool outer_end(int lane)              // mma.c:418-446
+    {
+        if (rel_stop(fprev, fcur, st.ftol_rel, st.ftol_abs)) ret = kRetFtol;
+        if (x_converged(lane)) ret = kRetXtol;
+        if (ret != kRetSuccess) return true;
+        rho = mulx(0.1, rho) > 1e-5 ? mulx(0.1, rho) : 1e-5;
+        if (k > 1 && lane < m) {
+            const double osc = mulx(subx(ycur, yprev), subx(yprev, yprevprev));
+            double s = mulx(sigma, osc < 0 ? 0.7 : (osc > 0 ? 1.2 : 1.0));
+            if (!nl_isinf(hi) && !nl_isinf(lo)) {
+                const double top = mulx(10.0, subx(hi, lo)), bot = mulx(0.01, subx(hi, lo));
+                s = s < top ? s : top;
+                s = s > bot ? s : bot;
+            }
+            sigma = s > 0.0 ? s : 0.0;                    // sigma_min = 0
+        }
+        return false;
+    }
+
+    // Feed F(trial()) and this lane's gradient component; `time_up`: the (rank-agreed) time limit has expired.
+    // Returns true when finished (code in ret, multipliers in y).
+    __device__ __forceinline__ bool feed_pre(double F, double grad, bool time_up, int lane)
+    {
+        if (awaiting_first) {                            // mma.c:218
+            awaiting_first = 0;
+            g = grad; ycur = y;
+            fbase = fmin = fcur = F;
+            nevals = 1;
+            return outer_top(time_up);
+        }
+        fcur = F;                                        // mma.c:297
+        ++nevals;
+        const bool inner_done = gval >= fcur;            // mma.c:304
+        if (fcur < fmin) {                               // mma.c:334 with m' = 0: always "feasible"
+            fbase = fmin = fcur;
+            y = ycur; g = grad;
+        }
+        if (limits_hit(time_up)) return true;
+        if (inner_done) {
+            if (outer_end(lane)) return true;
+            if (outer_top(time_up)) return true;
+        } else if (fcur > gval) {                        // mma.c:403-404
+            const double a = mulx(10.0, rho), b = mulx(1.1, addx(rho, divx(subx(fcur, gval), wval)));
+            rho = a < b ? a : b;
+        }
+        return false;
+    }
+
+    // The MMA dual evaluation with zero constraints on the m dual variables (mma.c:59-137, m = 0): the next trial
+    // point ycur and the approximant's gval / wval.
+    __device__ __forceinline__ void step(int lane)
+    {
+        const double s = sigma;
+        const bool has = lane < m && s != 0;
+        double gt = 0.0, wt = 0.0;
+        if (lane < m && s == 0) ycur = y;
+        if (has) {
+            double u = g;
+            const double v = addx(mulx(fabs(g), s), mulx(0.5, rho));
+            const double s2 = mulx(s, s);
+            u = mulx(u, s2);
+            const double r = divx(u, mulx(v, s));
+            double dy = divx(divx(u, v), subx(-1.0, __dsqrt_rn(fabs(subx(1.0, mulx(r, r))))));
+            double yc = addx(y, dy);
+            if (yc > hi) yc = hi;
+            else if (yc < lo) yc = lo;
+            if (yc > addx(y, mulx(0.9, s))) yc = addx(y, mulx(0.9, s));
+            else if (yc < subx(y, mulx(0.9, s))) yc = subx(y, mulx(0.9, s));
+            ycur = yc;
+            dy = subx(yc, y);
+            const double dy2 = mulx(dy, dy), dinv = divx(1.0, subx(s2, dy2)), c = mulx(s2, dy);
+            gt = mulx(addx(mulx(g, c), mulx(addx(mulx(fabs(g), s), mulx(0.5, rho)), dy2)), dinv);
+            wt = mulx(mulx(0.5, dy2), dinv);
+        }
+        double gs = fbase, ws = 0.0;                      // mma.c:123-125: the terms added in index order
+        for (int i = 0; i < m; ++i) {
+            const double gi = __shfl_sync(0xffffffffu, gt, i), wi = __shfl_sync(0xffffffffu, wt, i);
+            if (__shfl_sync(0xffffffffu, (int) has, i)) { gs = addx(gs, gi); ws = addx(ws, wi); }
+        }
+        gval = gs;
+        wval = ws;
+    }
+};
 
 constexpr int kPubSlots = kMaxParamM + 2;     // y_i | u_ccsaq | flags
 struct SolveState {                       // device global; the head is zeroed by the host before every launch
@@ -755,7 +1154,6 @@ struct SolveState {                       // device global; the head is zeroed b
 struct SolveArgs {
     DualArgs d;                           // arrays, geometry, workspace, exchange boxes (d.y: the warm start)
     SolveState *st;
-    double *grouptags;                    // [nvp][local groups] tagged slots {value, tag}
     unsigned long long tag0;              // launch id << 40; generation g carries tag0 | g
     double fval;                          // objective value at x
     double cval[kMaxParamM];              // constraint values with switched-off ones zeroed (mma.c:78)
@@ -764,12 +1162,14 @@ struct SolveArgs {
     volatile double *res_host;            // mapped pinned: raw sums [24] | y [32] | nevals | ret | generations
     NB_TR(unsigned long long *trace;)
 };
+constexpr int kResY = 24, kResCounts = 24 + 32;
 
 struct SharedMultipliers {                // what the point functions read in the solve kernel
     const double *y, *rhoc, *half_rhoc;   // y in shared memory; penalties from the parameter block
     double rho, half_rho, u_ccsaq;
     unsigned active;
-    int m, cons0, cons_n;
+    int m;
+    __device__ __forceinline__ double u() const { return u_ccsaq; }
 };
 
 // The folder CTA's loop (kept out of line so that its registers do not weigh on the sweep loop).
@@ -782,140 +1182,82 @@ __device__ __noinline__ void solve_folder(const SolveArgs &sa)
     const int sub = threadIdx.x >> 5;
     const unsigned ngroups = a.segs_per_vshard * a.local_vshards;
     __shared__ int s_exit;
-    __shared__ DualMachine s_mach;
-    __shared__ double s_grad[kMaxParamM];
     __shared__ double s_vs[kVirtualShards * NV];      // the shard sums of the generation in flight
     __shared__ double s_w[kVirtualShards * kGroupWarps * NV];     // per shard: the 8 fold-warp results
-    __shared__ double s_gt[kMaxParamM], s_wt[kMaxParamM];
-    __shared__ int s_has[kMaxParamM];
-    // ================================ the folder CTA ================================
+    WarpDualMachine mach;                             // meaningful in warp 0 only
     int final_pass = 0;
-    if (threadIdx.x == 0) {
-        s_exit = 0;
-        const int rc = s_mach.start(a.m, a.y, sa.lo, sa.hi, sa.stop);      // d.y carries the warm start
+    const unsigned long long t_start = nb_globaltimer();
+    if (threadIdx.x == 0) s_exit = 0;
+    if (sub == 0) {
+        const double y0 = lane < a.m ? a.y[lane] : 0.0, lo = lane < a.m ? sa.lo[lane] : 0.0, hi = lane < a.m ? sa.hi[lane] : 0.0;
+        const int rc = mach.start(a.m, y0, lo, hi, sa.stop, lane);       // d.y carries the warm start
         if (rc != kRetSuccess) {          // start point outside the box: report, publish nothing
-            sa.res_host[24 + kMaxParamM + 1] = (double) rc;
-            __threadfence_system();
-            *a.flag_host = a.seq;
-            __threadfence_system();
-            *reinterpret_cast<volatile int *>(&st->done) = 1;
-            s_exit = 1;
+            if (lane == 0) {
+                sa.res_host[kResCounts + 1] = (double) rc;
+                __threadfence_system();
+                *a.flag_host = a.seq;
+                __threadfence_system();
+                *reinterpret_cast<volatile int *>(&st->done) = 1;
+                s_exit = 1;
+            }
         } else {
             double u = a.rho;
-            for (int i = 0; i < a.m; ++i) u = addx(u, mulx(a.rhoc[i], s_mach.y[i]));
-            NB_TR(sa.trace[16] = nb_gtime();)
-            for (int i = 0; i < a.m; ++i) slot_put(st->pub + 2 * i, s_mach.y[i], sa.tag0 | 1ull);
-            slot_put(st->pub + 2 * kMaxParamM, u, sa.tag0 | 1ull);
-            slot_put(st->pub + 2 * (kMaxParamM + 1), __longlong_as_double(0ll), sa.tag0 | 1ull);
+            for (int i = 0; i < a.m; ++i) u = addx(u, mulx(a.rhoc[i], __shfl_sync(0xffffffffu, mach.y, i)));
+            NB_TR(if (lane == 0) sa.trace[16] = nb_globaltimer();)
+            if (lane < a.m) slot_put(st->pub + 2 * lane, mach.y, sa.tag0 | 1ull);
+            if (lane == 0) {
+                slot_put(st->pub + 2 * kMaxParamM, u, sa.tag0 | 1ull);
+                slot_put(st->pub + 2 * (kMaxParamM + 1), __longlong_as_double(0ll), sa.tag0 | 1ull);
+            }
         }
     }
-    for (int i = threadIdx.x; i < kVirtualShards * kGroupWarps * NV; i += 32 * kGroupWarps) s_w[i] = 0.0;
-    const unsigned fw_all = (a.segs_per_vshard + 31u) / 32u;
-    const unsigned fw_per = fw_all < (unsigned) kGroupWarps ? fw_all : (unsigned) kGroupWarps;      // non-empty fold warps per shard
-    const unsigned nitems = a.local_vshards * fw_per;
-    __syncthreads();
+    fold_init<NV>(s_w);
     if (s_exit) return;
-    const long long t_start = clock64();
     for (unsigned long long gen = 1;; ++gen) {
         const unsigned long long tag = sa.tag0 | gen;
-        // ---- shard sums, canonical order (see fold_shard_records).  Work item (v, w) = fold warp w of local
-        // shard v: chains t = 32 w + lane over records t, t + 256, ...  Items are dealt round-robin to the 8
-        // physical warps in (v, w) order -- shards complete roughly in index order, and when P <= 32 (small n, or
-        // one shard per rank with 8 GPUs) all shards are polled side by side.  Empty fold warps contribute the
-        // +0.0 parked in s_w at start-up.
-        for (unsigned item = sub; item < nitems; item += kGroupWarps) {
-            const unsigned v = item / fw_per, w = item % fw_per;
-            double acc[NV];
-#pragma unroll
-            for (int k = 0; k < NV; ++k) acc[k] = 0.0;
-            // slot (group gl, sum k) lives at [k][gl]: the 32 lanes of a poll read 512 contiguous bytes
-            const double *base = sa.grouptags + 2ull * (unsigned long long) v * a.segs_per_vshard;
-            // warp-uniform control flow: a warp polls until all of its lanes have their record (measured: a warp
-            // whose lanes left the poll loop at different times took ~9 us per shard instead of < 1 us)
-            for (unsigned r0 = 32u * w; r0 < a.segs_per_vshard; r0 += 32 * kGroupWarps) {
-                const unsigned r = r0 + lane;
-                const bool has = r < a.segs_per_vshard;
-                const double *rec = base + 2ull * (has ? r : 0u);
-                double val[NV];
-                for (;;) {                // the NV slots of a record are fetched together: one round trip per poll
-                    bool all = true;
-#pragma unroll
-                    for (int k = 0; k < NV; ++k) all = slot_peek(rec + 2ull * k * ngroups, tag, &val[k]) && all;
-                    if (__all_sync(0xffffffffu, all || !has)) break;
-                    __nanosleep(20);
-                }
-                if (has) {
-#pragma unroll
-                    for (int k = 0; k < NV; ++k) acc[k] = addx(acc[k], val[k]);
-                }
-            }
-            warp_fold<NV>(acc);
-            if (lane == 0) {
-#pragma unroll
-                for (int k = 0; k < NV; ++k) s_w[(v * kGroupWarps + w) * NV + k] = acc[k];
-            }
-        }
-        NB_TR(if (threadIdx.x == 0 && gen < kTraceGens) sa.trace[16 * gen + 14] = nb_gtime();)
-        __syncthreads();
-        if (sub == 0 && lane < NV) {
-            for (unsigned v = 0; v < a.local_vshards; ++v) {
-                double t = s_w[(v * kGroupWarps) * NV + lane];
-#pragma unroll
-                for (int w = 1; w < kGroupWarps; ++w) t = addx(t, s_w[(v * kGroupWarps + w) * NV + lane]);
-                s_vs[v * NV + lane] = t;
-            }
-        }
-        __syncwarp();
+        fold_generation<NV>(a.grouptags, ngroups, a.segs_per_vshard, a.local_vshards, tag, 0, NV, s_w, s_vs);
         // ---- warp 0: totals (exchange if sharded), the dual optimiser's turn, publication ----
         if (sub == 0) {
-            NB_TR(if (lane == 0 && gen < kTraceGens) sa.trace[16 * gen + 5] = nb_gtime();)
+            NB_TR(if (lane == 0 && gen < kTraceGens) sa.trace[16 * gen + 5] = nb_globaltimer();)
             double total = 0.0;               // lane k < NV holds sum k
             int timed_out = 0;
+            // the time limit: a rank-local clock test, made collective by the exchange (see box_exchange)
+            int time_up = sa.stop.maxtime > 0 && (double) (nb_globaltimer() - t_start) * 1e-9 >= sa.stop.maxtime;
             if (a.box[0] == nullptr) {
                 if (lane < NV) {
                     total = s_vs[lane];
                     for (unsigned v = 1; v < a.local_vshards; ++v) total = addx(total, s_vs[v * NV + lane]);
                 }
             } else {
-                total = box_exchange<true>(a.box, a.rank, a.world, a.seq + gen, s_vs, NV, a.local_vshards,
-                                           a.seg0 / a.segs_per_vshard, NV, lane, &timed_out);     // one tag per generation
+                total = box_exchange(a.box, a.rank, a.world, a.seq + gen, s_vs, NV, a.local_vshards,
+                                     a.seg0 / a.segs_per_vshard, NV, lane, time_up ? 1.0 : 0.0, &time_up, &timed_out);     // one tag per generation
             }
-            NB_TR(if (lane == 0 && gen < kTraceGens) sa.trace[16 * gen + 6] = nb_gtime();)
+            NB_TR(if (lane == 0 && gen < kTraceGens) sa.trace[16 * gen + 6] = nb_globaltimer();)
             // F and grad F from the sums, constants added in the reference's order (mma.c:75-78, :135)
             int finished = 0, next_final = 0;
             if (!final_pass) {
-                if (lane >= 3 && lane < 3 + a.m) s_grad[lane - 3] = -addx(sa.cval[lane - 3], total);   // -g_i(y)
-                const double sum0 = __shfl_sync(0xffffffffu, total, 0);
-                __syncwarp();
-                if (lane == 0) {
-                    const double *yt = s_mach.trial();
-                    double val = sa.fval;
-                    for (int i = 0; i < a.m; ++i) val = addx(val, mulx(yt[i], sa.cval[i]));
-                    val = addx(val, sum0);
-                    const double elapsed = (double) (clock64() - t_start) * 5e-10;     // ~2 GHz; only feeds maxtime
-                    finished = timed_out ? 1 : (s_mach.feed_pre(-val, s_grad, elapsed) ? 1 : 0);
-                    if (timed_out) s_mach.ret = kRetFailure;
-                }
-                finished = __shfl_sync(0xffffffffu, finished, 0);
-                if (!finished) {          // the m terms of the next trial point side by side (divisions, square root)
-                    __syncwarp();
-                    if (lane < a.m) s_has[lane] = s_mach.step_term(lane, &s_gt[lane], &s_wt[lane]) ? 1 : 0;
-                    __syncwarp();
-                    if (lane == 0) s_mach.step_sum(s_gt, s_wt, s_has);
-                    __syncwarp();
-                }
+                const double yt = mach.trial();
+                const double cv = lane < a.m ? sa.cval[lane] : 0.0;
+                const double gsum = __shfl_sync(0xffffffffu, total, (lane + 3) & 31);      // lane i < m: sum 3 + i
+                const double grad = lane < a.m ? -addx(cv, gsum) : 0.0;                     // -g_i(y)
+                double val = sa.fval;
+                for (int i = 0; i < a.m; ++i)
+                    val = addx(val, mulx(__shfl_sync(0xffffffffu, yt, i), __shfl_sync(0xffffffffu, cv, i)));
+                val = addx(val, __shfl_sync(0xffffffffu, total, 0));
+                finished = timed_out ? 1 : (mach.feed_pre(-val, grad, time_up != 0, lane) ? 1 : 0);
+                if (timed_out) mach.ret = kRetFailure;
+                if (!finished) mach.step(lane);
                 if (finished && !timed_out) next_final = 1;          // one more pass at the solution, storing x*(y)
             }
-            __syncwarp();
-            NB_TR(if (lane == 0 && gen < kTraceGens) sa.trace[16 * gen + 7] = nb_gtime();)
+            NB_TR(if (lane == 0 && gen < kTraceGens) sa.trace[16 * gen + 7] = nb_globaltimer();)
             if (final_pass || timed_out) {
                 // publish the result of the solve: raw sums of the final pass, multipliers, counts
                 if (lane < NV) sa.res_host[lane] = total;
-                if (lane < a.m) sa.res_host[24 + lane] = s_mach.y[lane];
+                if (lane < a.m) sa.res_host[kResY + lane] = mach.y;
                 if (lane == 0) {
-                    sa.res_host[24 + kMaxParamM] = (double) s_mach.nevals;
-                    sa.res_host[24 + kMaxParamM + 1] = (double) s_mach.ret;
-                    sa.res_host[24 + kMaxParamM + 2] = (double) gen;
+                    sa.res_host[kResCounts] = (double) mach.nevals;
+                    sa.res_host[kResCounts + 1] = (double) mach.ret;
+                    sa.res_host[kResCounts + 2] = (double) gen;
                 }
                 __threadfence_system();
                 __syncwarp();
@@ -927,26 +1269,25 @@ __device__ __noinline__ void solve_folder(const SolveArgs &sa)
                 }
             } else {
                 // publish generation gen + 1
-                const double *trial = next_final ? s_mach.y : s_mach.ycur;
+                const double trial = next_final ? mach.y : mach.ycur;
                 const unsigned long long ntag = sa.tag0 | (gen + 1);
-                NB_TR(if (lane == 0 && gen + 1 < kTraceGens) sa.trace[16 * (gen + 1)] = nb_gtime();)
-                if (lane < a.m) slot_put(st->pub + 2 * lane, trial[lane], ntag);
+                double u = a.rho;
+                for (int i = 0; i < a.m; ++i) u = addx(u, mulx(a.rhoc[i], __shfl_sync(0xffffffffu, trial, i)));
+                NB_TR(if (lane == 0 && gen + 1 < kTraceGens) sa.trace[16 * (gen + 1)] = nb_globaltimer();)
+                if (lane < a.m) slot_put(st->pub + 2 * lane, trial, ntag);
                 if (lane == 0) {
-                    double u = a.rho;
-                    for (int i = 0; i < a.m; ++i) u = addx(u, mulx(a.rhoc[i], trial[i]));
                     slot_put(st->pub + 2 * kMaxParamM, u, ntag);
                     slot_put(st->pub + 2 * (kMaxParamM + 1), __longlong_as_double((long long) next_final), ntag);
                 }
                 final_pass = next_final;
             }
-            final_pass = __shfl_sync(0xffffffffu, final_pass, 0);
         }
-        __syncthreads();
+        fold_barrier();
         if (s_exit) return;
     }
 }
 
-template <int VARIANT, int MAXM, bool FULL, int BLOCK, int UNROLL, int MINB>
+template <int VARIANT, int MAXM, bool FULL, bool POL, int BLOCK, int UNROLL, int MINB>
 __global__ void __launch_bounds__(BLOCK, MINB) dual_solve_kernel(const __grid_constant__ SolveArgs sa)
 {
     constexpr int MR = MAXM > 0 ? MAXM : 1;
@@ -970,9 +1311,12 @@ __global__ void __launch_bounds__(BLOCK, MINB) dual_solve_kernel(const __grid_co
 
     // ================================ sweeper CTAs ================================
     unsigned long long next_c = 0;
-    if (threadIdx.x == 0) { s_exit = 0; s_claim[0] = atomicAdd(&st->claim, 1ull); }
-    NB_TR(if (threadIdx.x == 0) { const unsigned long long t = nb_gtime(); atomicMax(&sa.trace[1], ~t); atomicMax(&sa.trace[2], t); })
+    if (threadIdx.x == 0) { s_exit = 0; s_store = 0; s_claim[0] = atomicAdd(&st->claim, 1ull); }
+    NB_TR(if (threadIdx.x == 0) { const unsigned long long t = nb_globaltimer(); atomicMax(&sa.trace[1], ~t); atomicMax(&sa.trace[2], t); })
     __syncthreads();
+
+    L2Policies pol;
+    pol.init(a.l2_keep);
 
     int parity = 0;
     unsigned long long my_gen = 0;        // generation whose multipliers are in s_y
@@ -982,6 +1326,8 @@ __global__ void __launch_bounds__(BLOCK, MINB) dual_solve_kernel(const __grid_co
         const unsigned gl = (unsigned) (c % ngroups);
         // wait until generation `want` is published (or the solve has finished); refresh the multipliers
         if (want != my_gen) {
+            // ... with the head of the group on its way from HBM to the L2 meanwhile
+            if (threadIdx.x == 32 && a.prefetch_chunks) prefetch_group_head(a, gl, a.prefetch_chunks);
             if (sub == 0) {                   // warp 0 polls, warp-uniformly: lane i < m: y_i, lane m: u, the others: flags
                 const int slot = lane < a.m ? lane : (lane == a.m ? kMaxParamM : kMaxParamM + 1);
                 const unsigned long long tag = sa.tag0 | want;
@@ -1003,7 +1349,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) dual_solve_kernel(const __grid_co
             }
             __syncthreads();
             if (s_exit) return;
-            NB_TR(if (threadIdx.x == 0 && want < kTraceGens) { const unsigned long long t = nb_gtime();
+            NB_TR(if (threadIdx.x == 0 && want < kTraceGens) { const unsigned long long t = nb_globaltimer();
                       atomicMax(&sa.trace[16 * want + 1], ~t); atomicMax(&sa.trace[16 * want + 2], t); })
             my_gen = want;
         }
@@ -1011,14 +1357,14 @@ __global__ void __launch_bounds__(BLOCK, MINB) dual_solve_kernel(const __grid_co
         if (threadIdx.x == 0) next_c = atomicAdd(&st->claim, 1ull);
 
         SharedMultipliers mu;
-        mu.y = s_y; mu.rhoc = a.rhoc; mu.half_rhoc = a.half_rhoc;
-        mu.rho = a.rho; mu.half_rho = a.half_rho; mu.u_ccsaq = s_u;
-        mu.active = a.active; mu.m = a.m; mu.cons0 = 0; mu.cons_n = a.m;
+        mu.y = s_y; mu.rhoc = a.rhoc; mu.half_rhoc = a.half_rhoc; mu.u_ccsaq = s_u;
+        mu.rho = a.rho; mu.half_rho = a.half_rho;
+        mu.active = a.active; mu.m = a.m;
         double acc[NV];
 #pragma unroll
         for (int k = 0; k < NV; ++k) acc[k] = 0.0;
-        NB_TR(const unsigned long long tr_s0 = nb_gtime();)
-        sweep_group<VARIANT, MAXM, FULL, UNROLL>(a, mu, s_store != 0, gl, sub, lane, acc);
+        NB_TR(const unsigned long long tr_s0 = nb_globaltimer();)
+        sweep_group<VARIANT, MAXM, FULL, UNROLL, POL>(a, mu, pol, s_store != 0, gl, sub, lane, acc);
 
         warp_fold<NV>(acc);
         double *srec = s_rec[parity];
@@ -1029,13 +1375,8 @@ __global__ void __launch_bounds__(BLOCK, MINB) dual_solve_kernel(const __grid_co
         if (threadIdx.x == 0) s_claim[(it + 1) & 1] = next_c;
         __syncthreads();
         parity ^= 1;
-        if (sub == 0 && lane < NV) {
-            double s = srec[lane];
-#pragma unroll
-            for (int w = 1; w < kGroupWarps; ++w) s = addx(s, srec[w * NV + lane]);
-            slot_put(sa.grouptags + 2ull * ((unsigned long long) lane * ngroups + gl), s, sa.tag0 | my_gen);
-        }
-        NB_TR(if (sub == 0 && lane == 0 && my_gen < kTraceGens) { const unsigned long long t = nb_gtime(); unsigned long long *r = sa.trace + 16 * my_gen;
+        if (sub == 0) put_group_record<NV>(srec, a.grouptags, ngroups, gl, sa.tag0 | my_gen, lane);
+        NB_TR(if (sub == 0 && lane == 0 && my_gen < kTraceGens) { const unsigned long long t = nb_globaltimer(); unsigned long long *r = sa.trace + 16 * my_gen;
                   atomicMax(r + 3, ~t); atomicMax(r + 4, t); atomicAdd(r + 8, t - tr_s0); atomicAdd(r + 9, 1ull); })
     }
 }
@@ -1065,17 +1406,61 @@ __global__ void __launch_bounds__(kBlock) penalty_axpy_kernel(double *__restrict
 __global__ void publish_kernel(const double *all_vsums /* [8][nvp] */, int nv, int nvp, volatile double *out_host,
                                volatile unsigned long long *flag_host, unsigned long long seq)
 {
-    if (threadIdx.x < nv) {
-        double s = all_vsums[threadIdx.x];
-        for (int v = 1; v < kVirtualShards; ++v) s = addx(s, all_vsums[v * nvp + threadIdx.x]);
-        out_host[threadIdx.x] = s;
-        __threadfence_system();
+    for (int k = threadIdx.x; k < nv; k += blockDim.x) {      // one CTA
+        double s = all_vsums[k];
+        for (int v = 1; v < kVirtualShards; ++v) s = addx(s, all_vsums[v * nvp + k]);
+        out_host[k] = s;
     }
+    __threadfence_system();
     __syncthreads();
     if (threadIdx.x == 0) {
         *flag_host = seq;
         __threadfence_system();
     }
+}
+
+// ---- one-element halo of the shard for stencil device callbacks (include/nlopt_b200.h: nlopt_b200_dfunc2, halo = 1) ----
+// Mailbox form: lane 0 hands this rank's first element to the left neighbour (its right halo cell), lane 1 the last
+// element to the right neighbour (its left halo cell), as tagged 128-bit peer stores into slots 20 / 21 of virtual-shard
+// record 0 (slots 0..19 carry the dual sums and the time flag); then each lane polls the cell it is owed.
+constexpr int kBoxHaloLeft = 20, kBoxHaloRight = 21;
+struct HaloArgs {
+    double *x;                    // shard start; cells x[-1] and x[n_pad] are the halo
+    unsigned long long n_local;   // > 0
+    unsigned long long right_cell;    // index of the right halo cell (n_local when the shard fills its padded length)
+    double *box[8];
+    int rank, world;
+    unsigned long long seq;
+};
+__global__ void halo_exchange_kernel(const __grid_constant__ HaloArgs a)
+{
+    const int lane = threadIdx.x;
+    const int buf = (int) (a.seq & 1ull);
+    const bool left = a.rank > 0, right = a.rank + 1 < a.world;
+    if (lane == 0 && left)
+        box_put(a.box[a.rank - 1] + 2ull * ((unsigned long long) buf * 8 * kBoxStride + kBoxHaloRight), a.x[0], a.seq);
+    if (lane == 1 && right)
+        box_put(a.box[a.rank + 1] + 2ull * ((unsigned long long) buf * 8 * kBoxStride + kBoxHaloLeft), a.x[a.n_local - 1], a.seq);
+    if ((lane == 0 && left) || (lane == 1 && right)) {
+        const double *mine = a.box[a.rank] + 2ull * ((unsigned long long) buf * 8 * kBoxStride + (lane == 0 ? kBoxHaloLeft : kBoxHaloRight));
+        const unsigned long long t0 = nb_globaltimer();
+        double v;
+        bool ok;
+        while (!(ok = box_get(mine, a.seq, &v)))
+            if (nb_globaltimer() - t0 > 10000000000ull) break;              // 10 s: a peer died
+        if (!ok) v = __longlong_as_double(0x7ff8000000000000ll);
+        if (lane == 0) a.x[-1] = v; else a.x[a.right_cell] = v;
+    }
+}
+// NCCL form: edges[r] = {first, last} of every rank (all-gathered); pick the neighbours' values
+__global__ void halo_apply_kernel(double *x, unsigned long long right_cell, const double *edges, int rank, int world)
+{
+    if (threadIdx.x == 0 && rank > 0) x[-1] = edges[2 * (rank - 1) + 1];
+    if (threadIdx.x == 1 && rank + 1 < world) x[right_cell] = edges[2 * (rank + 1)];
+}
+__global__ void halo_pack_kernel(const double *x, unsigned long long n_local, double *edges, int rank)
+{
+    if (threadIdx.x == 0) { edges[2 * rank] = x[0]; edges[2 * rank + 1] = x[n_local - 1]; }
 }
 
 __global__ void fill_kernel(double *dst, double value, unsigned long long n_local)

@@ -103,12 +103,20 @@ int default_cfg(Variant v, int maxm)
 // creates and destroys its state per call like the reference (mma.c:173, :450); cudaMalloc /
 // cudaHostAlloc of gigabytes costs tens to hundreds of milliseconds, so freed blocks are parked here
 // and handed back to the next call of a similar size.  nlopt_b200_release_cached_memory() empties it.
+// Device blocks are keyed by (device ordinal, size): a process whose threads drive different GPUs must never be
+// handed a block that lives on another device, and a block is freed with its owner selected.
 class BlockCache {
 public:
+    static int current_device()
+    {
+        int d = 0;
+        cudaGetDevice(&d);
+        return d;
+    }
     void *take(bool pinned, size_t bytes)
     {
         std::lock_guard<std::mutex> g(mu_);
-        auto &pool = pinned ? pinned_ : device_;
+        auto &pool = pinned ? pinned_ : device_[current_device()];
         auto it = pool.lower_bound(bytes);
         if (it != pool.end() && it->first <= bytes + bytes / 4 + 4096) {
             void *p = it->second;
@@ -117,21 +125,23 @@ public:
         }
         return nullptr;
     }
-    void give(bool pinned, size_t bytes, void *p)
+    void give(bool pinned, size_t bytes, void *p, int device = -1)
     {
         std::lock_guard<std::mutex> g(mu_);
-        auto &pool = pinned ? pinned_ : device_;
+        if (device < 0) device = current_device();
+        auto &pool = pinned ? pinned_ : device_[device];
         pool.emplace(bytes, p);
         while (pool.size() > 48) {                // keep the cache bounded: drop the smallest block
             auto it = pool.begin();
-            if (pinned) cudaFreeHost(it->second); else cudaFree(it->second);
+            if (pinned) cudaFreeHost(it->second); else free_on(device, it->second);
             pool.erase(it);
         }
     }
     void clear()
     {
         std::lock_guard<std::mutex> g(mu_);
-        for (auto &e : device_) cudaFree(e.second);
+        for (auto &d : device_)
+            for (auto &e : d.second) free_on(d.first, e.second);
         for (auto &e : pinned_) cudaFreeHost(e.second);
         device_.clear();
         pinned_.clear();
@@ -139,8 +149,16 @@ public:
     static BlockCache &get() { static BlockCache c; return c; }
 
 private:
+    static void free_on(int device, void *p)
+    {
+        const int cur = current_device();
+        if (cur != device) cudaSetDevice(device);
+        cudaFree(p);
+        if (cur != device) cudaSetDevice(cur);
+    }
     std::mutex mu_;
-    std::multimap<size_t, void *> device_, pinned_;
+    std::map<int, std::multimap<size_t, void *>> device_;
+    std::multimap<size_t, void *> pinned_;
 };
 
 cudaError_t cached_malloc(double **p, size_t bytes)
@@ -154,6 +172,8 @@ cudaError_t cached_host_alloc(double **p, size_t bytes)
     if (void *q = BlockCache::get().take(true, bytes)) { *p = (double *) q; return cudaSuccess; }
     return cudaHostAlloc(p, bytes, cudaHostAllocMapped);
 }
+
+constexpr size_t kGuard = 8;        // doubles of guard around x and xcur (halo cells)
 
 int pick_maxm(int m) { return m == 0 ? 0 : m <= 1 ? 1 : m <= 2 ? 2 : m <= 4 ? 4 : m <= 8 ? 8 : 16; }
 
@@ -184,17 +204,20 @@ void DeviceBackend::free_state()
 {
     if (stream_) cudaStreamSynchronize(stream_);
     if (copy_stream_) cudaStreamSynchronize(copy_stream_);
-    if (pool_) BlockCache::get().give(false, pool_bytes_, pool_);
-    if (pen_rows_) BlockCache::get().give(false, (size_t) pen_total_ * geo_.ld * sizeof(double), pen_rows_);
+    if (pool_) BlockCache::get().give(false, pool_bytes_, pool_, device_);
+    if (pen_rows_) BlockCache::get().give(false, (size_t) pen_total_ * geo_.ld * sizeof(double), pen_rows_, device_);
     pen_rows_ = nullptr;
     if (w_dev_) cudaFree(w_dev_);
     if (xtol_abs_dev_) cudaFree(xtol_abs_dev_);
-    for (const Owned &o : owned_) BlockCache::get().give(o.pinned, o.bytes, o.p);   // every small buffer
+    for (const Owned &o : owned_) BlockCache::get().give(o.pinned, o.bytes, o.p, device_);   // every small buffer
     owned_.clear();
     if (xfull_dev_) cudaFree(xfull_dev_);
     solve_state_ = nullptr;
+    vs2_dev_ = vs2_host_ = halo_edges_ = nullptr;
+    halo_ptr_ = nullptr;
     grouptags_ = nullptr;
     res_host_ = nullptr;
+    wide_dev_ = nullptr;
     if (h_x_) BlockCache::get().give(true, (size_t) geo_.n * sizeof(double), h_x_);
     for (int b = 0; b < 2; ++b) {
         if (h_grad_[b]) BlockCache::get().give(true, h_grad_cap_ * sizeof(double), h_grad_[b]);
@@ -204,7 +227,6 @@ void DeviceBackend::free_state()
     if (copy_stream_) cudaStreamDestroy(copy_stream_);
     pool_ = w_dev_ = xtol_abs_dev_ = partials_ = vsums_ = out_dev_ = xfull_dev_ = scalar_dev_ = nullptr;
     tickets_ = nullptr;
-    grouprecs_ = nullptr;
     out_host_ = nullptr;
     flag_host_ = nullptr;
     h_x_ = nullptr;
@@ -233,20 +255,22 @@ bool DeviceBackend::alloc_state()
         Geometry gr = Geometry::make(geo_.n, comm.world, r, target_chunks_, pmax_);
         if (gr.ld > shard_cap_) shard_cap_ = gr.ld;
     }
-    if (m_ > (unsigned) kMaxParamM)
-        return fail("more than 32 inequality constraints are not supported by this build of the dual kernel");
+    if (m_ > (unsigned) kWideMaxM)
+        return fail("more than 2048 inequality constraints: the dual kernel keeps 88 bytes of shared memory per constraint");
 
     NB_CUDA(cudaDeviceGetAttribute(&sm_count_, cudaDevAttrMultiProcessorCount, device_));
     NB_CUDA(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
     NB_CUDA(cudaStreamCreateWithFlags(&copy_stream_, cudaStreamNonBlocking));
 
     const size_t ld = geo_.ld;
-    const size_t total = (9 + 2 * (size_t) m_) * ld;
+    // x and xcur carry kGuard cells on either side: the halo of stencil device callbacks (x[-1], x[ld]); everything
+    // stays 64-byte aligned (ld is a multiple of 512 doubles)
+    const size_t total = (9 + 2 * (size_t) m_) * ld + 3 * kGuard;
     pool_bytes_ = total * sizeof(double);
     NB_CUDA(cached_malloc(&pool_, pool_bytes_));
     NB_CUDA(cudaMemsetAsync(pool_, 0, total * sizeof(double), stream_));
-    double *p = pool_;
-    x_ = p; p += ld;  xcur_ = p; p += ld;  xprev_ = p; p += ld;  xprevprev_ = p; p += ld;
+    double *p = pool_ + kGuard;
+    x_ = p; p += ld + kGuard;  xcur_ = p; p += ld + kGuard;  xprev_ = p; p += ld;  xprevprev_ = p; p += ld;
     lb_ = p; p += ld; ub_ = p; p += ld;    sigma_ = p; p += ld;  g_ = p; p += ld;  gcur_ = p; p += ld;
     G_ = p; p += (size_t) m_ * ld;
     Gcur_ = p;
@@ -278,7 +302,7 @@ void DeviceBackend::release_small(void *p)
 {
     for (size_t i = 0; i < owned_.size(); ++i)
         if (owned_[i].p == p) {
-            BlockCache::get().give(owned_[i].pinned, owned_[i].bytes, p);
+            BlockCache::get().give(owned_[i].pinned, owned_[i].bytes, p, device_);
             owned_.erase(owned_.begin() + (long) i);
             return;
         }
@@ -287,28 +311,41 @@ void DeviceBackend::release_small(void *p)
 bool DeviceBackend::alloc_workspace()
 {
     if (partials_) { release_small(partials_); partials_ = nullptr; }
-    if (grouprecs_) { release_small(grouprecs_); grouprecs_ = nullptr; }
     if (grouptags_) { release_small(grouptags_); grouptags_ = nullptr; }
     if (vsums_) { release_small(vsums_); vsums_ = nullptr; }
-    {
+    if (m_ <= (unsigned) kMaxParamM) {
         const int maxm = pick_maxm((int) m_);
         const int nv = 3 + (maxm > 0 ? maxm : 1);
         nvp_ = (nv + 3) / 4 * 4;                  // records are multiples of 32 bytes
+    } else {
+        nvp_ = (3 + (int) m_ + 3) / 4 * 4;        // wide kernel: 3 + m sums
     }
     const size_t ng = geo_.nseg_local;
-    if (!small_dev((void **) &partials_, ng * nvp_ * sizeof(double))) return false;   // end_outer_kernel: one record per group
-    if (!small_dev((void **) &grouprecs_, ng * nvp_ * sizeof(double))) return false;
+    const size_t rec = (size_t) (nvp_ > 24 ? nvp_ : 24);
+    if (!small_dev((void **) &partials_, ng * 4 * sizeof(double))) return false;   // end_outer_kernel: one record (3 sums) per group
+    // tagged group records {value, tag} of the dual kernels: [nvp][local groups]; tags never repeat (launch ids), so
+    // the slots only have to start from zero once
+    {
+        const size_t bytes = ng * (size_t) nvp_ * 2 * sizeof(double);
+        if (!small_dev((void **) &grouptags_, bytes)) return false;
+        NB_CUDA(cudaMemsetAsync(grouptags_, 0, bytes, stream_));
+    }
     if (!small_dev((void **) &vsums_, (size_t) kV * 24 * sizeof(double))) return false;
-    if (!out_dev_ && !small_dev((void **) &out_dev_, (size_t) kV * 24 * sizeof(double) + 64)) return false;
+    if (out_dev_ && out_rec_ < rec) { release_small(out_dev_); out_dev_ = nullptr; release_small((void *) out_host_); out_host_ = nullptr; }
+    if (!out_dev_ && !small_dev((void **) &out_dev_, (size_t) kV * rec * sizeof(double) + 64)) return false;
     if (!tickets_) {
         if (!small_dev((void **) &tickets_, 256)) return false;
         NB_CUDA(cudaMemsetAsync(tickets_, 0, (kV + 1) * sizeof(unsigned), stream_));
     }
-    if (!out_host_) {
-        if (!small_pinned((void **) &out_host_, 24 * sizeof(double))) return false;
+    if (!out_host_ && !small_pinned((void **) &out_host_, rec * sizeof(double))) return false;
+    out_rec_ = rec;
+    if (!flag_host_) {
         if (!small_pinned((void **) &flag_host_, 128)) return false;
         *flag_host_ = 0;
     }
+    if (m_ > (unsigned) kMaxParamM && !wide_dev_ && !small_dev((void **) &wide_dev_, 4 * (size_t) m_ * sizeof(double))) return false;
+    pend_val_.assign(1 + (size_t) m_, 0.0);
+    pend_set_.assign(1 + (size_t) m_, 0);
     NB_CUDA(cudaStreamSynchronize(stream_));
     return true;
 }
@@ -379,7 +416,10 @@ bool DeviceBackend::setup(const BackendConfig &cfg)
         if (Comm::instance().active())
             NB_CUDA(cudaMalloc(&xfull_dev_, (size_t) Comm::instance().world * shard_cap_ * sizeof(double)));
     }
-    if (Comm::instance().active() && !small_dev((void **) &scalar_dev_, 64 * sizeof(double))) return false;
+    if (Comm::instance().active()) {
+        scalar_cap_ = 1 + (size_t) m_;
+        if (!small_dev((void **) &scalar_dev_, (scalar_cap_ + 64) * sizeof(double))) return false;
+    }
     if (cfg.x0_host) {
         NB_CUDA(cudaMemcpyAsync(x_, cfg.x0_host + j0, nl * sizeof(double), cudaMemcpyHostToDevice, stream_));
         stats_->h2d_bytes += nl * sizeof(double);
@@ -526,7 +566,7 @@ bool DeviceBackend::eval_penalty_objective(Slot slot, bool want_grad, double *va
         if (comm.all_reduce_sum(tmp, pen_total_, stream_, &err_)) return false;
         NB_CUDA(cudaMemcpyAsync(buf.data(), tmp, pen_total_ * sizeof(double), cudaMemcpyDeviceToHost, stream_));
         NB_CUDA(cudaStreamSynchronize(stream_));
-        BlockCache::get().give(false, pen_total_ * sizeof(double), tmp);
+        BlockCache::get().give(false, pen_total_ * sizeof(double), tmp, device_);
         for (unsigned k = 0; k < pen_total_; ++k)
             if (partial[k]) vals[k] = buf[k];
     }
@@ -582,6 +622,11 @@ bool DeviceBackend::push_rows_to(double *dst, unsigned rows, const double *host_
 bool DeviceBackend::eval_user_objective(Slot slot, bool want_grad, double *value)
 {
     const FuncSpec &fs = cfg_.objective;
+    if (fs.df2) {
+        double *gs = want_grad ? (slot == kBase ? g_ : gcur_) : nullptr;
+        *value = 0.0;                                  // settled in finish_evals()
+        return enqueue_df2(fs, slot, gs, 0);
+    }
     if (fs.df) {
         double *xs = slot == kBase ? x_ : xcur_view();
         double *gs = want_grad ? (slot == kBase ? g_ : gcur_) : nullptr;
@@ -590,7 +635,8 @@ bool DeviceBackend::eval_user_objective(Slot slot, bool want_grad, double *value
         cb_seconds_ += wall_seconds() - t0;
         if (Comm::instance().active()) {           // shard contributions add up: settled in finish_evals()
             pend_val_[0] = v;
-            pend_mask_ |= 1ull;
+            pend_set_[0] = 1;
+            pend_any_ = true;
         }
         *value = v;
         return true;
@@ -608,6 +654,11 @@ bool DeviceBackend::eval_user_objective(Slot slot, bool want_grad, double *value
 bool DeviceBackend::eval_constraint(Slot slot, unsigned ic, unsigned row0, bool want_grad, double *values)
 {
     const FuncSpec &fs = cfg_.constraints[ic];
+    if (fs.df2) {
+        double *gs = want_grad ? (slot == kBase ? G_ : Gcur_) + (size_t) row0 * geo_.ld : nullptr;
+        values[0] = 0.0;
+        return enqueue_df2(fs, slot, gs, 1 + row0);
+    }
     if (fs.df) {
         double *xs = slot == kBase ? x_ : xcur_view();
         double *gs = want_grad ? (slot == kBase ? G_ : Gcur_) + (size_t) row0 * geo_.ld : nullptr;
@@ -616,7 +667,8 @@ bool DeviceBackend::eval_constraint(Slot slot, unsigned ic, unsigned row0, bool 
         cb_seconds_ += wall_seconds() - t0;
         if (Comm::instance().active()) {
             pend_val_[1 + row0] = v;
-            pend_mask_ |= 1ull << (1 + row0);
+            pend_set_[1 + row0] = 1;
+            pend_any_ = true;
         }
         values[0] = v;
         return true;
@@ -633,22 +685,122 @@ bool DeviceBackend::eval_constraint(Slot slot, unsigned ic, unsigned row0, bool 
 
 // Device callbacks on several ranks return shard-local values; one all-reduce settles every value of the point
 // (1 + m doubles; entries from host callbacks are global already and are not touched).
+// Asynchronous device callbacks (nlopt_b200_dfunc2): enqueue, remember which value is pending.
+bool DeviceBackend::enqueue_df2(const FuncSpec &fs, Slot slot, double *grad_dst, unsigned index)
+{
+    Comm &comm = Comm::instance();
+    if (!vs2_dev_) {
+        vs2_cap_ = 1 + (size_t) m_;
+        if (!small_dev((void **) &vs2_dev_, vs2_cap_ * kV * sizeof(double))) return false;
+        if (!small_pinned((void **) &vs2_host_, vs2_cap_ * kV * sizeof(double))) return false;
+        shard_.n = geo_.n; shard_.n_local = geo_.n_local; shard_.j0 = geo_.j0;
+        shard_.nchunks = geo_.nchunks; shard_.chunk0 = geo_.chunk0;
+        shard_.groups_total = geo_.S; shard_.group0 = geo_.seg0; shard_.groups_local = geo_.nseg_local; shard_.groups_per_vshard = geo_.P;
+        shard_.vshard0 = geo_.seg0 / geo_.P; shard_.local_vshards = geo_.local_vshards;
+        shard_.rank = comm.rank; shard_.world = comm.world;
+        pend2_.assign(vs2_cap_, nullptr);
+    }
+    if (!pend2_any_) NB_CUDA(cudaMemsetAsync(vs2_dev_, 0, vs2_cap_ * kV * sizeof(double), stream_));   // first callback of this point
+    if (fs.halo > 0 && !ensure_halo(slot)) return false;
+    double *xs = slot == kBase ? x_ : xcur_view();
+    const double t0 = wall_seconds();
+    fs.df2(&shard_, xs, grad_dst, vs2_dev_ + (size_t) index * kV, fs.data, stream_);
+    cb_seconds_ += wall_seconds() - t0;
+    NB_CUDA(cudaGetLastError());
+    pend2_[index] = &fs;
+    pend2_any_ = true;
+    return true;
+}
+
+// The halo cells of the slot's x for stencil callbacks: once per point (x_epoch_), only with several ranks.
+bool DeviceBackend::ensure_halo(Slot slot)
+{
+    Comm &comm = Comm::instance();
+    if (!comm.active()) return true;
+    double *xs = slot == kBase ? x_ : xcur_view();
+    if (halo_ptr_ == xs && halo_epoch_ == x_epoch_) return true;
+    if (geo_.n_local == 0) return fail("halo exchange: a rank owns no variables (n too small for this many ranks)");
+    if (comm.use_p2p()) {
+        HaloArgs a;
+        std::memset(&a, 0, sizeof a);
+        a.x = xs; a.n_local = geo_.n_local; a.right_cell = geo_.n_local;
+        for (int r = 0; r < comm.world; ++r) a.box[r] = comm.box_peer[r];
+        a.rank = comm.rank; a.world = comm.world;
+        a.seq = comm.next_seq();
+        halo_exchange_kernel<<<1, 32, 0, stream_>>>(a);
+    } else {
+        if (!halo_edges_ && !small_dev((void **) &halo_edges_, 2 * 8 * sizeof(double))) return false;
+        halo_pack_kernel<<<1, 32, 0, stream_>>>(xs, geo_.n_local, halo_edges_, comm.rank);
+        if (comm.all_gather_inplace(halo_edges_, 2, stream_, &err_)) return false;
+        halo_apply_kernel<<<1, 32, 0, stream_>>>(xs, geo_.n_local, halo_edges_, comm.rank, comm.world);
+    }
+    ++stats_->kernel_launches;
+    NB_CUDA(cudaGetLastError());
+    halo_ptr_ = xs;
+    halo_epoch_ = x_epoch_;
+    return true;
+}
+
 bool DeviceBackend::finish_evals(double *fvalue, double *cvalues)
 {
-    if (!pend_mask_) return true;
+    if (pend2_any_) {
+        // one exchange + one copy + one synchronisation for all values of the point.  Every slot of the [1+m][8] block
+        // is non-zero on exactly one rank, so the all-reduce is exact whatever its internal order; the 8 shard sums are
+        // then added in index order: the value does not depend on the number of ranks.
+        Comm &comm = Comm::instance();
+        if (comm.active() && comm.all_reduce_sum(vs2_dev_, vs2_cap_ * kV, stream_, &err_)) return false;
+        NB_CUDA(cudaMemcpyAsync(vs2_host_, vs2_dev_, vs2_cap_ * kV * sizeof(double), cudaMemcpyDeviceToHost, stream_));
+        NB_CUDA(cudaStreamSynchronize(stream_));
+        for (size_t i = 0; i < vs2_cap_; ++i) {
+            const FuncSpec *fs = pend2_[i];
+            if (!fs) continue;
+            double tot = vs2_host_[i * kV];
+            for (unsigned v = 1; v < kV; ++v) tot += vs2_host_[i * kV + v];
+            const double val = fs->dfin(tot, fs->data);
+            if (i == 0) { if (fvalue) *fvalue = val; else continue; }
+            else { if (cvalues) cvalues[i - 1] = val; else continue; }
+            pend2_[i] = nullptr;
+        }
+        pend2_any_ = false;
+        for (const FuncSpec *q : pend2_) pend2_any_ = pend2_any_ || q != nullptr;
+    }
+    if (!pend_any_) return true;
     Comm &comm = Comm::instance();
-    double buf[1 + kMaxParamM];
-    for (unsigned i = 0; i <= m_; ++i) buf[i] = ((pend_mask_ >> i) & 1ull) ? pend_val_[i] : 0.0;
     const size_t cnt = 1 + (size_t) m_;
-    NB_CUDA(cudaMemcpyAsync(scalar_dev_, buf, cnt * sizeof(double), cudaMemcpyHostToDevice, stream_));
+    std::vector<double> buf(cnt);
+    for (size_t i = 0; i < cnt; ++i) buf[i] = pend_set_[i] ? pend_val_[i] : 0.0;
+    if (cnt > scalar_cap_) {
+        if (scalar_dev_) release_small(scalar_dev_);
+        scalar_dev_ = nullptr;
+        if (!small_dev((void **) &scalar_dev_, (cnt + 64) * sizeof(double))) return false;
+        scalar_cap_ = cnt;
+    }
+    NB_CUDA(cudaMemcpyAsync(scalar_dev_, buf.data(), cnt * sizeof(double), cudaMemcpyHostToDevice, stream_));
     if (comm.all_reduce_sum(scalar_dev_, cnt, stream_, &err_)) return false;
-    NB_CUDA(cudaMemcpyAsync(buf, scalar_dev_, cnt * sizeof(double), cudaMemcpyDeviceToHost, stream_));
+    NB_CUDA(cudaMemcpyAsync(buf.data(), scalar_dev_, cnt * sizeof(double), cudaMemcpyDeviceToHost, stream_));
     NB_CUDA(cudaStreamSynchronize(stream_));
-    if (fvalue && (pend_mask_ & 1ull)) { *fvalue = buf[0]; pend_mask_ &= ~1ull; }
+    if (fvalue && pend_set_[0]) { *fvalue = buf[0]; pend_set_[0] = 0; }
     if (cvalues)
         for (unsigned i = 0; i < m_; ++i)
-            if ((pend_mask_ >> (1 + i)) & 1ull) { cvalues[i] = buf[1 + i]; pend_mask_ &= ~(1ull << (1 + i)); }
+            if (pend_set_[1 + i]) { cvalues[i] = buf[1 + i]; pend_set_[1 + i] = 0; }
+    pend_any_ = false;
+    for (size_t i = 0; i < cnt; ++i) pend_any_ = pend_any_ || pend_set_[i];
     return true;
+}
+
+// Collective OR of a rank-local decision (the time limit): one 8-byte all-reduce.  Every rank calls it at the same
+// points of the driver loop (ccsa_driver.cpp: Loop::timed_out), so the ranks cannot disagree about MAXTIME.
+bool DeviceBackend::agree_any(bool local)
+{
+    Comm &comm = Comm::instance();
+    if (!comm.active()) return local;
+    double v = local ? 1.0 : 0.0;
+    double *slot = scalar_dev_ + scalar_cap_;          // the spare doubles behind the value buffer
+    if (cudaMemcpyAsync(slot, &v, sizeof v, cudaMemcpyHostToDevice, stream_) != cudaSuccess) return local;
+    if (comm.all_reduce_sum(slot, 1, stream_, &err_)) return local;
+    if (cudaMemcpyAsync(&v, slot, sizeof v, cudaMemcpyDeviceToHost, stream_) != cudaSuccess) return local;
+    if (cudaStreamSynchronize(stream_) != cudaSuccess) return local;
+    return v > 0.0;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -677,7 +829,21 @@ bool DeviceBackend::wait_flag()
     }
 }
 
-void DeviceBackend::fill_dual_args(DualArgs &a, const double *y, const DualScalars &sc, int cons0, int cons_n)
+// operand arrays to load evict_last (DualArgs::l2_keep), in order of preference: the arrays that never move
+// (sigma, lb, ub), then x, grad f and the gradient rows -- as many as fit into l2_keep_bytes_
+unsigned DeviceBackend::l2_keep_mask() const
+{
+    if (l2_keep_bytes_ == 0) return 0u;
+    const size_t per = geo_.ld * sizeof(double);
+    size_t budget = l2_keep_bytes_ / (per ? per : 1);
+    static const int order[5] = {3, 1, 2, 0, 4};
+    unsigned mask = 0;
+    for (int k = 0; k < 5 && budget > 0; ++k, --budget) mask |= 1u << order[k];
+    for (unsigned i = 0; i < m_ && i < (unsigned) kMaxParamM && budget > 0; ++i, --budget) mask |= 1u << (5 + i);
+    return mask;
+}
+
+void DeviceBackend::fill_dual_args(DualArgs &a, const double *y, const DualScalars &sc)
 {
     std::memset(&a, 0, sizeof a);
     a.x = x_; a.lb = lb_; a.ub = ub_; a.sigma = sigma_; a.g = g_; a.G = G_;
@@ -685,39 +851,54 @@ void DeviceBackend::fill_dual_args(DualArgs &a, const double *y, const DualScala
     a.ld = geo_.ld;
     a.nchunks = geo_.nchunks; a.chunk0 = geo_.chunk0;
     a.nseg_total = geo_.S; a.seg0 = geo_.seg0; a.segs_per_vshard = geo_.P; a.local_vshards = geo_.local_vshards;
-    a.grouprecs = grouprecs_; a.vsums = vsums_;
-    a.tickets = tickets_; a.out_dev = out_dev_;
+    a.grouptags = grouptags_;
+    a.tag = (1ull << 63) | ++eval_tag_;          // the solve kernel's tags (launch id << 40 | generation) stay below 2^63
+    a.out_dev = out_dev_;
     a.out_host = out_host_; a.flag_host = flag_host_;
     a.seq = seq_ = Comm::instance().active() ? Comm::instance().next_seq() : seq_ + 1;
     a.publish_host = Comm::instance().active() ? 0 : 1;
     a.nvp = nvp_;
+    const bool wide = m_ > (unsigned) kMaxParamM;
     {
         Comm &cm = Comm::instance();
         a.rank = cm.rank;
         a.world = cm.world;
-        for (int r = 0; r < 8; ++r) a.box[r] = (cm.active() && cm.use_p2p() && r < cm.world) ? cm.box_peer[r] : nullptr;
+        // the mailbox holds records of <= 19 sums: the wide kernel exchanges through ncclAllGather
+        for (int r = 0; r < 8; ++r) a.box[r] = (cm.active() && cm.use_p2p() && !wide && r < cm.world) ? cm.box_peer[r] : nullptr;
     }
+    a.l2_keep = l2_keep_mask();
+    a.prefetch_chunks = prefetch_chunks_;
     a.m = (int) m_;
-    a.cons0 = cons0; a.cons_n = cons_n;
     a.rho = sc.rho;
     a.half_rho = 0.5 * sc.rho;
     a.active = 0;
     double u = sc.rho;                                   // ccsa_quadratic.c:116-120, j-independent
+    if (wide) wide_host_.resize(4 * (size_t) m_);
     for (unsigned i = 0; i < m_; ++i) {
-        a.y[i] = y[i];
-        a.rhoc[i] = sc.rhoc[i];
-        a.half_rhoc[i] = 0.5 * sc.rhoc[i];
-        if (!(variant_ == kMMA && std::isnan(sc.fcval[i]))) a.active |= 1u << i;
+        const bool on = !(variant_ == kMMA && std::isnan(sc.fcval[i]));
+        if (wide) {
+            wide_host_[i] = y[i];
+            wide_host_[m_ + i] = sc.rhoc[i];
+            wide_host_[2 * (size_t) m_ + i] = 0.5 * sc.rhoc[i];
+            wide_host_[3 * (size_t) m_ + i] = on ? 1.0 : 0.0;
+        } else {
+            a.y[i] = y[i];
+            a.rhoc[i] = sc.rhoc[i];
+            a.half_rhoc[i] = 0.5 * sc.rhoc[i];
+            if (on) a.active |= 1u << i;
+        }
         u += sc.rhoc[i] * y[i];
     }
     a.u_ccsaq = u;
+    a.wide = wide_dev_;
 }
 
-bool DeviceBackend::launch_dual(const double *y, const DualScalars &sc, bool store, int chunk0, int chunk_n, bool wait)
+bool DeviceBackend::launch_dual(const double *y, const DualScalars &sc, bool store, bool wait)
 {
     DualArgs a;
-    fill_dual_args(a, y, sc, chunk0, chunk_n);
+    fill_dual_args(a, y, sc);
 
+    const bool wide = m_ > (unsigned) kMaxParamM;
     const int maxm = pick_maxm((int) m_);
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (time_kernels_) {
@@ -730,12 +911,26 @@ bool DeviceBackend::launch_dual(const double *y, const DualScalars &sc, bool sto
         e1 = ev_pool_[ev_used_++];
         cudaEventRecord(e0, stream_);
     }
-    const bool full_m = (int) m_ == maxm && (variant_ == kCCSAQ || a.active == (m_ >= 32 ? 0xffffffffu : ((1u << m_) - 1u)));
+    const bool full_m = !wide && (int) m_ == maxm && (variant_ == kCCSAQ || a.active == ((1u << m_) - 1u));
     // MMA with 16 gradient rows is register-starved in the register form (64 % of peak); the TMA-staged form
     // reaches 72 % (profiles/r01_tune_tma.jsonl) and is the default there.  Everywhere else the register
     // form is faster and the TMA form is opt-in (kernel_cfg 10 / 11 / 12 = 3 / 2 / 4 stages).
     const bool tma_default = kernel_cfg_ < 0 && variant_ == kMMA && maxm == 16 && full_m;
-    if ((tma_default || (kernel_cfg_ >= 10 && kernel_cfg_ <= 12)) && full_m && (maxm == 1 || maxm == 4 || maxm == 16)) {
+    if (wide) {
+        // any number of constraints: rows streamed in blocks of 8, per-row scalars in dynamic shared memory
+        NB_CUDA(cudaMemcpyAsync(wide_dev_, wide_host_.data(), 4 * (size_t) m_ * sizeof(double), cudaMemcpyHostToDevice, stream_));
+        DualKernel fn = variant_ == kMMA ? (store ? (DualKernel) dual_eval_wide_kernel<0, true> : (DualKernel) dual_eval_wide_kernel<0, false>)
+                                         : (store ? (DualKernel) dual_eval_wide_kernel<1, true> : (DualKernel) dual_eval_wide_kernel<1, false>);
+        const size_t mp = ((size_t) m_ + kWideRows - 1) / kWideRows * kWideRows;
+        const size_t smem = 12 * mp * sizeof(double);
+        NB_CUDA(cudaFuncSetAttribute((const void *) fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+        int per_sm = 0;
+        NB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kBlock, smem));
+        if (per_sm < 1) return fail("dual_eval_wide_kernel does not fit on an SM");
+        long long pgrid = (long long) sm_count_ * (ctas_per_sm_ > 0 ? ctas_per_sm_ : per_sm);
+        if (pgrid > (long long) geo_.nseg_local) pgrid = geo_.nseg_local;
+        fn<<<(unsigned) (pgrid < 1 ? 1 : pgrid) + 1, kBlock, smem, stream_>>>(a);
+    } else if ((tma_default || (kernel_cfg_ >= 10 && kernel_cfg_ <= 12)) && full_m && (maxm == 1 || maxm == 4 || maxm == 16)) {
         // TMA-staged form: producer warp + 8 consumer warps, dynamic shared memory = stages x (5+m) x 4 KB
         int stages = kernel_cfg_ == 10 ? 3 : kernel_cfg_ == 11 ? 2 : kernel_cfg_ == 12 ? 4 : 2;
         if (maxm == 16) stages = 2;
@@ -747,29 +942,26 @@ bool DeviceBackend::launch_dual(const double *y, const DualScalars &sc, bool sto
         if (per_sm < 1) return fail("dual_eval_tma_kernel does not fit on an SM");
         long long pgrid = (long long) sm_count_ * (ctas_per_sm_ > 0 ? ctas_per_sm_ : 6);     // oversubscribed 2-3x: evens out the tail
         if (pgrid > (long long) geo_.nseg_local) pgrid = geo_.nseg_local;
-        fn<<<(unsigned) (pgrid < 1 ? 1 : pgrid), kTmaBlock, smem, stream_>>>(a);
+        fn<<<(unsigned) (pgrid < 1 ? 1 : pgrid) + 1, kTmaBlock, smem, stream_>>>(a);
     } else {
-        // persistent kernel: the grid is sized to the machine, not to the problem
+        // persistent kernel: the grid is sized to the machine, not to the problem (+ the folder CTA)
         int cfg = kernel_cfg_ >= 0 && kernel_cfg_ < kNumCfgs ? kernel_cfg_ : default_cfg(variant_, maxm);
-        (void) full_m;
         if (maxm >= 8) cfg = 3;
         const KernelCfg c = kCfgs[cfg];
-        const bool full = (int) m_ == maxm && (variant_ == kCCSAQ || a.active == (m_ >= 32 ? 0xffffffffu : ((1u << m_) - 1u)));
-        DualKernel fn = variant_ == kMMA ? (full ? pick_kernel<0, true>(maxm, cfg, store) : pick_kernel<0, false>(maxm, cfg, store))
-                                         : (full ? pick_kernel<1, true>(maxm, cfg, store) : pick_kernel<1, false>(maxm, cfg, store));
-        const int slots = c.block / (32 * kGroupWarps);
-        const long long want = ((long long) geo_.nseg_local + slots - 1) / slots;
+        DualKernel fn = variant_ == kMMA ? (full_m ? pick_kernel<0, true>(maxm, cfg, store) : pick_kernel<0, false>(maxm, cfg, store))
+                                         : (full_m ? pick_kernel<1, true>(maxm, cfg, store) : pick_kernel<1, false>(maxm, cfg, store));
+        const long long want = (long long) geo_.nseg_local;
         const long long cap = (long long) sm_count_ * (ctas_per_sm_ > 0 ? ctas_per_sm_ : 4 * c.minb);
         const int pgrid = (int) (want < cap ? want : cap);
-        fn<<<pgrid < 1 ? 1 : pgrid, c.block, 0, stream_>>>(a);
+        fn<<<(pgrid < 1 ? 1 : pgrid) + 1, c.block, 0, stream_>>>(a);
     }
     if (time_kernels_) cudaEventRecord(e1, stream_);
     ++stats_->kernel_launches;
     NB_CUDA(cudaGetLastError());
     if (!a.publish_host && a.box[0] == nullptr) {
-        const int nv = 3 + (maxm > 0 ? maxm : 1);
+        const int nv = wide ? 3 + (int) m_ : 3 + (maxm > 0 ? maxm : 1);
         if (Comm::instance().all_gather_inplace(out_dev_, (size_t) geo_.local_vshards * nvp_, stream_, &err_)) return false;
-        publish_kernel<<<1, 32, 0, stream_>>>(out_dev_, nv, nvp_, out_host_, flag_host_, a.seq);
+        publish_kernel<<<1, 256, 0, stream_>>>(out_dev_, nv, nvp_, out_host_, flag_host_, a.seq);
         ++stats_->kernel_launches;
         NB_CUDA(cudaGetLastError());
     }
@@ -779,22 +971,13 @@ bool DeviceBackend::launch_dual(const double *y, const DualScalars &sc, bool sto
 bool DeviceBackend::dual_eval(const double *y, const DualScalars &sc, bool materialize, DualSums *out)
 {
     if (materialize) { cand_in_x_ = false; ++x_epoch_; }   // xcur_ is about to hold the candidate
-    const int maxm = pick_maxm((int) m_);
-    const int step = maxm > 0 ? maxm : 1;
-    int c0 = 0;
-    do {
-        const int cn = (int) m_ - c0 < step ? (int) m_ - c0 : step;
-        if (!launch_dual(y, sc, materialize && c0 == 0, c0, cn, true)) return false;
-        if (Comm::instance().active() && std::isnan(out_host_[0]) && std::isnan(out_host_[1]) && std::isnan(out_host_[2]))
-            return fail("the cross-rank exchange of the dual sums timed out or produced NaN (is every rank running the same calls?)");
-        if (c0 == 0) {
-            out->val = out_host_[0];
-            out->gval = out_host_[1];
-            out->wval = out_host_[2];
-        }
-        for (int k = 0; k < cn; ++k) out->gc[c0 + k] = out_host_[3 + k];
-        c0 += step;
-    } while (c0 < (int) m_);
+    if (!launch_dual(y, sc, materialize, true)) return false;
+    if (Comm::instance().active() && std::isnan(out_host_[0]) && std::isnan(out_host_[1]) && std::isnan(out_host_[2]))
+        return fail("the cross-rank exchange of the dual sums timed out or produced NaN (is every rank running the same calls?)");
+    out->val = out_host_[0];
+    out->gval = out_host_[1];
+    out->wval = out_host_[2];
+    for (unsigned k = 0; k < m_; ++k) out->gc[k] = out_host_[3 + k];
     return true;
 }
 
@@ -807,16 +990,22 @@ typedef void (*SolveKernel)(const SolveArgs);
 // One configuration per row count.  Two alternatives were measured on the box and removed (profiles/r01_summary.md):
 // two chunks in flight per sweep step (slower at n = 1e7 over 8 GPUs, 39.3 vs 32.3 us per evaluation) and
 // 4 CTAs/SM at 64 registers (spills: 149 vs 129 us per CCSAQ evaluation at n = 1e7, m = 4).
-template <int VARIANT, bool FULL>
+template <int VARIANT, bool FULL, bool POL>
 SolveKernel pick_solve_kernel(int maxm)
 {
     switch (maxm) {
-    case 1: return dual_solve_kernel<VARIANT, 1, FULL, 256, 1, 3>;
-    case 2: return dual_solve_kernel<VARIANT, 2, FULL, 256, 1, 3>;
-    case 4: return dual_solve_kernel<VARIANT, 4, FULL, 256, 1, 3>;
-    case 8: return dual_solve_kernel<VARIANT, 8, FULL, 256, 1, 2>;
-    default: return dual_solve_kernel<VARIANT, 16, FULL, 256, 1, 2>;
+    case 1: return dual_solve_kernel<VARIANT, 1, FULL, POL, 256, 1, 3>;
+    case 2: return dual_solve_kernel<VARIANT, 2, FULL, POL, 256, 1, 3>;
+    case 4: return dual_solve_kernel<VARIANT, 4, FULL, POL, 256, 1, 3>;
+    case 8: return dual_solve_kernel<VARIANT, 8, FULL, POL, 256, 1, 2>;
+    default: return dual_solve_kernel<VARIANT, 16, FULL, POL, 256, 1, 2>;
     }
+}
+template <int VARIANT>
+SolveKernel pick_solve_kernel2(int maxm, bool full, bool pol)
+{
+    return full ? (pol ? pick_solve_kernel<VARIANT, true, true>(maxm) : pick_solve_kernel<VARIANT, true, false>(maxm))
+                : (pol ? pick_solve_kernel<VARIANT, false, true>(maxm) : pick_solve_kernel<VARIANT, false, false>(maxm));
 }
 }  // namespace
 
@@ -826,7 +1015,7 @@ bool DeviceBackend::supports_dual_solve() const
     const Comm &cm = Comm::instance();
     if (cm.active() && !cm.use_p2p()) return false;
     if (variant_ == kMMA && m_ > 8) return false;      // the TMA-staged evaluation kernel wins there (see launch_dual)
-    return fused_solve_ok_ && m_ >= 1 && m_ <= 16;
+    return fused_solve_ok_ && m_ >= 1 && m_ <= (unsigned) kMaxParamM;
 }
 
 bool DeviceBackend::dual_solve(double *y, const double *lo, const double *hi, const double *stop6, const DualScalars &sc,
@@ -836,18 +1025,17 @@ bool DeviceBackend::dual_solve(double *y, const double *lo, const double *hi, co
         if (!small_dev(&solve_state_, (sizeof(SolveState) + 255) / 256 * 256)) return false;
         NB_CUDA(cudaMemsetAsync(solve_state_, 0, sizeof(SolveState), stream_));
         if (!small_pinned((void **) &res_host_, 64 * sizeof(double))) return false;
+        static_assert(kResCounts + 3 <= 64, "result record");
     }
     SolveArgs sa;
-    fill_dual_args(sa.d, y, sc, 0, (int) m_);
+    fill_dual_args(sa.d, y, sc);
     sa.st = static_cast<SolveState *>(solve_state_);
-    if (!grouptags_ || solve_launch_id_ >= (1ull << 23)) {       // tags are (launch id, generation): start from a clean slate
+    if (solve_launch_id_ >= (1ull << 22)) {       // tags are (launch id, generation): start from a clean slate
         const size_t bytes = (size_t) geo_.nseg_local * nvp_ * 2 * sizeof(double);
-        if (!grouptags_ && !small_dev((void **) &grouptags_, bytes)) return false;
         NB_CUDA(cudaMemsetAsync(grouptags_, 0, bytes, stream_));
         NB_CUDA(cudaMemsetAsync(solve_state_, 0, sizeof(SolveState), stream_));
         solve_launch_id_ = 0;
     }
-    sa.grouptags = grouptags_;
     sa.tag0 = ++solve_launch_id_ << 40;
     sa.fval = sc.fval;
     for (unsigned i = 0; i < (unsigned) kMaxParamM; ++i) {
@@ -867,8 +1055,8 @@ bool DeviceBackend::dual_solve(double *y, const double *lo, const double *hi, co
 
     const int maxm = pick_maxm((int) m_);
     const bool full = (int) m_ == maxm && (variant_ == kCCSAQ || sa.d.active == ((1u << m_) - 1u));
-    SolveKernel fn = variant_ == kMMA ? (full ? pick_solve_kernel<0, true>(maxm) : pick_solve_kernel<0, false>(maxm))
-                                      : (full ? pick_solve_kernel<1, true>(maxm) : pick_solve_kernel<1, false>(maxm));
+    const bool use_pol = sa.d.l2_keep != 0u;
+    SolveKernel fn = variant_ == kMMA ? pick_solve_kernel2<0>(maxm, full, use_pol) : pick_solve_kernel2<1>(maxm, full, use_pol);
     int per_sm = 0;
     NB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, 256, 0));
     if (per_sm < 1) return fail("dual_solve_kernel does not fit on an SM");
@@ -928,9 +1116,9 @@ bool DeviceBackend::dual_solve(double *y, const double *lo, const double *hi, co
         }
     }
 #endif
-    const long gens = (long) res_host_[24 + kMaxParamM + 2];
-    *ret = (int) res_host_[24 + kMaxParamM + 1];
-    *nevals = (long) res_host_[24 + kMaxParamM];
+    const long gens = (long) res_host_[kResCounts + 2];
+    *ret = (int) res_host_[kResCounts + 1];
+    *nevals = (long) res_host_[kResCounts];
     if (Comm::instance().active() && gens > 0) Comm::instance().advance_seq((unsigned long long) gens);
     if (*ret == kRetInvalid) return true;            // nothing ran; the caller reports it
     if (*ret == kRetFailure) return fail("the cross-rank exchange inside the dual solve timed out");
@@ -939,7 +1127,7 @@ bool DeviceBackend::dual_solve(double *y, const double *lo, const double *hi, co
     out->wval = res_host_[2];
     for (unsigned i = 0; i < m_; ++i) {
         out->gc[i] = res_host_[3 + i];
-        y[i] = res_host_[24 + i];
+        y[i] = res_host_[kResY + i];
     }
     return true;
 }
@@ -962,10 +1150,9 @@ bool DeviceBackend::time_dual(const double *y, const DualScalars &sc, bool mater
     cudaEvent_t e0, e1;
     NB_CUDA(cudaEventCreate(&e0));
     NB_CUDA(cudaEventCreate(&e1));
-    const int cn = (int) m_ < 16 ? (int) m_ : 16;
     NB_CUDA(cudaEventRecord(e0, stream_));
     for (int it = 0; it < iters; ++it)
-        if (!launch_dual(y, sc, materialize, 0, cn, false)) return false;
+        if (!launch_dual(y, sc, materialize, false)) return false;
     NB_CUDA(cudaEventRecord(e1, stream_));
     NB_CUDA(cudaStreamSynchronize(stream_));
     float ms = 0;
@@ -1125,10 +1312,14 @@ bool DeviceBackend::configure(const char *key, long long value)
     if (k == "kernel_cfg") { kernel_cfg_ = (int) value; return true; }
     if (k == "ctas_per_sm") { ctas_per_sm_ = (int) value; return true; }
     if (k == "fused_solve") { fused_solve_ok_ = value != 0; return true; }
-    if (k == "pmax" || k == "target_chunks" || k == "fill_div") {
-        if (value < 1) return fail("bad value");
+    if (k == "prefetch_chunks") { prefetch_chunks_ = value < 0 ? 0u : (unsigned) value; return true; }
+    if (k == "l2_keep_mb") { l2_keep_bytes_ = value <= 0 ? 0 : (size_t) value << 20; return true; }
+    if (k == "pmax" || k == "target_chunks" || k == "fill_div" || k == "group_base" || k == "geometry_rule") {
+        if (value < 1 && k != "geometry_rule") return fail("bad value");
         if (k == "pmax") pmax_ = (unsigned) value;
         else if (k == "target_chunks") target_chunks_ = (unsigned) value;
+        else if (k == "group_base") Geometry::group_base() = (unsigned) value;
+        else if (k == "geometry_rule") Geometry::rule() = (int) value;
         else Geometry::fill_div() = (unsigned) value;
         if (pool_) {
             Geometry g2 = Geometry::make(geo_.n, geo_.world, geo_.rank, target_chunks_, pmax_);
@@ -1157,6 +1348,7 @@ long long DeviceBackend::query(const char *key) const
     if (k == "ld") return (long long) geo_.ld;
     if (k == "launches") return stats_->kernel_launches;
     if (k == "maxm") return pick_maxm((int) m_);
+    if (k == "l2_keep_mask") return (long long) l2_keep_mask();
     return -1;
 }
 
@@ -1310,6 +1502,16 @@ int nlopt_b200_dual_time(nlopt_b200_dual h, const double *y, int want_xcur, int 
 int nlopt_b200_dual_configure(nlopt_b200_dual h, const char *key, long long value) { return ok(h, h->be.configure(key, value)); }
 
 long long nlopt_b200_dual_query(nlopt_b200_dual h, const char *key) { return h->be.query(key); }
+
+void nlopt_b200_shard_geometry(unsigned long long n, int rank, int world, nlopt_b200_shard *out)
+{
+    nb200::Geometry g = nb200::Geometry::make(n, world, rank, nb200::kDefaultTargetChunks, nb200::kDefaultPmax);
+    out->n = n; out->n_local = g.n_local; out->j0 = g.j0;
+    out->nchunks = g.nchunks; out->chunk0 = g.chunk0;
+    out->groups_total = g.S; out->group0 = g.seg0; out->groups_local = g.nseg_local; out->groups_per_vshard = g.P;
+    out->vshard0 = g.seg0 / g.P; out->local_vshards = g.local_vshards;
+    out->rank = rank; out->world = world;
+}
 
 void nlopt_b200_shard_range(unsigned long long n, int rank, int world, unsigned long long *j0, unsigned long long *count)
 {

@@ -32,6 +32,9 @@ public:
     bool eval_objective(Slot slot, bool want_grad, double *value) override;
     bool eval_constraint(Slot slot, unsigned ic, unsigned row0, bool want_grad, double *values) override;
     bool finish_evals(double *fvalue, double *cvalues) override;
+    bool agree_any(bool local) override;
+    bool enqueue_df2(const FuncSpec &fs, Slot slot, double *grad_dst, unsigned index);
+    bool ensure_halo(Slot slot);
     bool eval_user_objective(Slot slot, bool want_grad, double *value);
     bool push_rows_to(double *dst, unsigned rows, const double *host_grad);
     bool eval_penalty_objective(Slot slot, bool want_grad, double *value);
@@ -67,8 +70,9 @@ private:
     bool alloc_workspace();
     double *array(const char *which);
     double *xcur_view() { return cand_in_x_ ? x_ : xcur_; }
-    void fill_dual_args(struct DualArgs &a, const double *y, const DualScalars &sc, int cons0, int cons_n);
-    bool launch_dual(const double *y, const DualScalars &sc, bool store, int chunk0, int chunk_n, bool wait);
+    void fill_dual_args(struct DualArgs &a, const double *y, const DualScalars &sc);
+    bool launch_dual(const double *y, const DualScalars &sc, bool store, bool wait);
+    unsigned l2_keep_mask() const;
     bool wait_flag();
     bool host_x_for(Slot slot);                      // bring the slot's x to pinned host memory (cached per epoch)
     bool push_grad_rows(Slot slot, int row0, unsigned rows, bool is_objective, const double *host_grad);
@@ -88,7 +92,13 @@ private:
     int sm_count_ = 148, ctas_per_sm_ = 0;
     void *solve_state_ = nullptr;     // SolveState (device) of the persistent dual-solve kernel
     double *res_host_ = nullptr;      // its mapped pinned result record
-    double *grouptags_ = nullptr;     // its tagged group-record slots {value, tag}, [local groups][nvp]
+    double *grouptags_ = nullptr;     // tagged group-record slots {value, tag} of the dual kernels, [nvp][local groups]
+    unsigned long long eval_tag_ = 0;  // tags of the one-evaluation kernels: 1 << 63 | counter
+    double *wide_dev_ = nullptr;      // m > 16: y | rhoc | rhoc/2 | active flags of the evaluation in flight
+    std::vector<double> wide_host_;
+    size_t l2_keep_bytes_ = 0;        // operand bytes to load evict_last (knob b200_l2_keep_mb)
+    unsigned prefetch_chunks_ = 2;    // knob b200_prefetch_chunks (solve kernel: L2 prefetch of a waiting sweeper's next group)
+    size_t out_rec_ = 0;              // doubles per result record (>= 24, >= 3 + m)
     unsigned long long solve_launch_id_ = 0;   // tag = launch id << 40 | generation: never matches a stale slot
     bool fused_solve_ok_ = true;
     int kernel_cfg_ = -1;         // -1: measured default for (variant, m)          // index into the launch-geometry table of device_backend.cu
@@ -102,7 +112,7 @@ private:
     bool cand_in_x_ = true;       // the latest candidate's values live in x_ (start point / just accepted)
 
     // reduction workspace + result mailbox
-    double *partials_ = nullptr, *grouprecs_ = nullptr, *vsums_ = nullptr, *out_dev_ = nullptr;
+    double *partials_ = nullptr, *vsums_ = nullptr, *out_dev_ = nullptr;
     unsigned *tickets_ = nullptr;
     double *out_host_ = nullptr;                     // mapped pinned
     unsigned long long *flag_host_ = nullptr;        // mapped pinned
@@ -119,8 +129,19 @@ private:
     double *pen_rows_ = nullptr;                     // augmented-Lagrangian objective: gradient rows of the folded constraints
     unsigned pen_total_ = 0;                         // their number (scalar constraints)
     double *scalar_dev_ = nullptr;                   // multi-rank device callbacks: value all-reduce
-    double pend_val_[1 + 32] = {};                   // shard-local values waiting for finish_evals()
-    unsigned long long pend_mask_ = 0;
+    std::vector<double> pend_val_;                   // shard-local values waiting for finish_evals()
+    std::vector<char> pend_set_;
+    bool pend_any_ = false;
+    size_t scalar_cap_ = 0;
+    // asynchronous device callbacks (nlopt_b200_dfunc2): [1+m][8] virtual-shard sums, device + pinned mirror
+    double *vs2_dev_ = nullptr, *vs2_host_ = nullptr;
+    size_t vs2_cap_ = 0;
+    std::vector<const FuncSpec *> pend2_;
+    bool pend2_any_ = false;
+    nlopt_b200_shard shard_{};
+    double *halo_edges_ = nullptr;
+    const double *halo_ptr_ = nullptr;
+    unsigned long long halo_epoch_ = 0;
     size_t shard_cap_ = 0;                           // largest padded shard length over all ranks
     unsigned long long x_epoch_ = 1, h_x_epoch_ = 0; // which (slot, epoch) h_x_ currently mirrors
     int h_x_slot_ = -1;

@@ -9,8 +9,10 @@
 // This file states that two-level recursion directly for the m' = 0 case, as an explicit state
 // machine (`DualMachine`): the caller evaluates F(trial()) -- one launch of the n-dimensional dual
 // kernel -- and feeds the value and gradient back; the machine answers with the next trial point
-// or with a result code.  The same code runs on the host (DualMMA::solve, the north_star default)
-// and, compiled by nvcc, inside the persistent dual-solve kernel (one launch per dual SOLVE).
+// or with a result code.  This is the HOST form (any m; DualMMA::solve drives it, one kernel launch per
+// evaluation).  The persistent dual-solve kernel carries the same algorithm as a warp-parallel,
+// register-resident machine (WarpDualMachine, ccsa_kernels.cuh: lane i owns multiplier i) that performs the
+// same IEEE operations in the same order -- tests/test_gpu_parity.py asserts bit-identical solves.
 //   DualMachine::feed  = mma.c:145-452 specialised to "no constraints, always feasible"
 //   DualMachine::step  = mma.c:59-137 with m = 0 (the level-3 evaluation)
 #pragma once
@@ -30,7 +32,6 @@ using std::sqrt;
 
 namespace nb200 {
 
-constexpr int kDualMaxM = 32;      // == kMaxParamM of ccsa_kernels.cuh
 
 inline double wall_seconds()
 {
@@ -61,11 +62,13 @@ enum { kRetSuccess = 1, kRetFtol = 3, kRetXtol = 4, kRetMaxeval = 5, kRetMaxtime
        kRetInvalid = -2 };
 
 struct DualMachine {
-    int m;
-    double y[kDualMaxM];            // accepted multipliers (in: warm start, out: result)
-    double g[kDualMaxM];            // gradient of F at y
-    double sigma[kDualMaxM], ycur[kDualMaxM], yprev[kDualMaxM], yprevprev[kDualMaxM];
-    double lo[kDualMaxM], hi[kDualMaxM];
+    int m = 0;
+    // m entries each, carved out of one block owned by the machine (no cap on m: the reference has none, mma.c:173)
+    double *y = nullptr;            // accepted multipliers (in: warm start, out: result)
+    double *g = nullptr;            // gradient of F at y
+    double *sigma = nullptr, *ycur = nullptr, *yprev = nullptr, *yprevprev = nullptr;
+    double *lo = nullptr, *hi = nullptr;
+    std::vector<double> store;
     double rho, fbase, fmin, fcur, fprev, gval, wval;
     unsigned k;
     long nevals;
@@ -74,9 +77,16 @@ struct DualMachine {
     DualStop st;
 
     // returns kRetSuccess when an evaluation at trial() is wanted, else the final code (kRetInvalid)
-    NB_HD int start(int m_, const double *y0, const double *lo_, const double *hi_, const DualStop &stop)
+    int start(int m_, const double *y0, const double *lo_, const double *hi_, const DualStop &stop)
     {
         m = m_;
+        store.assign(8 * (size_t) (m > 0 ? m : 1), 0.0);
+        {
+            double *p = store.data();
+            const size_t mm = (size_t) (m > 0 ? m : 1);
+            y = p; g = p + mm; sigma = p + 2 * mm; ycur = p + 3 * mm; yprev = p + 4 * mm; yprevprev = p + 5 * mm;
+            lo = p + 6 * mm; hi = p + 7 * mm;
+        }
         st = stop;
         ret = kRetSuccess;
         nevals = 0;
@@ -92,11 +102,11 @@ struct DualMachine {
         return ret;
     }
 
-    NB_HD const double *trial() const { return awaiting_first ? y : ycur; }
+    const double *trial() const { return awaiting_first ? y : ycur; }
 
     // Feed F(trial()) and its gradient; `elapsed` = seconds since start().  Returns true when finished
     // (result code in ret, multipliers in y, best value in fmin).
-    NB_HD bool feed(double F, const double *grad, double elapsed)
+    bool feed(double F, const double *grad, double elapsed)
     {
         if (feed_pre(F, grad, elapsed)) return true;
         step();
@@ -105,7 +115,7 @@ struct DualMachine {
 
     // feed() without the closing step(): a warp runs step_term(i) on m lanes side by side and then
     // step_sum() on one (same operations in the same order => same bits as step()).
-    NB_HD bool feed_pre(double F, const double *grad, double elapsed)
+    bool feed_pre(double F, const double *grad, double elapsed)
     {
         if (awaiting_first) {                            // mma.c:218
             awaiting_first = 0;
@@ -134,7 +144,7 @@ struct DualMachine {
 
     // Term i of the MMA dual evaluation with zero constraints on the m dual variables (mma.c:59-137, m = 0):
     // ycur_i <- argmin of the separable approximant around y; false: sigma_i == 0, no contribution.
-    NB_HD bool step_term(int i, double *gterm, double *wterm)
+    bool step_term(int i, double *gterm, double *wterm)
     {
         const double s = sigma[i];
         if (s == 0) { ycur[i] = y[i]; return false; }
@@ -158,7 +168,7 @@ struct DualMachine {
     }
 
     // gval / wval as at mma.c:123-125: the terms added in index order
-    NB_HD void step_sum(const double *gterm, const double *wterm, const int *has)
+    void step_sum(const double *gterm, const double *wterm, const int *has)
     {
         double gs = fbase, ws = 0;
         for (int i = 0; i < m; ++i)
@@ -168,14 +178,14 @@ struct DualMachine {
     }
 
 private:
-    NB_HD bool limits_hit(double elapsed)
+    bool limits_hit(double elapsed)
     {
         if (st.maxeval > 0 && nevals >= st.maxeval) ret = kRetMaxeval;       // stopval is -inf: never reached
         else if (st.maxtime > 0 && elapsed >= st.maxtime) ret = kRetMaxtime;
         return ret != kRetSuccess;
     }
 
-    NB_HD bool outer_top(double elapsed)                 // mma.c:255-265
+    bool outer_top(double elapsed)                 // mma.c:255-265
     {
         fprev = fcur;
         if (limits_hit(elapsed)) return true;
@@ -185,7 +195,7 @@ private:
         return false;
     }
 
-    NB_HD bool outer_end()                               // mma.c:418-446
+    bool outer_end()                               // mma.c:418-446
     {
         if (rel_stop(fprev, fcur, st.ftol_rel, st.ftol_abs)) ret = kRetFtol;
         if (x_converged()) ret = kRetXtol;
@@ -205,7 +215,7 @@ private:
         return false;
     }
 
-    NB_HD void step()
+    void step()
     {
         double gs = fbase, ws = 0;
         for (int i = 0; i < m; ++i) {
@@ -218,7 +228,7 @@ private:
 
     // nlopt_stop_x on (ycur, yprev) with unit weights and a uniform xtol_abs (stop.c:98-108).
     // The dual object always carries an xtol_abs array (nlopt_set_xtol_abs1, optimize.c:825).
-    NB_HD bool x_converged() const
+    bool x_converged() const
     {
         double dn = 0, xn = 0;
         for (int i = 0; i < m; ++i) dn += fabs(ycur[i] - yprev[i]);
@@ -241,7 +251,6 @@ public:
     int solve(Eval &&eval, double *y, const double *lo, const double *hi, const DualStop &st,
               double *fmin_out, long *nevals_out)
     {
-        if (m_ > (unsigned) kDualMaxM) return kRetInvalid;
         const double t0 = wall_seconds();
         int rc = mach_.start((int) m_, y, lo, hi, st);
         if (rc != kRetSuccess) return rc;

@@ -27,22 +27,42 @@ struct Geometry {
     unsigned long long j0 = 0, n_local = 0;      // this rank's variable range
     unsigned long long ld = 0;                   // padded local length: whole chunks (multiple of 512 doubles)
 
-    // tuning constant of choose_P (process-wide): groups wanted before groups start to grow
-    static unsigned &fill_div() { static unsigned v = 888; return v; }
+    // tuning constants of choose_P (process-wide)
+    static unsigned &fill_div() { static unsigned v = 888; return v; }      // rule 0: groups wanted before groups start to grow
+    static unsigned &group_base() { static unsigned v = 440; return v; }    // rule 1: see below
+    static int &rule() { static int v = 1; return v; }
 
     static unsigned long long cut(unsigned s, unsigned long long nchunks, unsigned S)
     {
         return (unsigned long long) s * nchunks / S;
     }
 
-    // Group size: `target_chunks` chunks for large n, fewer for small n so that there are still enough
-    // groups (about 1000: measured optimum at n = 1e6..3e6, profiles/r01_summary.md) to fill the machine; P = groups per virtual shard, capped at pmax.
+    // Number of groups S = 8 P as a function of n alone.
+    // Rule 1 (default).  The persistent kernels run 3 CTAs on each of the 148 SMs: 443 sweepers + the folder.  A rank
+    // owns S / world groups per generation, so S is chosen from base * {1, 2, 4, 8} with base = 440: 1, 2, 4 or 8 ranks
+    // then see a whole number of sweeper "waves" (3520 groups: 7.95 / 3.97 / 1.99 / 0.99 waves) -- the largest such S
+    // that keeps a group at two chunks or more.  Large n (groups would exceed `target_chunks` chunks): S = nchunks /
+    // target_chunks, small groups even out the tail of a generation.  Small n: one chunk per group.
+    // Rule 0 (round 1): about 1000 groups for mid-size n, `target_chunks` chunks per group for large n.
     static unsigned choose_P(unsigned long long nchunks, unsigned target_chunks, unsigned pmax)
     {
-        unsigned long long fill = nchunks / fill_div();
-        if (fill < 1) fill = 1;
-        if (fill < target_chunks) target_chunks = (unsigned) fill;
-        unsigned long long want = (nchunks + (unsigned long long) kV * target_chunks - 1) / ((unsigned long long) kV * target_chunks);
+        unsigned long long want;
+        if (rule() == 0) {
+            unsigned long long fill = nchunks / fill_div();
+            if (fill < 1) fill = 1;
+            if (fill < target_chunks) target_chunks = (unsigned) fill;
+            want = (nchunks + (unsigned long long) kV * target_chunks - 1) / ((unsigned long long) kV * target_chunks);
+        } else {
+            const unsigned long long base = group_base() / kV ? group_base() / kV : 1;      // P of the smallest candidate
+            const unsigned long long big = (nchunks + (unsigned long long) kV * target_chunks - 1) / ((unsigned long long) kV * target_chunks);
+            if (big >= 8 * base) want = big;
+            else {
+                want = 0;
+                for (unsigned long long f = 8; f >= 1; f >>= 1)
+                    if (kV * base * f * 2 <= nchunks) { want = base * f; break; }
+                if (!want) want = nchunks / kV < base ? nchunks / kV : base;               // one chunk (or less) per group
+            }
+        }
         if (want < 1) want = 1;
         if (want > pmax) want = pmax;
         return (unsigned) want;

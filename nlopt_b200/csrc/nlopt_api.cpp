@@ -294,6 +294,9 @@ static nlopt_result set_objective(nlopt_opt opt, nlopt_func f, nlopt_b200_dfunc 
     if (opt->munge_on_destroy) opt->munge_on_destroy(opt->f_data);
     opt->f = f;
     opt->df = df;
+    opt->df2 = nullptr;
+    opt->dfin = nullptr;
+    opt->halo = 0;
     opt->f_data = data;
     opt->pre = pre;
     opt->maximize = maximize;
@@ -314,6 +317,20 @@ nlopt_result nlopt_set_max_objective(nlopt_opt opt, nlopt_func f, void *d)
 { return set_objective(opt, f, nullptr, nullptr, d, 1); }
 nlopt_result nlopt_b200_set_min_objective_device(nlopt_opt opt, nlopt_b200_dfunc f, void *d)
 { return set_objective(opt, nullptr, f, nullptr, d, 0); }
+
+/* marker stored in the `df` field of callbacks registered in the asynchronous form: never called */
+static double df2_marker(unsigned, unsigned long long, const double *, double *, void *, void *) { return 0.0; }
+
+nlopt_result nlopt_b200_set_min_objective_device2(nlopt_opt opt, nlopt_b200_dfunc2 f, nlopt_b200_dfinish fin, void *d, int halo)
+{
+    if (!f || !fin || halo < 0 || halo > 1) return NLOPT_INVALID_ARGS;
+    nlopt_result r = set_objective(opt, nullptr, df2_marker, nullptr, d, 0);
+    if (r < 0) return r;
+    opt->df2 = f;
+    opt->dfin = fin;
+    opt->halo = halo;
+    return r;
+}
 
 nlopt_algorithm nlopt_get_algorithm(const nlopt_opt opt) { return opt->algorithm; }
 unsigned nlopt_get_dimension(const nlopt_opt opt) { return opt->n; }
@@ -484,6 +501,18 @@ nlopt_result nlopt_add_inequality_constraint(nlopt_opt opt, nlopt_func fc, void 
 { return add_any(opt, false, false, 1, fc, nullptr, nullptr, nullptr, d, &tol); }
 nlopt_result nlopt_b200_add_inequality_constraint_device(nlopt_opt opt, nlopt_b200_dfunc fc, void *d, double tol)
 { return add_any(opt, false, false, 1, nullptr, nullptr, fc, nullptr, d, &tol); }
+nlopt_result nlopt_b200_add_inequality_constraint_device2(nlopt_opt opt, nlopt_b200_dfunc2 fc, nlopt_b200_dfinish fin, void *d,
+                                                          double tol, int halo)
+{
+    if (!fc || !fin || halo < 0 || halo > 1) return NLOPT_INVALID_ARGS;
+    nlopt_result r = add_any(opt, false, false, 1, nullptr, nullptr, df2_marker, nullptr, d, &tol);
+    if (r < 0) return r;
+    nb200::ConstraintRec &c = opt->fc.back();
+    c.df2 = fc;
+    c.dfin = fin;
+    c.halo = halo;
+    return r;
+}
 nlopt_result nlopt_add_equality_mconstraint(nlopt_opt opt, unsigned m, nlopt_mfunc h, void *d, const double *tol)
 { return add_any(opt, true, true, m, nullptr, h, nullptr, nullptr, d, tol); }
 nlopt_result nlopt_add_precond_equality_constraint(nlopt_opt opt, nlopt_func h, nlopt_precond pre, void *d, double tol)
@@ -892,12 +921,15 @@ nlopt_result run_ccsa(nlopt_opt opt, double *x_host, double *x_dev, double *minf
     cfg.n = n;
     cfg.objective.f = opt->f;
     cfg.objective.df = opt->df;
+    cfg.objective.df2 = opt->df2;
+    cfg.objective.dfin = opt->dfin;
+    cfg.objective.halo = opt->halo;
     cfg.objective.data = opt->f_data;
     cfg.penalty = opt->penalty;
     std::vector<double> tol;
     for (const auto &c : opt->fc) {
         nb200::FuncSpec s;
-        s.m = c.m; s.f = c.f; s.mf = c.mf; s.df = c.df; s.data = c.f_data;
+        s.m = c.m; s.f = c.f; s.mf = c.mf; s.df = c.df; s.df2 = c.df2; s.dfin = c.dfin; s.halo = c.halo; s.data = c.f_data;
         cfg.constraints.push_back(s);
         tol.insert(tol.end(), c.tol.begin(), c.tol.end());
     }
@@ -923,6 +955,8 @@ nlopt_result run_ccsa(nlopt_opt opt, double *x_host, double *x_dev, double *minf
     opt->stats.seconds_setup = nb200::wall_seconds() - t0;
 
     /* library-specific knobs ride on the named-parameter mechanism (no ABI change) */
+    if (nlopt_has_param(opt, "b200_geometry_rule")) be->configure("geometry_rule", (long long) nlopt_get_param(opt, "b200_geometry_rule", 1.0));
+    if (nlopt_has_param(opt, "b200_group_base")) be->configure("group_base", (long long) nlopt_get_param(opt, "b200_group_base", 440.0));
     if (nlopt_get_param(opt, "b200_time_kernels", 0.0) != 0.0) be->configure("time_kernels", 1);
     if (nlopt_has_param(opt, "b200_pmax")) be->configure("pmax", (long long) nlopt_get_param(opt, "b200_pmax", 0.0));
     if (nlopt_has_param(opt, "b200_target_chunks"))
@@ -930,6 +964,8 @@ nlopt_result run_ccsa(nlopt_opt opt, double *x_host, double *x_dev, double *minf
     prm.fused_solve = (int) nlopt_get_param(opt, "b200_fused_solve", 1.0);
     if (nlopt_has_param(opt, "b200_kernel_cfg")) be->configure("kernel_cfg", (long long) nlopt_get_param(opt, "b200_kernel_cfg", 0.0));
     if (nlopt_has_param(opt, "b200_ctas_per_sm")) be->configure("ctas_per_sm", (long long) nlopt_get_param(opt, "b200_ctas_per_sm", 0.0));
+    if (nlopt_has_param(opt, "b200_prefetch_chunks")) be->configure("prefetch_chunks", (long long) nlopt_get_param(opt, "b200_prefetch_chunks", 0.0));
+    if (nlopt_has_param(opt, "b200_l2_keep_mb")) be->configure("l2_keep_mb", (long long) nlopt_get_param(opt, "b200_l2_keep_mb", 0.0));
 
     nb200::StopCriteria st;                          /* optimize.c:553-566 */
     st.minf_max = opt->stopval;

@@ -18,6 +18,9 @@ struct ConstraintRec {
     nlopt_func f = nullptr;         // scalar host callback
     nlopt_mfunc mf = nullptr;       // vector host callback
     nlopt_b200_dfunc df = nullptr;  // scalar device callback (extension)
+    nlopt_b200_dfunc2 df2 = nullptr;    // asynchronous form (df then holds a marker)
+    nlopt_b200_dfinish dfin = nullptr;
+    int halo = 0;
     nlopt_precond pre = nullptr;
     void *f_data = nullptr;
     std::vector<double> tol;        // m feasibility tolerances
@@ -36,6 +39,9 @@ struct nlopt_opt_s {
 
     nlopt_func f = nullptr;
     nlopt_b200_dfunc df = nullptr;
+    nlopt_b200_dfunc2 df2 = nullptr;
+    nlopt_b200_dfinish dfin = nullptr;
+    int halo = 0;
     void *f_data = nullptr;
     nlopt_precond pre = nullptr;
     int maximize = 0;

@@ -12,6 +12,7 @@
 // (numpy), so device gradients are bit-identical to the host callbacks' gradients.
 #include <chrono>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -28,17 +29,18 @@ struct Tick {
 
 // ---- device functors ---------------------------------------------------------------------------------
 struct RosenbrockDev {
-    __device__ double operator()(unsigned long long j, unsigned long long n, long long jl, long long n_local,
+    static constexpr int halo = 1;           // reads x[jl - 1] and x[jl + 1] across shard boundaries
+    __device__ double operator()(unsigned long long j, unsigned long long n, long long jl, long long,
                                  const double *x, double *grad_j) const
     {
         const double xj = x[jl];
         double term = 0.0, gsum = 0.0;
-        if (j + 1 < n && jl + 1 < n_local) {
+        if (j + 1 < n) {
             const double d = __dsub_rn(x[jl + 1], __dmul_rn(xj, xj)), e = __dsub_rn(1.0, xj);
             term = __dadd_rn(__dmul_rn(__dmul_rn(100.0, d), d), __dmul_rn(e, e));
             gsum = __dadd_rn(0.0, __dsub_rn(__dmul_rn(__dmul_rn(-400.0, xj), d), __dmul_rn(2.0, e)));
         }
-        if (jl > 0) {
+        if (j > 0) {
             const double xm = x[jl - 1];
             gsum = __dadd_rn(gsum, __dmul_rn(200.0, __dsub_rn(xj, __dmul_rn(xm, xm))));
         }
@@ -76,6 +78,24 @@ struct QuadraticDev {
     double finish(double s) const { return 0.5 * s; }
 };
 
+// synthetic SIMP compliance (BASELINE config 4): f(x) = sum_j a_j / (eps + (1 - eps) x_j^3),
+// a_j = 0.5 + u01(seed, 0, j).  Same expression order as nb200p_simp_host below.
+struct SimpDev {
+    unsigned long long seed;
+    double eps;
+    __device__ double operator()(unsigned long long j, unsigned long long, long long jl, long long, const double *x,
+                                 double *grad_j) const
+    {
+        const double a = __dadd_rn(0.5, nb200::u01(seed, 0, j));
+        const double xj = x[jl], x2 = __dmul_rn(xj, xj), x3 = __dmul_rn(x2, xj);
+        const double ome = __dsub_rn(1.0, eps);
+        const double d = __dadd_rn(eps, __dmul_rn(ome, x3));
+        if (grad_j) *grad_j = -__ddiv_rn(__dmul_rn(__dmul_rn(a, __dmul_rn(ome, 3.0)), x2), __dmul_rn(d, d));
+        return __ddiv_rn(a, d);
+    }
+    double finish(double s) const { return s; }
+};
+
 struct MeanDev {
     double inv_n, offset;
     __device__ double operator()(unsigned long long, unsigned long long, long long jl, long long, const double *x,
@@ -99,6 +119,10 @@ struct nb200p_quad_data {
 struct nb200p_mean_data {
     double offset;
 };
+struct nb200p_simp_data {
+    unsigned long long seed;
+    double eps;
+};
 
 struct nb200p_problem_s {
     RosenbrockDev rosen;
@@ -107,6 +131,8 @@ struct nb200p_problem_s {
     std::vector<MeanDev *> mean;
     std::vector<double *> dev_rows;
     std::vector<nb200p_lin_data *> lin_host;
+    SimpDev simp;
+    std::vector<void *> misc_host;          // small data records of the host callbacks (freed with the problem)
 };
 
 extern "C" {
@@ -120,6 +146,7 @@ void nb200p_destroy(nb200p_problem_s *p)
     for (LinearDev *l : p->lin) delete l;
     for (MeanDev *m : p->mean) delete m;
     for (nb200p_lin_data *l : p->lin_host) delete l;
+    for (void *q : p->misc_host) std::free(q);
     delete p;
 }
 
@@ -159,7 +186,55 @@ int nb200p_add_mean_device(nb200p_problem_s *p, nlopt_opt opt, double offset, do
     return nlopt_b200::add_inequality_constraint(opt, m, tol);
 }
 
+int nb200p_set_simp_device(nb200p_problem_s *p, nlopt_opt opt, unsigned long long seed, double eps)
+{
+    p->simp.seed = seed;
+    p->simp.eps = eps;
+    return nlopt_b200::set_min_objective(opt, &p->simp);
+}
+
 // ---- host callbacks (nlopt_func shape; work with any NLopt-ABI library) ----------------------------------
+double nb200p_simp_host(unsigned n, const double *x, double *grad, void *data)
+{
+    Tick t;
+    const nb200p_simp_data *sd = static_cast<const nb200p_simp_data *>(data);
+    const double ome = 1.0 - sd->eps;
+    double f = 0.0;
+    for (unsigned j = 0; j < n; ++j) {
+        const double a = 0.5 + nb200::u01(sd->seed, 0, j);
+        const double x2 = x[j] * x[j], x3 = x2 * x[j];
+        const double d = sd->eps + ome * x3;
+        if (grad) grad[j] = -(((a * (ome * 3.0)) * x2) / (d * d));
+        f += a / d;
+    }
+    return f;
+}
+
+void *nb200p_make_simp_data(nb200p_problem_s *p, unsigned long long seed, double eps)
+{
+    nb200p_simp_data *d = static_cast<nb200p_simp_data *>(std::malloc(sizeof(nb200p_simp_data)));
+    d->seed = seed;
+    d->eps = eps;
+    p->misc_host.push_back(d);
+    return d;
+}
+
+void *nb200p_make_mean_data(nb200p_problem_s *p, double offset)
+{
+    nb200p_mean_data *d = static_cast<nb200p_mean_data *>(std::malloc(sizeof(nb200p_mean_data)));
+    d->offset = offset;
+    p->misc_host.push_back(d);
+    return d;
+}
+
+void *nb200p_make_quad_data(nb200p_problem_s *p, unsigned long long seed)
+{
+    nb200p_quad_data *d = static_cast<nb200p_quad_data *>(std::malloc(sizeof(nb200p_quad_data)));
+    d->seed = seed;
+    p->misc_host.push_back(d);
+    return d;
+}
+
 double nb200p_rosenbrock_host(unsigned n, const double *x, double *grad, void *)
 {
     Tick t;

@@ -25,6 +25,11 @@ def _load():
     L.nb200p_add_mean_device.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_double]
     L.nb200p_make_linear_data.restype = C.c_void_p
     L.nb200p_make_linear_data.argtypes = [C.c_void_p, c_double_p, C.c_double]
+    L.nb200p_set_simp_device.argtypes = [C.c_void_p, C.c_void_p, C.c_ulonglong, C.c_double]
+    for nm, args in (("nb200p_make_simp_data", [C.c_void_p, C.c_ulonglong, C.c_double]),
+                     ("nb200p_make_mean_data", [C.c_void_p, C.c_double]), ("nb200p_make_quad_data", [C.c_void_p, C.c_ulonglong])):
+        getattr(L, nm).restype = C.c_void_p
+        getattr(L, nm).argtypes = args
     return L
 
 
@@ -86,6 +91,26 @@ class Problem:
             self._keep.append(w)
             d = self.L.nb200p_make_linear_data(self.h, w.ctypes.data_as(c_double_p), 0.5 + 0.1 * k)
             opt._check(lib_.nlopt_add_inequality_constraint(opt._h, self._fn("nb200p_linear_host"), d, tol))
+
+    def simp_host(self, opt, seed=0x5EED0000, eps=1e-3, vol=0.4, tol=0.0):
+        """BASELINE config 4: synthetic SIMP compliance + volume constraint, plain C host callbacks"""
+        lib_ = opt._lib
+        d = self.L.nb200p_make_simp_data(self.h, seed, eps)
+        opt._check(lib_.nlopt_set_min_objective(opt._h, self._fn("nb200p_simp_host"), d))
+        dm = self.L.nb200p_make_mean_data(self.h, -vol)
+        opt._check(lib_.nlopt_add_inequality_constraint(opt._h, self._fn("nb200p_mean_host"), dm, tol))
+
+    def simp_device(self, opt, seed=0x5EED0000, eps=1e-3, vol=0.4, tol=0.0):
+        opt._check(self.L.nb200p_set_simp_device(self.h, opt._h, seed, eps))
+        opt._check(self.L.nb200p_add_mean_device(self.h, opt._h, -vol, tol))
+
+    def quadratic_host(self, opt, seed=0x5EED0000, offset=0.1, tol=0.0):
+        """BASELINE config 2 with host callbacks (the device form is quadratic_device)"""
+        lib_ = opt._lib
+        d = self.L.nb200p_make_quad_data(self.h, seed)
+        opt._check(lib_.nlopt_set_min_objective(opt._h, self._fn("nb200p_quadratic_host"), d))
+        dm = self.L.nb200p_make_mean_data(self.h, offset)
+        opt._check(lib_.nlopt_add_inequality_constraint(opt._h, self._fn("nb200p_mean_host"), dm, tol))
 
     def callback_seconds(self):
         return self.L.nb200p_callback_seconds()

@@ -17,6 +17,17 @@
 
 #define RHO_FLOOR 1e-5 /* MMA_RHOMIN / CCSA_RHOMIN, mma.c:41, ccsa_quadratic.c:58 */
 
+/* The n-term sums of the dual functions are accumulated in `acc_t`.  The default build uses double, like the
+ * reference (bit-identical to oracle/_ref).  -DPORT_WIDE_SUMS (tools/noise_floor_c3.py only) accumulates in the x87
+ * 80-bit format: the same per-variable terms, a nearly exact sum -- it measures how far the reference's own
+ * sequential double summation moves a run at large n (the noise floor end-to-end comparisons are judged against). */
+#ifdef PORT_WIDE_SUMS
+typedef long double acc_t;
+#define PORT_MAX_WIDE_M 64
+#else
+typedef double acc_t;
+#endif
+
 /* ------------------------------------------------------------------ */
 /* small predicates (stop.c:219-228, :254-263)                         */
 
@@ -45,14 +56,20 @@ double port_dual_mma(const port_dual_in *in, const double *y, double *grad, port
 {
     const unsigned n = in->n, m = in->m;
     unsigned i, j;
-    double val, gsum, wsum;
+    acc_t val, gsum, wsum;
+#ifdef PORT_WIDE_SUMS
+    acc_t gcw[PORT_MAX_WIDE_M];
+#define GC(i) gcw[i]
+#else
+#define GC(i) out->gc[i]
+#endif
 
     /* mma.c:75-78: a NaN constraint value switches that constraint off */
     val = gsum = in->f0;
     wsum = 0;
     for (i = 0; i < m; ++i) {
-        out->gc[i] = is_nan(in->c0[i]) ? 0 : in->c0[i];
-        val += y[i] * out->gc[i];
+        GC(i) = is_nan(in->c0[i]) ? 0 : in->c0[i];
+        val += y[i] * (double) GC(i);
     }
 
     for (j = 0; j < n; ++j) {
@@ -98,15 +115,18 @@ double port_dual_mma(const port_dual_in *in, const double *y, double *grad, port
         for (i = 0; i < m; ++i)
             if (!is_nan(in->c0[i])) {
                 const double a = in->grad_c[(size_t) i * n + j];
-                out->gc[i] += (a * c + (fabs(a) * sj + 0.5 * in->rhoc[i]) * dx2) * dinv;
+                GC(i) += (a * c + (fabs(a) * sj + 0.5 * in->rhoc[i]) * dx2) * dinv;
             }
     }
-    out->g0 = gsum;
-    out->w = wsum;
+    out->g0 = (double) gsum;
+    out->w = (double) wsum;
+#ifdef PORT_WIDE_SUMS
+    for (i = 0; i < m; ++i) out->gc[i] = (double) gcw[i];
+#endif
     /* mma.c:135-136: we maximise the dual, so hand back the negation */
     if (grad)
         for (i = 0; i < m; ++i) grad[i] = -out->gc[i];
-    return -val;
+    return -(double) val;
 }
 
 /* ------------------------------------------------------------------ */
@@ -116,14 +136,17 @@ double port_dual_ccsaq(const port_dual_in *in, const double *y, double *grad, po
 {
     const unsigned n = in->n, m = in->m;
     unsigned i, j;
-    double val, gsum, wsum;
+    acc_t val, gsum, wsum;
+#ifdef PORT_WIDE_SUMS
+    acc_t gcw[PORT_MAX_WIDE_M];
+#endif
 
     /* ccsa_quadratic.c:95-98 (no NaN handling in this flavour) */
     val = gsum = in->f0;
     wsum = 0;
     for (i = 0; i < m; ++i) {
-        out->gc[i] = in->c0[i];
-        val += y[i] * out->gc[i];
+        GC(i) = in->c0[i];
+        val += y[i] * (double) GC(i);
     }
 
     for (j = 0; j < n; ++j) {
@@ -158,14 +181,18 @@ double port_dual_ccsaq(const port_dual_in *in, const double *y, double *grad, po
         gsum += gj * dx + in->rho * q;
         wsum += q;
         for (i = 0; i < m; ++i)
-            out->gc[i] += in->grad_c[(size_t) i * n + j] * dx + in->rhoc[i] * q;
+            GC(i) += in->grad_c[(size_t) i * n + j] * dx + in->rhoc[i] * q;
     }
-    out->g0 = gsum;
-    out->w = wsum;
+    out->g0 = (double) gsum;
+    out->w = (double) wsum;
+#ifdef PORT_WIDE_SUMS
+    for (i = 0; i < m; ++i) out->gc[i] = (double) gcw[i];
+#endif
     if (grad)
         for (i = 0; i < m; ++i) grad[i] = -out->gc[i];
-    return -val;
+    return -(double) val;
 }
+#undef GC
 
 /* ------------------------------------------------------------------ */
 /* sigma handling -- mma.c:202-210 and :431-442, ccsa_quadratic.c:324-332, :577-590 */

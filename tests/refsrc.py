@@ -59,3 +59,33 @@ def compile_reference_testopt(libpath, outdir):
            os.path.join(REF, "src", "util", "mt19937ar.c"), "-o", exe, f"-L{libdir}", f"-l:{libfile}", f"-Wl,-rpath,{libdir}", "-lm"]
     subprocess.check_call(cmd)
     return exe
+
+
+REFPROG_DIR = os.path.join(ROOT, "tests", "_build", "refprog")
+
+
+def build_reference_programs_for_gpu():
+    """The reference's own test programs -- test/t_tutorial.cxx and test/cpp_functor.cxx over the reference-generated
+    nlopt.hpp, and the benchmark driver test/testopt.c -- compiled UNMODIFIED, where the sources lie, with `-lnlopt`
+    against this repository's libnlopt.so.1 (nlopt_b200/compat).  Outputs go to tests/_build/refprog (git-ignored; it
+    travels to the GPU box with the snapshot, where tests/test_dropin_gpu.py runs them on the CUDA library).  The
+    run-time search path is relative ($ORIGIN), so the binaries work from any checkout location."""
+    if not available():
+        return []
+    compat = os.path.join(ROOT, "nlopt_b200", "compat")
+    os.makedirs(REFPROG_DIR, exist_ok=True)
+    generate_hpp(REFPROG_DIR)
+    rpath = "-Wl,-rpath,$ORIGIN/../../../nlopt_b200/compat"
+    out = []
+    for name in ("t_tutorial.cxx", "cpp_functor.cxx"):
+        exe = os.path.join(REFPROG_DIR, os.path.splitext(name)[0])
+        subprocess.check_call(["g++", "-O1", "-std=c++11", f"-I{REFPROG_DIR}", f"-I{os.path.join(REF, 'src', 'api')}",
+                               os.path.join(REF, "test", name), "-o", exe, f"-L{compat}", "-lnlopt", rpath])
+        out.append(exe)
+    exe = os.path.join(REFPROG_DIR, "testopt")
+    subprocess.check_call(["gcc", "-O1", "-DHAVE_GETOPT", "-DHAVE_GETOPT_H", f"-I{REF}/src/api", f"-I{REF}/src/util",
+                           f"-I{os.path.join(ROOT, 'oracle', 'ref_config')}", os.path.join(REF, "test", "testopt.c"),
+                           os.path.join(REF, "test", "testfuncs.c"), os.path.join(REF, "src", "util", "timer.c"),
+                           os.path.join(REF, "src", "util", "mt19937ar.c"), "-o", exe, f"-L{compat}", "-lnlopt", rpath, "-lm"])
+    out.append(exe)
+    return out

@@ -50,8 +50,10 @@ def check_dual(variant, inst, y=None, pmax=None):
 
 @pytest.mark.parametrize("variant", [ob.MMA, ob.CCSAQ])
 @pytest.mark.parametrize("n,m", [(1, 0), (2, 2), (3, 1), (5, 2), (255, 3), (4097, 4), (100001, 1), (100000, 4),
-                                 (250000, 8), (60000, 16), (30000, 5), (20000, 12), (9999, 20), (5000, 32)])
+                                 (250000, 8), (60000, 16), (30000, 5), (20000, 12), (9999, 20), (5000, 32),
+                                 (7001, 17), (40000, 33), (30000, 64), (12345, 100), (3000, 257)])
 def test_dual_kernel_vs_oracle(built, variant, n, m):
+    """m <= 16: register-row kernels; m > 16: the wide kernel (no cap on m, like mma.c:173)."""
     check_dual(variant, synth.kernel_instance(n, m))
 
 
@@ -106,6 +108,40 @@ def test_dual_kernel_nan_constraint_mma(built):
     inst["c0"] = np.array([-0.1, np.nan, 0.2])
     got = check_dual(ob.MMA, inst)
     assert got["gc"][1] == 0.0
+    # the same rule in the wide kernel (per-row flags instead of a bit mask)
+    inst = synth.kernel_instance(20000, 40)
+    inst["c0"][[3, 17, 39]] = np.nan
+    got = check_dual(ob.MMA, inst)
+    assert got["gc"][3] == 0.0 and got["gc"][17] == 0.0 and got["gc"][39] == 0.0
+
+
+@pytest.mark.parametrize("variant", [ob.MMA, ob.CCSAQ])
+def test_wide_kernel_geometry_independence_and_special_lanes(built, variant):
+    n, m = 70001, 37
+    inst = synth.kernel_instance(n, m)
+    inst["sigma"][::7] = 0.0
+    inst["lb"][::7] = inst["x"][::7]; inst["ub"][::7] = inst["x"][::7]
+    inst["lb"][3::11] = -np.inf
+    inst["ub"][5::13] = np.inf
+    base = check_dual(variant, inst)
+    for cps in (1, 3):
+        h = DualHandle(variant, inst)
+        h.configure("ctas_per_sm", cps)
+        got = h.eval(inst["y"], want_xcur=True)
+        assert got["ret"] == base["ret"] and np.array_equal(got["gc"], base["gc"]) and np.array_equal(got["xcur"], base["xcur"])
+
+
+@pytest.mark.parametrize("variant", [ob.MMA, ob.CCSAQ])
+def test_l2_residency_hints_do_not_change_results(built, variant):
+    """b200_l2_keep_mb only changes the cache policy of the operand loads: every bit of the result stays."""
+    inst = synth.kernel_instance(300001, 4)
+    base = check_dual(variant, inst)
+    for mb in (3, 12, 100):
+        h = DualHandle(variant, inst)
+        h.configure("l2_keep_mb", mb)
+        assert h.query("l2_keep_mask") != 0
+        got = h.eval(inst["y"], want_xcur=True)
+        assert got["ret"] == base["ret"] and np.array_equal(got["gc"], base["gc"]) and np.array_equal(got["xcur"], base["xcur"])
 
 
 def test_dual_kernel_special_lanes(built):
@@ -380,6 +416,41 @@ def test_weights_abs_tolerance_vector_constraint_and_maximize_on_gpu(built):
         o.add_inequality_constraint(c, 1e-8)
     x = o.optimize(P.TUT_X0)
     assert np.array_equal(x, a["x"]) and o.last_optimum_value() == -a["minf"]
+
+
+@pytest.mark.parametrize("variant", [ob.MMA, ob.CCSAQ])
+def test_many_constraints_end_to_end_vs_oracle(built, variant):
+    """m = 40 > 32 (the cap of round 1; the reference has none, mma.c:173): whole runs through the wide kernel and the
+    host-driven dual optimiser against the oracle port."""
+    alg = nl.LD_MMA if variant == ob.MMA else nl.LD_CCSAQ
+    n, m = 6000, 40
+    cons = [P.lin_constraint(k, n) for k in range(m)]
+    lb, ub = np.full(n, -2.0), np.full(n, 2.0)
+    r = _run(alg, n, P.rosen_f, cons, [1e-8] * m, lb, ub, P.rosen_x0(n), maxeval=12)
+    ref = ob.port_minimize(variant, P.rosen_f, cons, [1e-8] * m, lb, ub, P.rosen_x0(n), maxeval=12)
+    assert r["ret"] == ref["ret"] and r["numevals"] == ref["numevals"]
+    assert abs(r["minf"] - ref["minf"]) <= 1e-6 * abs(ref["minf"])
+    assert np.max(np.abs(r["x"] - ref["x"])) <= 1e-5
+
+
+@pytest.mark.parametrize("variant", [ob.MMA, ob.CCSAQ])
+@pytest.mark.parametrize("opts", [dict(dual_ftol_rel=1e-6), dict(dual_xtol_rel=1e-5), dict(dual_xtol_abs=1e-7, dual_ftol_rel=0.0),
+                                  dict(dual_maxeval=7), dict(dual_ftol_abs=1e-9), dict(dual_maxeval=1)])
+def test_fused_solve_stop_rules_equal_host_driven(built, variant, opts):
+    """Every stopping rule of the dual optimiser (optimize.c:822-826) inside the persistent kernel -- the warp-parallel
+    machine's FTOL / XTOL / MAXEVAL exits -- against the host machine driving one launch per evaluation: bit-identical
+    runs, and the same runs as the oracle to the end-to-end tolerance."""
+    alg = nl.LD_MMA if variant == ob.MMA else nl.LD_CCSAQ
+    n, m = 30000, 4
+    cons = [P.lin_constraint(k, n) for k in range(m)]
+    lb, ub = np.full(n, -2.0), np.full(n, 2.0)
+    pair = [_run(alg, n, P.rosen_f, cons, [1e-8] * m, lb, ub, P.rosen_x0(n), maxeval=12, b200_fused_solve=f, **opts) for f in (1, 0)]
+    a, b = pair
+    assert a["ret"] == b["ret"] and a["numevals"] == b["numevals"] and a["minf"] == b["minf"] and np.array_equal(a["x"], b["x"])
+    assert a["opt"].get_stats()["dual_evals"] == b["opt"].get_stats()["dual_evals"]
+    ref = ob.port_minimize(variant, P.rosen_f, cons, [1e-8] * m, lb, ub, P.rosen_x0(n), maxeval=12, **opts)
+    assert a["ret"] == ref["ret"] and a["numevals"] == ref["numevals"]
+    assert abs(a["minf"] - ref["minf"]) <= 1e-6 * abs(ref["minf"])
 
 
 def test_device_path_has_no_cpu_fallback_symbols(built):
