@@ -241,6 +241,16 @@ nlopt_result nlopt_b200_set_min_objective_device2(nlopt_opt opt, nlopt_b200_dfun
                                                   void *f_data, int halo);
 nlopt_result nlopt_b200_add_inequality_constraint_device2(nlopt_opt opt, nlopt_b200_dfunc2 fc, nlopt_b200_dfinish finish,
                                                           void *fc_data, double tol, int halo);
+/* Sharded HOST callbacks (one process per GPU): the callback sees only this rank's variables -- x_shard and grad_shard
+ * hold the n_local entries starting at global index j0 -- and returns its ADDITIVE contribution to the function value
+ * (a constant term is added by one rank only, e.g. the one with j0 == 0); the library sums the contributions over the
+ * ranks.  Compared with a plain nlopt_func on several ranks (every rank receives the full x and uploads its shard of the
+ * gradient) each rank moves n_local instead of n doubles per evaluation over PCIe, and the callback's work is divided
+ * by the number of ranks.  With one rank this is the plain callback with j0 = 0, n_local = n. */
+typedef double (*nlopt_b200_sfunc)(unsigned n_local, unsigned long long j0, unsigned long long n, const double *x_shard,
+                                   double *grad_shard, void *func_data);
+nlopt_result nlopt_b200_set_min_objective_sharded(nlopt_opt opt, nlopt_b200_sfunc f, void *f_data);
+nlopt_result nlopt_b200_add_inequality_constraint_sharded(nlopt_opt opt, nlopt_b200_sfunc fc, void *fc_data, double tol);
 /* like nlopt_optimize, but x_dev is a device array of this rank's shard (in/out) */
 nlopt_result nlopt_b200_optimize_device(nlopt_opt opt, double *x_dev, double *opt_f);
 

@@ -17,7 +17,7 @@ import ctypes as C
 
 import numpy as np
 
-from ._capi import (NLOPT_B200_DFUNC, NLOPT_FUNC, NLOPT_MFUNC, Library, Stats, c_double_p,
+from ._capi import (NLOPT_B200_DFUNC, NLOPT_FUNC, NLOPT_PRECOND, NLOPT_MFUNC, Library, Stats, c_double_p,
                     default_library)
 
 # --- algorithm ids (reference nlopt.h:72-154) ---------------------------------
@@ -135,6 +135,25 @@ class opt:
 
     def set_max_objective(self, f):
         self._check(self._lib.nlopt_set_max_objective(self._h, self._wrap_func(f), None))
+
+    # preconditioned forms (nlopt.h:70, options.c:322-337): pre(x, v, vpre) writes vpre = H(x) v
+    def _wrap_precond(self, pre):
+        def thunk(n, x, v, vpre, _data):
+            try:
+                pre(np.ctypeslib.as_array(x, shape=(n,)), np.ctypeslib.as_array(v, shape=(n,)), np.ctypeslib.as_array(vpre, shape=(n,)))
+            except BaseException as e:
+                self._exc = e
+                self._lib.nlopt_force_stop(self._h)
+
+        cb = NLOPT_PRECOND(thunk)
+        self._keep.append(cb)
+        return C.cast(cb, C.c_void_p)
+
+    def set_precond_min_objective(self, f, pre):
+        self._check(self._lib.nlopt_set_precond_min_objective(self._h, self._wrap_func(f), self._wrap_precond(pre), None))
+
+    def add_precond_inequality_constraint(self, fc, pre, tol=0.0):
+        self._check(self._lib.nlopt_add_precond_inequality_constraint(self._h, self._wrap_func(fc), self._wrap_precond(pre), None, float(tol)))
 
     def add_inequality_constraint(self, fc, tol=0.0):
         self._check(self._lib.nlopt_add_inequality_constraint(self._h, self._wrap_func(fc), None, float(tol)))

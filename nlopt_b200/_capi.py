@@ -15,6 +15,7 @@ c_double_p = C.POINTER(C.c_double)
 # callback shapes, reference nlopt.h:60-66
 NLOPT_FUNC = C.CFUNCTYPE(C.c_double, C.c_uint, c_double_p, c_double_p, C.c_void_p)
 NLOPT_MFUNC = C.CFUNCTYPE(None, C.c_uint, c_double_p, C.c_uint, c_double_p, c_double_p, C.c_void_p)
+NLOPT_PRECOND = C.CFUNCTYPE(None, C.c_uint, c_double_p, c_double_p, c_double_p, C.c_void_p)
 # extension: device callback (include/nlopt_b200.h)
 NLOPT_B200_DFUNC = C.CFUNCTYPE(C.c_double, C.c_uint, C.c_ulonglong, C.c_void_p, C.c_void_p,
                                C.c_void_p, C.c_void_p)
@@ -141,6 +142,8 @@ _EXT = {
     "nlopt_b200_add_inequality_constraint_device2":
         (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_int]),
     "nlopt_b200_shard_geometry": (None, [C.c_ulonglong, C.c_int, C.c_int, C.c_void_p]),
+    "nlopt_b200_set_min_objective_sharded": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "nlopt_b200_add_inequality_constraint_sharded": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double]),
     "nlopt_b200_optimize_device": (C.c_int, [C.c_void_p, C.c_void_p, c_double_p]),
     "nlopt_b200_get_stats": (C.c_int, [C.c_void_p, C.POINTER(Stats)]),
     "nlopt_b200_dual_create": (C.c_void_p, [C.c_int, C.c_uint, C.c_uint]),

@@ -21,6 +21,7 @@ struct FuncSpec {
     nlopt_b200_dfunc2 df2 = nullptr;         // asynchronous device callback (takes precedence over df) ...
     nlopt_b200_dfinish dfin = nullptr;       // ... and its host-side finish
     int halo = 0;
+    nlopt_b200_sfunc sf = nullptr;           // sharded host callback
     void *data = nullptr;
 };
 

@@ -219,6 +219,13 @@ void DeviceBackend::free_state()
     res_host_ = nullptr;
     wide_dev_ = nullptr;
     if (h_x_) BlockCache::get().give(true, (size_t) geo_.n * sizeof(double), h_x_);
+    if (h_xs_) BlockCache::get().give(true, (geo_.n_local ? geo_.n_local : 1) * sizeof(double), h_xs_);
+    for (int b = 0; b < 2; ++b) {
+        if (h_gs_[b]) BlockCache::get().give(true, (geo_.n_local ? geo_.n_local : 1) * sizeof(double), h_gs_[b]);
+        if (h_gs_done_[b]) cudaEventDestroy(h_gs_done_[b]);
+        h_gs_[b] = nullptr; h_gs_done_[b] = nullptr;
+    }
+    h_xs_ = nullptr;
     for (int b = 0; b < 2; ++b) {
         if (h_grad_[b]) BlockCache::get().give(true, h_grad_cap_ * sizeof(double), h_grad_[b]);
         if (h_grad_done_[b]) cudaEventDestroy(h_grad_done_[b]);
@@ -406,6 +413,16 @@ bool DeviceBackend::setup(const BackendConfig &cfg)
     if (cfg.penalty)
         for (int pass = 0; pass < 2; ++pass)
             for (const FuncSpec &c : (pass == 0 ? cfg.penalty->eq : cfg.penalty->ineq)) any_host_cb = any_host_cb || c.f || c.mf;
+    bool any_sharded_cb = cfg.objective.sf != nullptr;
+    for (const FuncSpec &c : cfg.constraints) any_sharded_cb = any_sharded_cb || c.sf;
+    if (any_sharded_cb) {
+        const size_t cap = geo_.n_local ? geo_.n_local : 1;
+        NB_CUDA(cached_host_alloc(&h_xs_, cap * sizeof(double)));
+        for (int b = 0; b < 2; ++b) {
+            NB_CUDA(cached_host_alloc(&h_gs_[b], cap * sizeof(double)));
+            NB_CUDA(cudaEventCreateWithFlags(&h_gs_done_[b], cudaEventDisableTiming));
+        }
+    }
     if (any_host_cb) {
         NB_CUDA(cached_host_alloc(&h_x_, (size_t) geo_.n * sizeof(double)));
         h_grad_cap_ = (size_t) max_cdim_ * geo_.n;
@@ -622,6 +639,7 @@ bool DeviceBackend::push_rows_to(double *dst, unsigned rows, const double *host_
 bool DeviceBackend::eval_user_objective(Slot slot, bool want_grad, double *value)
 {
     const FuncSpec &fs = cfg_.objective;
+    if (fs.sf) return eval_sharded(fs, slot, want_grad ? (slot == kBase ? g_ : gcur_) : nullptr, 0, value);
     if (fs.df2) {
         double *gs = want_grad ? (slot == kBase ? g_ : gcur_) : nullptr;
         *value = 0.0;                                  // settled in finish_evals()
@@ -654,6 +672,7 @@ bool DeviceBackend::eval_user_objective(Slot slot, bool want_grad, double *value
 bool DeviceBackend::eval_constraint(Slot slot, unsigned ic, unsigned row0, bool want_grad, double *values)
 {
     const FuncSpec &fs = cfg_.constraints[ic];
+    if (fs.sf) return eval_sharded(fs, slot, want_grad ? (slot == kBase ? G_ : Gcur_) + (size_t) row0 * geo_.ld : nullptr, 1 + row0, values);
     if (fs.df2) {
         double *gs = want_grad ? (slot == kBase ? G_ : Gcur_) + (size_t) row0 * geo_.ld : nullptr;
         values[0] = 0.0;
@@ -685,6 +704,45 @@ bool DeviceBackend::eval_constraint(Slot slot, unsigned ic, unsigned row0, bool 
 
 // Device callbacks on several ranks return shard-local values; one all-reduce settles every value of the point
 // (1 + m doubles; entries from host callbacks are global already and are not touched).
+// Sharded host callbacks (nlopt_b200_sfunc): this rank's n_local variables down, its n_local gradient entries up, the
+// additive value contribution settled with the others in finish_evals().
+bool DeviceBackend::eval_sharded(const FuncSpec &fs, Slot slot, double *grad_dst, unsigned index, double *value)
+{
+    const size_t nl = geo_.n_local;
+    const double *src = slot == kBase ? x_ : xcur_view();
+    if (!(h_xs_slot_ == (int) slot && h_xs_epoch_ == x_epoch_)) {
+        NB_CUDA(cudaMemcpyAsync(h_xs_, src, nl * sizeof(double), cudaMemcpyDeviceToHost, stream_));
+        NB_CUDA(cudaStreamSynchronize(stream_));
+        stats_->d2h_bytes += nl * sizeof(double);
+        h_xs_slot_ = (int) slot;
+        h_xs_epoch_ = x_epoch_;
+    }
+    double *grad = nullptr;
+    int b = 0;
+    if (grad_dst) {
+        b = h_gs_next_;
+        h_gs_next_ ^= 1;
+        cudaEventSynchronize(h_gs_done_[b]);      // the previous upload out of this buffer has finished
+        grad = h_gs_[b];
+    }
+    const double t0 = wall_seconds();
+    const double v = fs.sf((unsigned) nl, geo_.j0, geo_.n, h_xs_, grad, fs.data);
+    cb_seconds_ += wall_seconds() - t0;
+    if (grad_dst) {
+        NB_CUDA(cudaMemcpyAsync(grad_dst, grad, nl * sizeof(double), cudaMemcpyHostToDevice, copy_stream_));
+        NB_CUDA(cudaEventRecord(h_gs_done_[b], copy_stream_));
+        NB_CUDA(cudaStreamWaitEvent(stream_, h_gs_done_[b], 0));
+        stats_->h2d_bytes += nl * sizeof(double);
+    }
+    if (Comm::instance().active()) {
+        pend_val_[index] = v;
+        pend_set_[index] = 1;
+        pend_any_ = true;
+    }
+    *value = v;
+    return true;
+}
+
 // Asynchronous device callbacks (nlopt_b200_dfunc2): enqueue, remember which value is pending.
 bool DeviceBackend::enqueue_df2(const FuncSpec &fs, Slot slot, double *grad_dst, unsigned index)
 {
@@ -867,7 +925,8 @@ void DeviceBackend::fill_dual_args(DualArgs &a, const double *y, const DualScala
         for (int r = 0; r < 8; ++r) a.box[r] = (cm.active() && cm.use_p2p() && !wide && r < cm.world) ? cm.box_peer[r] : nullptr;
     }
     a.l2_keep = l2_keep_mask();
-    a.prefetch_chunks = prefetch_chunks_;
+    // the L2 prefetch of a waiting sweeper only pays when the operands of a generation do not stay in the L2 anyway
+    a.prefetch_chunks = (prefetch_forced_ || (5 + (size_t) m_) * geo_.ld * sizeof(double) >= (64u << 20)) ? prefetch_chunks_ : 0u;
     a.m = (int) m_;
     a.rho = sc.rho;
     a.half_rho = 0.5 * sc.rho;
@@ -1175,6 +1234,7 @@ void DeviceBackend::accept_candidate()
     std::swap(G_, Gcur_);
     cand_in_x_ = true;
     if (h_x_slot_ == (int) kCandidate && h_x_epoch_ == x_epoch_) h_x_slot_ = (int) kBase;   // same values, new name
+    if (h_xs_slot_ == (int) kCandidate && h_xs_epoch_ == x_epoch_) h_xs_slot_ = (int) kBase;
 }
 
 bool DeviceBackend::first_outer()
@@ -1312,7 +1372,7 @@ bool DeviceBackend::configure(const char *key, long long value)
     if (k == "kernel_cfg") { kernel_cfg_ = (int) value; return true; }
     if (k == "ctas_per_sm") { ctas_per_sm_ = (int) value; return true; }
     if (k == "fused_solve") { fused_solve_ok_ = value != 0; return true; }
-    if (k == "prefetch_chunks") { prefetch_chunks_ = value < 0 ? 0u : (unsigned) value; return true; }
+    if (k == "prefetch_chunks") { prefetch_chunks_ = value < 0 ? 0u : (unsigned) value; prefetch_forced_ = true; return true; }
     if (k == "l2_keep_mb") { l2_keep_bytes_ = value <= 0 ? 0 : (size_t) value << 20; return true; }
     if (k == "pmax" || k == "target_chunks" || k == "fill_div" || k == "group_base" || k == "geometry_rule") {
         if (value < 1 && k != "geometry_rule") return fail("bad value");

@@ -35,6 +35,7 @@ public:
     bool agree_any(bool local) override;
     bool enqueue_df2(const FuncSpec &fs, Slot slot, double *grad_dst, unsigned index);
     bool ensure_halo(Slot slot);
+    bool eval_sharded(const FuncSpec &fs, Slot slot, double *grad_dst, unsigned index, double *value);
     bool eval_user_objective(Slot slot, bool want_grad, double *value);
     bool push_rows_to(double *dst, unsigned rows, const double *host_grad);
     bool eval_penalty_objective(Slot slot, bool want_grad, double *value);
@@ -97,7 +98,8 @@ private:
     double *wide_dev_ = nullptr;      // m > 16: y | rhoc | rhoc/2 | active flags of the evaluation in flight
     std::vector<double> wide_host_;
     size_t l2_keep_bytes_ = 0;        // operand bytes to load evict_last (knob b200_l2_keep_mb)
-    unsigned prefetch_chunks_ = 2;    // knob b200_prefetch_chunks (solve kernel: L2 prefetch of a waiting sweeper's next group)
+    bool prefetch_forced_ = false;
+    unsigned prefetch_chunks_ = 3;    // knob b200_prefetch_chunks (solve kernel: L2 prefetch of a waiting sweeper's next group)
     size_t out_rec_ = 0;              // doubles per result record (>= 24, >= 3 + m)
     unsigned long long solve_launch_id_ = 0;   // tag = launch id << 40 | generation: never matches a stale slot
     bool fused_solve_ok_ = true;
@@ -125,6 +127,10 @@ private:
     size_t h_grad_cap_ = 0;
     int h_grad_next_ = 0;
     cudaEvent_t h_grad_done_[2] = {nullptr, nullptr};
+    double *h_xs_ = nullptr, *h_gs_[2] = {nullptr, nullptr};     // sharded host callbacks: pinned shard of x, gradient staging
+    cudaEvent_t h_gs_done_[2] = {nullptr, nullptr};
+    int h_gs_next_ = 0, h_xs_slot_ = -1;
+    unsigned long long h_xs_epoch_ = 0;
     double *xfull_dev_ = nullptr;                    // multi-rank host callbacks: gathered x
     double *pen_rows_ = nullptr;                     // augmented-Lagrangian objective: gradient rows of the folded constraints
     unsigned pen_total_ = 0;                         // their number (scalar constraints)

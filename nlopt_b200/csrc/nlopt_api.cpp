@@ -170,6 +170,7 @@ double flipped(unsigned n, const double *x, double *grad, void *p)
 }
 
 nlopt_result run_ccsa(nlopt_opt opt, double *x_host, double *x_dev, double *minf);
+nlopt_result run_ccsa_precond(nlopt_opt opt, double *x, double *minf, const nb200::CcsaParams &prm);
 nlopt_result run_auglag(nlopt_opt opt, double *x_host, double *minf);
 
 }  // namespace
@@ -297,6 +298,7 @@ static nlopt_result set_objective(nlopt_opt opt, nlopt_func f, nlopt_b200_dfunc 
     opt->df2 = nullptr;
     opt->dfin = nullptr;
     opt->halo = 0;
+    opt->sf = nullptr;
     opt->f_data = data;
     opt->pre = pre;
     opt->maximize = maximize;
@@ -329,6 +331,15 @@ nlopt_result nlopt_b200_set_min_objective_device2(nlopt_opt opt, nlopt_b200_dfun
     opt->df2 = f;
     opt->dfin = fin;
     opt->halo = halo;
+    return r;
+}
+
+nlopt_result nlopt_b200_set_min_objective_sharded(nlopt_opt opt, nlopt_b200_sfunc f, void *d)
+{
+    if (!f) return NLOPT_INVALID_ARGS;
+    nlopt_result r = set_objective(opt, nullptr, df2_marker, nullptr, d, 0);
+    if (r < 0) return r;
+    opt->sf = f;
     return r;
 }
 
@@ -511,6 +522,14 @@ nlopt_result nlopt_b200_add_inequality_constraint_device2(nlopt_opt opt, nlopt_b
     c.df2 = fc;
     c.dfin = fin;
     c.halo = halo;
+    return r;
+}
+nlopt_result nlopt_b200_add_inequality_constraint_sharded(nlopt_opt opt, nlopt_b200_sfunc fc, void *d, double tol)
+{
+    if (!fc) return NLOPT_INVALID_ARGS;
+    nlopt_result r = add_any(opt, false, false, 1, nullptr, nullptr, df2_marker, nullptr, d, &tol);
+    if (r < 0) return r;
+    opt->fc.back().sf = fc;
     return r;
 }
 nlopt_result nlopt_add_equality_mconstraint(nlopt_opt opt, unsigned m, nlopt_mfunc h, void *d, const double *tol)
@@ -910,9 +929,12 @@ nlopt_result run_ccsa(nlopt_opt opt, double *x_host, double *x_dev, double *minf
 
     bool any_pre = opt->pre != nullptr;
     for (const auto &c : opt->fc) any_pre = any_pre || c.pre != nullptr;
-    if (any_pre && opt->algorithm == NLOPT_LD_CCSAQ) {
-        set_err(opt, "preconditioned CCSAQ (ccsa_quadratic.c:299-324) is not built into this library");
-        return NLOPT_INVALID_ARGS;
+    if (any_pre && opt->algorithm == NLOPT_LD_CCSAQ) {          /* ccsa_quadratic.c: the !no_precond branch */
+        if (!x_host || opt->df) {
+            set_err(opt, "preconditioned CCSAQ takes host x and host callbacks (nlopt_precond is a host function)");
+            return NLOPT_INVALID_ARGS;
+        }
+        return run_ccsa_precond(opt, x_host, minf, prm);
     }
 
     /* hand the O(n) state to the device */
@@ -924,12 +946,13 @@ nlopt_result run_ccsa(nlopt_opt opt, double *x_host, double *x_dev, double *minf
     cfg.objective.df2 = opt->df2;
     cfg.objective.dfin = opt->dfin;
     cfg.objective.halo = opt->halo;
+    cfg.objective.sf = opt->sf;
     cfg.objective.data = opt->f_data;
     cfg.penalty = opt->penalty;
     std::vector<double> tol;
     for (const auto &c : opt->fc) {
         nb200::FuncSpec s;
-        s.m = c.m; s.f = c.f; s.mf = c.mf; s.df = c.df; s.df2 = c.df2; s.dfin = c.dfin; s.halo = c.halo; s.data = c.f_data;
+        s.m = c.m; s.f = c.f; s.mf = c.mf; s.df = c.df; s.df2 = c.df2; s.dfin = c.dfin; s.halo = c.halo; s.sf = c.sf; s.data = c.f_data;
         cfg.constraints.push_back(s);
         tol.insert(tol.end(), c.tol.begin(), c.tol.end());
     }
@@ -1009,6 +1032,246 @@ bool rel_stop_host(double vold, double vnew, double reltol, double abstol)      
     if (nb200::nl_isinf(vold)) return false;
     const double d = std::fabs(vnew - vold);
     return d < abstol || d < reltol * (std::fabs(vnew) + std::fabs(vold)) * 0.5 || (reltol > 0 && vnew == vold);
+}
+
+// ---- preconditioned CCSAQ (ccsa_quadratic.c:153-206, :299-324, :415-441) ------------------------------------------
+// With a preconditioner H (user function v -> H(x0) v, nlopt.h:70) on the objective and/or on constraints, the
+// convex model around x0 is no longer separable:
+//     g(x) = f(x0) + grad f . dx + rho/2 sum_j (dx_j / sigma_j)^2 + 1/2 dx^T H dx        (gfunc, :153-181)
+// so there is no closed-form dual.  The reference solves the model problem  min g0  s.t.  gi <= 0  in the trust box
+// max(lb, x0 - sigma) <= x <= min(ub, x0 + sigma) with a nested n-dimensional optimiser -- the dual optimiser's
+// algorithm and tolerances, i.e. LD_MMA by default (:299-324) -- and keeps the CCSA outer / inner logic unchanged.
+// Here the nested problem is an ordinary LD_MMA run of THIS library: its dual evaluations over the n variables are
+// the CUDA kernels; g0 / gi are host callbacks because nlopt_precond is a host function (they see x on the host like
+// any nlopt_func).  The O(n) glue of this outer loop (sigma update, stop norms) stays on the host: each inner
+// iteration is dominated by a whole nested solve.
+// One deliberate difference: the reference never assigns dd.wval on this branch (it reads an uninitialised stack
+// slot in the rho updates at :550-556); here w = 1/2 sum (dx_j / sigma_j)^2, the value the separable branch uses.
+struct PrecondModel {
+    unsigned n = 0, m = 0;
+    const double *x0 = nullptr, *sigma = nullptr, *dfdx = nullptr, *dfcdx = nullptr;
+    double fval = 0, rho = 0;
+    const double *fcval = nullptr, *rhoc = nullptr;
+    nlopt_precond pre = nullptr;
+    void *pre_data = nullptr;
+    std::vector<nlopt_precond> prec;
+    std::vector<void *> prec_data;
+    std::vector<double> scratch;             // dx | H dx
+    long count = 0;
+};
+
+double precond_gfunc(PrecondModel &d, double f, const double *dfdx, double rho, nlopt_precond pre, void *pre_data, const double *x,
+                     double *grad)                                     // ccsa_quadratic.c:153-181
+{
+    const unsigned n = d.n;
+    double *dx = d.scratch.data(), *Hdx = dx + n;
+    double val = f;
+    for (unsigned j = 0; j < n; ++j) {
+        const double sigma2inv = 1.0 / (d.sigma[j] * d.sigma[j]);
+        dx[j] = x[j] - d.x0[j];
+        val += dfdx[j] * dx[j] + (0.5 * rho) * (dx[j] * dx[j]) * sigma2inv;
+        if (grad) grad[j] = dfdx[j] + rho * dx[j] * sigma2inv;
+    }
+    if (pre) {
+        pre(n, d.x0, dx, Hdx, pre_data);
+        for (unsigned j = 0; j < n; ++j) val += 0.5 * dx[j] * Hdx[j];
+        if (grad)
+            for (unsigned j = 0; j < n; ++j) grad[j] += Hdx[j];
+    }
+    return val;
+}
+
+double precond_g0(unsigned, const double *x, double *grad, void *dp)     // :183-191
+{
+    PrecondModel &d = *static_cast<PrecondModel *>(dp);
+    ++d.count;
+    return precond_gfunc(d, d.fval, d.dfdx, d.rho, d.pre, d.pre_data, x, grad);
+}
+
+void precond_gi(unsigned m, double *result, unsigned n, const double *x, double *grad, void *dp)      // :194-206
+{
+    PrecondModel &d = *static_cast<PrecondModel *>(dp);
+    for (unsigned i = 0; i < m; ++i)
+        result[i] = precond_gfunc(d, d.fcval[i], d.dfcdx + (size_t) i * n, d.rhoc[i], d.prec[i], d.prec_data[i], x,
+                                  grad ? grad + (size_t) i * n : nullptr);
+}
+
+nlopt_result run_ccsa_precond(nlopt_opt opt, double *x, double *minf, const nb200::CcsaParams &prm)
+{
+    const unsigned n = opt->n;
+    unsigned m = 0;
+    for (const auto &c : opt->fc) m += c.m;
+    const double t_start = nb200::wall_seconds();
+    opt->stats = nlopt_b200_stats{};
+    opt->numevals = 0;
+    auto forced = [&]() { return opt->force_stop != 0; };
+    auto evals_out = [&]() { return opt->maxeval > 0 && opt->numevals >= opt->maxeval; };
+    auto timed_out = [&]() { return opt->maxtime > 0 && nb200::wall_seconds() - t_start >= opt->maxtime; };
+
+    std::vector<double> sigma(n), dfdx(n), dfdx_cur(n), xcur(n), xprev(n), xprevprev(n), pre_lb(n), pre_ub(n);
+    std::vector<double> dfcdx((size_t) m * n), dfcdx_cur((size_t) m * n), fcval(m), fcval_cur(m), rhoc(m, prm.rho_init), gcval(m), tol;
+    for (const auto &c : opt->fc) tol.insert(tol.end(), c.tol.begin(), c.tol.end());
+    PrecondModel dd;
+    dd.n = n; dd.m = m;
+    dd.x0 = x; dd.sigma = sigma.data(); dd.dfdx = dfdx.data(); dd.dfcdx = dfcdx.data();
+    dd.fcval = fcval.data(); dd.rhoc = rhoc.data();
+    dd.pre = opt->pre; dd.pre_data = opt->f_data;
+    for (const auto &c : opt->fc)
+        for (unsigned k = 0; k < c.m; ++k) { dd.prec.push_back(c.pre); dd.prec_data.push_back(c.f_data); }
+    dd.scratch.assign(2 * (size_t) n, 0.0);
+
+    // the nested optimiser (ccsa_quadratic.c:299-324): dual algorithm and tolerances, objective g0, constraints gi
+    nlopt_opt pre_opt = nlopt_create(NLOPT_LD_MMA, n);
+    if (!pre_opt) { set_err(opt, "failure creating precond. optimizer"); return NLOPT_FAILURE; }
+    struct Guard { nlopt_opt o; ~Guard() { nlopt_destroy(o); } } guard{pre_opt};
+    nlopt_result ret = nlopt_set_min_objective(pre_opt, precond_g0, &dd);
+    if (ret >= 0 && m) ret = nlopt_add_inequality_mconstraint(pre_opt, m, precond_gi, &dd, nullptr);
+    if (ret >= 0) ret = nlopt_set_ftol_rel(pre_opt, prm.dual_ftol_rel);
+    if (ret >= 0) ret = nlopt_set_ftol_abs(pre_opt, prm.dual_ftol_abs);
+    if (ret >= 0) ret = nlopt_set_maxeval(pre_opt, prm.dual_maxeval);
+    if (ret < 0) return ret;
+    opt->force_stop_child = pre_opt;                  // nlopt_force_stop on the outer object reaches the nested run
+
+    for (unsigned j = 0; j < n; ++j) {                // :324-332
+        if (opt->has_dx && opt->dx[j] > 0) sigma[j] = opt->dx[j];
+        else if (nb200::nl_isinf(opt->ub[j]) || nb200::nl_isinf(opt->lb[j])) sigma[j] = 1.0;
+        else sigma[j] = 0.5 * (opt->ub[j] - opt->lb[j]);
+        sigma[j] = sigma[j] > prm.sigma_min ? sigma[j] : prm.sigma_min;
+    }
+    double rho = prm.rho_init, fcur;
+    auto eval_f = [&](const double *xx, double *g) { ++opt->numevals; return opt->f(n, xx, g, opt->f_data); };
+    auto eval_c = [&](const double *xx, double *vals, double *grads) -> bool {
+        unsigned i = 0;
+        for (const auto &c : opt->fc) {
+            if (c.f) vals[i] = c.f(n, xx, grads ? grads + (size_t) i * n : nullptr, c.f_data);
+            else c.mf(c.m, vals + i, n, xx, grads ? grads + (size_t) i * n : nullptr, c.f_data);
+            i += c.m;
+            if (forced()) return false;
+        }
+        return true;
+    };
+    dd.fval = fcur = *minf = eval_f(x, dfdx.data());
+    xcur.assign(x, x + n);
+    if (forced()) return NLOPT_FORCED_STOP;
+    if (!eval_c(x, fcval.data(), dfcdx.data())) return NLOPT_FORCED_STOP;
+    bool feasible = true;
+    double infeasibility = 0;
+    for (unsigned i = 0; i < m; ++i) {
+        feasible = feasible && fcval[i] <= 0;
+        if (fcval[i] > infeasibility) infeasibility = fcval[i];
+    }
+    auto check_stop = [&]() -> nlopt_result {
+        if (forced()) return NLOPT_FORCED_STOP;
+        if (evals_out()) return NLOPT_MAXEVAL_REACHED;
+        if (timed_out()) return NLOPT_MAXTIME_REACHED;
+        if (feasible && *minf < opt->stopval) return NLOPT_STOPVAL_REACHED;
+        return NLOPT_SUCCESS;
+    };
+    unsigned k = 0;
+    for (;;) {                                        // outer iterations (:404)
+        const double fprev = fcur;
+        if ((ret = check_stop()) != NLOPT_SUCCESS) return ret;
+        if (++k > 1) xprevprev = xprev;
+        xprev = xcur;
+        int inner_nevals = 0;
+        for (;;) {                                    // inner iterations (:417)
+            for (unsigned j = 0; j < n; ++j) {        // :441-446
+                pre_lb[j] = opt->lb[j] > x[j] - sigma[j] ? opt->lb[j] : x[j] - sigma[j];
+                pre_ub[j] = opt->ub[j] < x[j] + sigma[j] ? opt->ub[j] : x[j] + sigma[j];
+                xcur[j] = x[j];
+            }
+            nlopt_set_lower_bounds(pre_opt, pre_lb.data());
+            nlopt_set_upper_bounds(pre_opt, pre_ub.data());
+            dd.rho = rho; dd.count = 0;
+            if (opt->maxtime > 0) {
+                const double left = opt->maxtime - (nb200::wall_seconds() - t_start);
+                nlopt_set_maxtime(pre_opt, left > 0 ? left : 1e-9);
+            }
+            double pre_min;
+            const nlopt_result reti = nlopt_optimize(pre_opt, xcur.data(), &pre_min);
+            opt->stats.dual_evals += pre_opt->stats.dual_evals;
+            opt->stats.kernel_launches += pre_opt->stats.kernel_launches;
+            ++opt->stats.dual_solves;
+            if (reti < 0 || reti == NLOPT_MAXTIME_REACHED) {
+                if (reti < 0 && nlopt_get_errmsg(pre_opt)) set_err(opt, "nested model solve: %s", nlopt_get_errmsg(pre_opt));
+                return forced() ? NLOPT_FORCED_STOP : reti;
+            }
+            const double gval = precond_g0(n, xcur.data(), nullptr, &dd);       // :465-467
+            if (m) precond_gi(m, gcval.data(), n, xcur.data(), nullptr, &dd);
+            double wval = 0;
+            for (unsigned j = 0; j < n; ++j) { const double q = (xcur[j] - x[j]) / sigma[j]; wval += 0.5 * q * q; }
+            if (prm.verbosity) std::printf("CCSA dual converged in %ld iters to g=%g:\n", dd.count, gval);
+
+            fcur = eval_f(xcur.data(), prm.inner_gradients ? dfdx_cur.data() : nullptr);
+            ++inner_nevals;
+            if (forced()) return NLOPT_FORCED_STOP;
+            bool feasible_cur = true, inner_done = gval >= fcur;
+            double infeasibility_cur = 0;
+            if (!eval_c(xcur.data(), fcval_cur.data(), prm.inner_gradients ? dfcdx_cur.data() : nullptr)) return NLOPT_FORCED_STOP;
+            for (unsigned i = 0; i < m; ++i) {
+                feasible_cur = feasible_cur && fcval_cur[i] <= tol[i];
+                inner_done = inner_done && gcval[i] >= fcval_cur[i];
+                if (fcval_cur[i] > infeasibility_cur) infeasibility_cur = fcval_cur[i];
+            }
+            inner_done = inner_done || (prm.inner_maxeval > 0 && inner_nevals == prm.inner_maxeval);
+            const bool take = prm.always_improve
+                ? ((fcur < *minf && (inner_done || feasible_cur || !feasible)) || (!feasible && infeasibility_cur < infeasibility))
+                : inner_done;
+            if (take) {                               // :500-545
+                if (!prm.inner_gradients) {
+                    fcur = opt->f(n, xcur.data(), dfdx_cur.data(), opt->f_data);
+                    if (forced()) return NLOPT_FORCED_STOP;
+                    if (!eval_c(xcur.data(), fcval_cur.data(), dfcdx_cur.data())) return NLOPT_FORCED_STOP;
+                }
+                dd.fval = *minf = fcur;
+                infeasibility = infeasibility_cur;
+                fcval = fcval_cur;
+                std::copy(xcur.begin(), xcur.end(), x);
+                dfdx = dfdx_cur;
+                dfcdx = dfcdx_cur;
+                dd.dfdx = dfdx.data(); dd.dfcdx = dfcdx.data(); dd.fcval = fcval.data();
+                if (infeasibility_cur == 0) feasible = true;
+            }
+            if ((ret = check_stop()) != NLOPT_SUCCESS) return ret;
+            if (inner_done) break;
+            if (fcur > gval) {                        // :550-556
+                const double a = 10 * rho, b = 1.1 * (rho + (fcur - gval) / wval);
+                rho = a < b ? a : b;
+            }
+            for (unsigned i = 0; i < m; ++i)
+                if (fcval_cur[i] > gcval[i]) {
+                    const double a = 10 * rhoc[i], b = 1.1 * (rhoc[i] + (fcval_cur[i] - gcval[i]) / wval);
+                    rhoc[i] = a < b ? a : b;
+                }
+        }
+        ret = NLOPT_SUCCESS;                          // :566-570: nlopt_stop_ftol, nlopt_stop_x
+        if (rel_stop_host(fprev, fcur, opt->ftol_rel, opt->ftol_abs)) ret = NLOPT_FTOL_REACHED;
+        {
+            double dn = 0, xn = 0;
+            bool below = opt->has_xtol_abs;
+            for (unsigned j = 0; j < n; ++j) {
+                const double w = opt->has_x_weights ? opt->x_weights[j] : 1.0;
+                dn += w * std::fabs(xcur[j] - xprev[j]);
+                xn += w * std::fabs(xcur[j]);
+                if (opt->has_xtol_abs && std::fabs(xcur[j] - xprev[j]) >= opt->xtol_abs[j]) below = false;
+            }
+            if (dn < opt->xtol_rel * xn || below) ret = NLOPT_XTOL_REACHED;
+        }
+        if (ret != NLOPT_SUCCESS) return ret;
+        rho = 0.1 * rho > 1e-5 ? 0.1 * rho : 1e-5;   // :573-590
+        for (unsigned i = 0; i < m; ++i) rhoc[i] = 0.1 * rhoc[i] > 1e-5 ? 0.1 * rhoc[i] : 1e-5;
+        if (k > 1)
+            for (unsigned j = 0; j < n; ++j) {
+                const double dx2 = (xcur[j] - xprev[j]) * (xprev[j] - xprevprev[j]);
+                sigma[j] *= dx2 < 0 ? 0.7 : (dx2 > 0 ? 1.2 : 1.0);
+                if (!nb200::nl_isinf(opt->ub[j]) && !nb200::nl_isinf(opt->lb[j])) {
+                    const double r = opt->ub[j] - opt->lb[j];
+                    sigma[j] = sigma[j] < 10 * r ? sigma[j] : 10 * r;
+                    sigma[j] = sigma[j] > 1e-8 * r ? sigma[j] : 1e-8 * r;
+                }
+                sigma[j] = sigma[j] > prm.sigma_min ? sigma[j] : prm.sigma_min;
+            }
+    }
 }
 
 bool stop_x_host(const nlopt_opt opt, const double *x, const double *oldx)      // nlopt_stop_x, stop.c:98-108

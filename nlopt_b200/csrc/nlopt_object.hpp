@@ -21,6 +21,7 @@ struct ConstraintRec {
     nlopt_b200_dfunc2 df2 = nullptr;    // asynchronous form (df then holds a marker)
     nlopt_b200_dfinish dfin = nullptr;
     int halo = 0;
+    nlopt_b200_sfunc sf = nullptr;      // sharded host callback (df then holds a marker)
     nlopt_precond pre = nullptr;
     void *f_data = nullptr;
     std::vector<double> tol;        // m feasibility tolerances
@@ -42,6 +43,7 @@ struct nlopt_opt_s {
     nlopt_b200_dfunc2 df2 = nullptr;
     nlopt_b200_dfinish dfin = nullptr;
     int halo = 0;
+    nlopt_b200_sfunc sf = nullptr;
     void *f_data = nullptr;
     nlopt_precond pre = nullptr;
     int maximize = 0;

@@ -210,6 +210,34 @@ double nb200p_simp_host(unsigned n, const double *x, double *grad, void *data)
     return f;
 }
 
+// sharded forms (nlopt_b200_sfunc): this rank's variables only, additive value contribution
+double nb200p_simp_sharded(unsigned n_local, unsigned long long j0, unsigned long long, const double *x, double *grad, void *data)
+{
+    Tick t;
+    const nb200p_simp_data *sd = static_cast<const nb200p_simp_data *>(data);
+    const double ome = 1.0 - sd->eps;
+    double f = 0.0;
+    for (unsigned jl = 0; jl < n_local; ++jl) {
+        const double a = 0.5 + nb200::u01(sd->seed, 0, j0 + jl);
+        const double x2 = x[jl] * x[jl], x3 = x2 * x[jl];
+        const double d = sd->eps + ome * x3;
+        if (grad) grad[jl] = -(((a * (ome * 3.0)) * x2) / (d * d));
+        f += a / d;
+    }
+    return f;
+}
+
+double nb200p_mean_sharded(unsigned n_local, unsigned long long j0, unsigned long long n, const double *x, double *grad, void *data)
+{
+    Tick t;
+    const double inv_n = 1.0 / (double) n;
+    double s = 0.0;
+    for (unsigned jl = 0; jl < n_local; ++jl) s += x[jl];
+    if (grad)
+        for (unsigned jl = 0; jl < n_local; ++jl) grad[jl] = inv_n;
+    return s * inv_n + (j0 == 0 ? static_cast<const nb200p_mean_data *>(data)->offset : 0.0);
+}
+
 void *nb200p_make_simp_data(nb200p_problem_s *p, unsigned long long seed, double eps)
 {
     nb200p_simp_data *d = static_cast<nb200p_simp_data *>(std::malloc(sizeof(nb200p_simp_data)));

@@ -100,6 +100,14 @@ class Problem:
         dm = self.L.nb200p_make_mean_data(self.h, -vol)
         opt._check(lib_.nlopt_add_inequality_constraint(opt._h, self._fn("nb200p_mean_host"), dm, tol))
 
+    def simp_sharded(self, opt, seed=0x5EED0000, eps=1e-3, vol=0.4, tol=0.0):
+        """config 4 with sharded host callbacks (product library only): each rank evaluates its own variables"""
+        lib_ = opt._lib
+        d = self.L.nb200p_make_simp_data(self.h, seed, eps)
+        opt._check(lib_.nlopt_b200_set_min_objective_sharded(opt._h, C.cast(self.L.nb200p_simp_sharded, C.c_void_p), d))
+        dm = self.L.nb200p_make_mean_data(self.h, -vol)
+        opt._check(lib_.nlopt_b200_add_inequality_constraint_sharded(opt._h, C.cast(self.L.nb200p_mean_sharded, C.c_void_p), dm, tol))
+
     def simp_device(self, opt, seed=0x5EED0000, eps=1e-3, vol=0.4, tol=0.0):
         opt._check(self.L.nb200p_set_simp_device(self.h, opt._h, seed, eps))
         opt._check(self.L.nb200p_add_mean_device(self.h, opt._h, -vol, tol))

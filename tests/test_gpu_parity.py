@@ -453,6 +453,31 @@ def test_fused_solve_stop_rules_equal_host_driven(built, variant, opts):
     assert abs(a["minf"] - ref["minf"]) <= 1e-6 * abs(ref["minf"])
 
 
+def test_sharded_host_callbacks_equal_plain_host_callbacks(built):
+    """nlopt_b200_sfunc with one rank is the plain callback (j0 = 0, n_local = n): identical runs, bit for bit; and the
+    device-functor form of the same problem agrees to the end-to-end tolerance."""
+    from nlopt_b200.problems import Problem
+    n = 200000
+    out = []
+    for kind in ("host", "sharded", "device"):
+        o = nl.opt(nl.LD_MMA, n)
+        o.set_lower_bounds(0.0); o.set_upper_bounds(1.0)
+        p = Problem()
+        getattr(p, "simp_" + kind)(o)
+        o.set_maxeval(15)
+        if kind == "device":
+            import torch
+            x = torch.full((n,), 0.4, dtype=torch.float64, device="cuda")
+            o.optimize_device(x.data_ptr())
+            x = x.cpu().numpy()
+        else:
+            x = o.optimize(np.full(n, 0.4))
+        out.append((o.last_optimize_result(), o.get_numevals(), o.last_optimum_value(), x))
+    assert out[0][:3] == out[1][:3] and np.array_equal(out[0][3], out[1][3])
+    assert out[2][0] == out[0][0] and out[2][1] == out[0][1]
+    assert abs(out[2][2] - out[0][2]) <= 1e-7 * abs(out[0][2]) and np.max(np.abs(out[2][3] - out[0][3])) <= 1e-6
+
+
 def test_device_path_has_no_cpu_fallback_symbols(built):
     """the product library must not contain or import anything from the oracle"""
     import subprocess, nlopt_b200._capi as capi

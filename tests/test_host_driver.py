@@ -354,3 +354,71 @@ def test_distinct_objects_on_distinct_threads(hosttest_lib):
     for t in ts:
         t.join()
     assert got == want
+
+
+def precond_problem(n, seed=3):
+    """f(x) = 1/2 x^T A x - b^T x with A = tridiag(-1, d_j, -1) SPD, preconditioner H = A (the exact Hessian); one linear
+    constraint with the zero preconditioner (its model is then the plain separable one)."""
+    rng = np.random.default_rng(seed)
+    d = 2.5 + rng.random(n)
+    b = rng.standard_normal(n)
+
+    def A(v):
+        out = d * v
+        out[:-1] -= v[1:]
+        out[1:] -= v[:-1]
+        return out
+
+    def f(x, g):
+        Ax = A(x)
+        if g.size:
+            g[:] = Ax - b
+        return float(0.5 * x @ Ax - b @ x)
+
+    def pre(x, v, vpre):
+        vpre[:] = A(v)
+
+    w = (1.0 + 0.5 * np.sin(0.37 * np.arange(n))) / n
+
+    def c(x, g):
+        if g.size:
+            g[:] = w
+        return float(w @ x) + 0.05
+    return f, pre, c, A, b
+
+
+def run_precond(lib, n, with_constraint_pre=False, **kw):
+    f, pre, c, A, b = precond_problem(n)
+    o = nl.opt(nl.LD_CCSAQ, n, library=lib)
+    o.set_lower_bounds(np.full(n, -2.0)); o.set_upper_bounds(np.full(n, 2.0))
+    o.set_precond_min_objective(f, pre)
+    if with_constraint_pre:
+        o.add_precond_inequality_constraint(c, lambda x, v, vpre: vpre.__setitem__(slice(None), 0.0), 1e-8)
+    else:
+        o.add_inequality_constraint(c, 1e-8)
+    for k, v in kw.items():
+        if k in ("xtol_rel", "ftol_rel", "maxeval"):
+            getattr(o, "set_" + k)(v)
+        else:
+            o.set_param(k, v)
+    x = o.optimize(np.zeros(n))
+    return dict(ret=o.last_optimize_result(), x=x, minf=o.last_optimum_value(), numevals=o.get_numevals())
+
+
+@pytest.mark.parametrize("with_constraint_pre", [False, True])
+def test_preconditioned_ccsaq_converges_to_the_reference_optimum(hosttest_lib, reflib, with_constraint_pre):
+    """SURVEY.md 8(f)-2, ccsa_quadratic.c:153-206, :299-324, :415-441.  With the exact Hessian as preconditioner the
+    model is exact, so every inner iteration is conservative and both libraries walk to the constrained optimum of the
+    quadratic; trajectories are not comparable step by step (the reference reads an uninitialised dd.wval on this
+    branch), the optimum is: f* to 1e-7 relative, x* to 1e-5, and the KKT residual of the returned point."""
+    n = 60
+    a = run_precond(hosttest_lib, n, with_constraint_pre, xtol_rel=1e-9, maxeval=60, dual_ftol_rel=1e-12)
+    b = run_precond(reflib, n, with_constraint_pre, xtol_rel=1e-9, maxeval=60, dual_ftol_rel=1e-12)
+    assert a["ret"] > 0 and b["ret"] > 0
+    assert abs(a["minf"] - b["minf"]) <= 1e-7 * max(1.0, abs(b["minf"]))
+    assert np.max(np.abs(a["x"] - b["x"])) <= 1e-5
+    f, pre, c, A, bb = precond_problem(n)
+    g = A(a["x"]) - bb
+    w = (1.0 + 0.5 * np.sin(0.37 * np.arange(n))) / n
+    lam = -float(g @ w) / float(w @ w)        # multiplier of the active linear constraint (interior of the box here)
+    assert lam > 0 and np.max(np.abs(g + lam * w)) <= 1e-4

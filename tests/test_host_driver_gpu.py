@@ -107,3 +107,8 @@ def test_maxtime_returns_maxtime(gpulib):
               xtol_rel=1e-15, maxeval=100000)
     assert r["ret"] == nl.MAXTIME_REACHED
     assert time.perf_counter() - t0 < 5.0
+
+
+@pytest.mark.parametrize("with_constraint_pre", [False, True])
+def test_preconditioned_ccsaq_converges_to_the_reference_optimum(gpulib, reflib, with_constraint_pre):
+    H.test_preconditioned_ccsaq_converges_to_the_reference_optimum(gpulib, reflib, with_constraint_pre)
