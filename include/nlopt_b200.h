@@ -290,6 +290,14 @@ int nlopt_b200_dual_set_scalars(nlopt_b200_dual h, double f0, double rho, const 
 /* out[0] = -val (what the dual optimiser minimises), out[1] = g0, out[2] = w, out[3..3+m) = g_i;
  * grad (may be NULL) receives -g_i.  want_xcur != 0 also materialises x*(y) on the device. */
 int nlopt_b200_dual_eval(nlopt_b200_dual h, const double *y, int want_xcur, double *out, double *grad);
+/* A whole dual solve on the resident arrays -- what mma.c:275-288 does with nlopt_optimize_limited(dual_opt, y, ...) and
+ * the final dual_func call: maximise the dual over [lo, hi]^m from the warm start y (in/out) with the level-2/3
+ * optimiser of optimize.c:818-826 (ftol_rel, maxeval; the other tolerances 0), then evaluate once more at the solution
+ * storing x*(y).  m <= 16 runs as ONE persistent kernel launch; larger m one launch per evaluation.  out[] as for
+ * nlopt_b200_dual_eval at the solution; *nevals = dual evaluations performed (the final one included);
+ * *kernel_ms = device time of the dual kernels (CUDA events). */
+int nlopt_b200_dual_solve(nlopt_b200_dual h, double *y, const double *lo, const double *hi, double ftol_rel, int maxeval,
+                          double *out, int *result, long *nevals, double *kernel_ms);
 int nlopt_b200_dual_download_xcur(nlopt_b200_dual h, double *xcur_host);
 int nlopt_b200_dual_download(nlopt_b200_dual h, const char *which, double *host);  /* "x","sigma","xprev",... */
 /* sigma kernels (mma.c:202-210, :431-442) and the fused end-of-outer-iteration pass */

@@ -153,6 +153,8 @@ _EXT = {
     "nlopt_b200_dual_fill_synthetic": (C.c_int, [C.c_void_p, C.c_ulonglong]),
     "nlopt_b200_dual_set_scalars": (C.c_int, [C.c_void_p, C.c_double, C.c_double, c_double_p, c_double_p]),
     "nlopt_b200_dual_eval": (C.c_int, [C.c_void_p, c_double_p, C.c_int, c_double_p, c_double_p]),
+    "nlopt_b200_dual_solve": (C.c_int, [C.c_void_p, c_double_p, c_double_p, c_double_p, C.c_double, C.c_int, c_double_p,
+                                        C.POINTER(C.c_int), C.POINTER(C.c_long), c_double_p]),
     "nlopt_b200_dual_download_xcur": (C.c_int, [C.c_void_p, c_double_p]),
     "nlopt_b200_dual_download": (C.c_int, [C.c_void_p, C.c_char_p, c_double_p]),
     "nlopt_b200_dual_sigma_init": (C.c_int, [C.c_void_p, c_double_p, C.c_double]),

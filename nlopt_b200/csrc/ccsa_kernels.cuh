@@ -1173,8 +1173,10 @@ struct SharedMultipliers {                // what the point functions read in th
 };
 
 // The folder CTA's loop (kept out of line so that its registers do not weigh on the sweep loop).
+// s_vs [8 x NV] (the shard sums of the generation in flight) and s_w [8 x 8 x NV] (per shard: the 8 fold-warp results)
+// are provided by the caller: the TMA-staged kernel's folder CTA lends its (otherwise unused) stage ring.
 template <int NV>
-__device__ __noinline__ void solve_folder(const SolveArgs &sa)
+__device__ __noinline__ void solve_folder(const SolveArgs &sa, double *s_vs, double *s_w)
 {
     const DualArgs &a = sa.d;
     SolveState *st = sa.st;
@@ -1182,8 +1184,6 @@ __device__ __noinline__ void solve_folder(const SolveArgs &sa)
     const int sub = threadIdx.x >> 5;
     const unsigned ngroups = a.segs_per_vshard * a.local_vshards;
     __shared__ int s_exit;
-    __shared__ double s_vs[kVirtualShards * NV];      // the shard sums of the generation in flight
-    __shared__ double s_w[kVirtualShards * kGroupWarps * NV];     // per shard: the 8 fold-warp results
     WarpDualMachine mach;                             // meaningful in warp 0 only
     int final_pass = 0;
     const unsigned long long t_start = nb_globaltimer();
@@ -1295,7 +1295,9 @@ __global__ void __launch_bounds__(BLOCK, MINB) dual_solve_kernel(const __grid_co
     static_assert(BLOCK == 32 * kGroupWarps, "one group slot per CTA");
     static_assert(kGroupWarps == kVirtualShards, "the folder CTA gives one warp to each virtual shard");
     if (blockIdx.x == gridDim.x - 1) {
-        solve_folder<NV>(sa);
+        __shared__ double s_vs[kVirtualShards * NV];
+        __shared__ double s_w[kVirtualShards * kGroupWarps * NV];
+        solve_folder<NV>(sa, s_vs, s_w);
         return;
     }
     const DualArgs &a = sa.d;
@@ -1379,6 +1381,225 @@ __global__ void __launch_bounds__(BLOCK, MINB) dual_solve_kernel(const __grid_co
         NB_TR(if (sub == 0 && lane == 0 && my_gen < kTraceGens) { const unsigned long long t = nb_globaltimer(); unsigned long long *r = sa.trace + 16 * my_gen;
                   atomicMax(r + 3, ~t); atomicMax(r + 4, t); atomicAdd(r + 8, t - tr_s0); atomicAdd(r + 9, 1ull); })
     }
+}
+
+// ---- the persistent dual-solve kernel, TMA-staged form --------------------------------------------------------
+// For small shards (several GPUs, or mid-size n) a generation is LATENCY-bound in the register form: a sweeper CTA walks
+// its few chunks one after the other, each step a dependent load -> compute, and nothing is in flight while it waits
+// for the next multipliers.  Here a producer warp feeds a ring of STAGES shared-memory stages with 1-D TMA bulk copies
+// (one 4 KB chunk of each of the 5+m operand arrays per stage).  The operands do not depend on the multipliers, so the
+// producer simply runs ahead: across chunk, group AND generation boundaries.  While the folder CTA folds, exchanges,
+// steps the dual optimiser and publishes y_{g+1}, every sweeper's ring fills with the first chunks of generation g + 1;
+// when y arrives the consumers start from shared memory and the producer keeps STAGES chunks in flight behind them.
+//   producer (warp 8, one thread): claims groups from the same monotonic counter as the register form (claim c ->
+//     generation c / ngroups + 1, group c % ngroups), and for every chunk waits for a free stage, writes the stage's
+//     metadata {generation, group, first/last chunk, pair offset}, arms the "full" barrier and issues the bulk loads.
+//   consumers (warps 0-7): follow the stage metadata -- first chunk of a group in a new generation: wait for that
+//     generation's multipliers (warp 0 polls the tagged slots, as in the register form); every chunk: operands from
+//     shared memory to registers, release the stage, evaluate; last chunk of a group: warp records -> group record ->
+//     tagged slots.  Same lanes, same per-warp accumulators, same fold tree: the same bits as every other kernel here.
+//   leaving: when the solve is over the consumers stop the producer and wait for the copies it has already issued
+//     (a CTA must not retire with bulk copies into its shared memory in flight).
+struct StageMeta {
+    unsigned long long gen;       // generation the chunk belongs to
+    unsigned long long p;         // pair offset of the chunk
+    unsigned gl;                  // local group
+    unsigned flags;               // 1: first chunk of its group, 2: last chunk, 4: empty group (no data in the stage)
+};
+
+__device__ __forceinline__ bool mbar_test(unsigned long long *bar, unsigned parity)
+{
+    unsigned ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(smem_addr(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+
+template <int VARIANT, int MAXM, int STAGES, int MINB>
+__global__ void __launch_bounds__(kTmaBlock, MINB) dual_solve_tma_kernel(const __grid_constant__ SolveArgs sa)
+{
+    constexpr int MR = MAXM > 0 ? MAXM : 1;
+    constexpr int NV = 3 + MR;
+    constexpr int NARR = 5 + MAXM;
+    static_assert(MAXM >= 1, "the solve kernels need at least one constraint");
+    extern __shared__ __align__(128) unsigned char s_raw[];
+    double2 *s_tile = reinterpret_cast<double2 *>(s_raw);     // [STAGES][NARR][kChunkPairs]
+    __shared__ unsigned long long s_full[STAGES], s_empty[STAGES];
+    __shared__ StageMeta s_meta[STAGES];
+    __shared__ double s_rec[2][kGroupWarps * NV];
+    __shared__ double s_y[kMaxParamM];
+    __shared__ double s_u;
+    __shared__ int s_store, s_exit;
+    __shared__ volatile int s_stop, s_prod_done;
+    __shared__ volatile unsigned long long s_issued;
+
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    if (blockIdx.x == gridDim.x - 1) {                        // the folder CTA: its 8 first warps; its stage ring holds the fold scratch
+        double *scratch = reinterpret_cast<double *>(s_raw);
+        static_assert((size_t) STAGES * NARR * kChunkBytes >= (size_t) (kVirtualShards * NV + kVirtualShards * kGroupWarps * NV) * sizeof(double), "fold scratch fits the ring");
+        if (warp < kGroupWarps) solve_folder<NV>(sa, scratch, scratch + kVirtualShards * NV);
+        return;
+    }
+    const DualArgs &a = sa.d;
+    SolveState *st_g = sa.st;
+    const unsigned ngroups = a.segs_per_vshard * a.local_vshards;
+
+    if (threadIdx.x == 0) {
+        for (int st = 0; st < STAGES; ++st) {
+            mbar_init(&s_full[st], 1);
+            mbar_init(&s_empty[st], kGroupWarps);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        s_exit = 0; s_store = 0; s_stop = 0; s_prod_done = 0; s_issued = 0ull;
+    }
+    __syncthreads();
+
+    if (warp == kGroupWarps) {
+        // ---------------- producer ----------------
+        if (lane == 0) {
+            const double *src[NARR];
+            src[0] = a.x; src[1] = a.lb; src[2] = a.ub; src[3] = a.sigma; src[4] = a.g;
+#pragma unroll
+            for (int i = 0; i < MAXM; ++i) src[5 + i] = a.G + (unsigned long long) i * a.ld;
+            int st = 0;
+            unsigned phase = 0;
+            unsigned long long issued = 0;
+            bool stop = false;
+            while (!stop) {
+                const unsigned long long c = atomicAdd(&st_g->claim, 1ull);
+                const unsigned long long gen = c / ngroups + 1;
+                const unsigned gl = (unsigned) (c % ngroups);
+                unsigned long long p_lo, p_hi;
+                group_pairs(a.nchunks, a.nseg_total, a.chunk0, a.seg0 + gl, &p_lo, &p_hi);
+                const bool empty = p_lo == p_hi;
+                for (unsigned long long p = p_lo; p < p_hi || (empty && p == p_lo); p += kChunkPairs) {
+                    while (!mbar_test(&s_empty[st], phase ^ 1u))          // a fresh barrier passes at once
+                        if (s_stop) { stop = true; break; }
+                    if (stop) break;
+                    StageMeta mt;
+                    mt.gen = gen; mt.p = p; mt.gl = gl;
+                    mt.flags = (p == p_lo ? 1u : 0u) | ((empty || p + kChunkPairs >= p_hi) ? 2u : 0u) | (empty ? 4u : 0u);
+                    s_meta[st] = mt;
+                    if (empty) {
+                        mbar_arrive(&s_full[st]);                         // no bytes: the phase completes on this arrival
+                    } else {
+                        mbar_expect_tx(&s_full[st], NARR * kChunkBytes);
+#pragma unroll
+                        for (int k = 0; k < NARR; ++k)
+                            tma_bulk_load(s_tile + ((size_t) st * NARR + k) * kChunkPairs, src[k] + 2 * p, kChunkBytes, &s_full[st]);
+                    }
+                    s_issued = ++issued;
+                    if (++st == STAGES) { st = 0; phase ^= 1u; }
+                    if (empty) break;
+                }
+            }
+            __threadfence_block();
+            s_prod_done = 1;
+        }
+        return;
+    }
+
+    // ---------------- consumers ----------------
+    const int sub = warp;
+    int st = 0;
+    unsigned phase = 0;
+    int parity = 0;
+    unsigned long long my_gen = 0, consumed = 0;
+    SharedMultipliers mu;
+    mu.y = s_y; mu.rhoc = a.rhoc; mu.half_rhoc = a.half_rhoc; mu.u_ccsaq = 0.0;
+    mu.rho = a.rho; mu.half_rho = a.half_rho;
+    mu.active = a.active; mu.m = a.m;
+    double acc[NV];
+#pragma unroll
+    for (int k = 0; k < NV; ++k) acc[k] = 0.0;
+    bool store = false;
+    for (;;) {
+        mbar_wait(&s_full[st], phase);                        // the stage's bytes and its metadata are visible
+        const StageMeta mt = s_meta[st];
+        if (mt.flags & 1u) {
+            if (mt.gen != my_gen) {
+                // wait until generation mt.gen is published (or the solve has finished); refresh the multipliers
+                if (sub == 0) {
+                    const int slot = lane < a.m ? lane : (lane == a.m ? kMaxParamM : kMaxParamM + 1);
+                    const unsigned long long tag = sa.tag0 | mt.gen;
+                    double v;
+                    int ex = 0;
+                    unsigned spins = 0;
+                    for (;;) {
+                        if (__all_sync(0xffffffffu, slot_get(st_g->pub + 2 * slot, tag, &v))) break;
+                        if ((++spins & 7u) == 0u && __any_sync(0xffffffffu, ld_gpu_s32(&st_g->done))) {
+                            ex = !__all_sync(0xffffffffu, slot_get(st_g->pub + 2 * slot, tag, &v));
+                            break;
+                        }
+                        __nanosleep(20);
+                    }
+                    if (ex) s_exit = 1;
+                    else if (lane < a.m) s_y[lane] = v;
+                    else if (lane == a.m) s_u = v;
+                    else if (lane == a.m + 1) s_store = (int) (__double_as_longlong(v) & 1ll);
+                }
+                asm volatile("bar.sync 1, %0;" ::"r"(32 * kGroupWarps) : "memory");
+                if (s_exit) break;
+                my_gen = mt.gen;
+                mu.u_ccsaq = s_u;
+                store = s_store != 0;
+            }
+#pragma unroll
+            for (int k = 0; k < NV; ++k) acc[k] = 0.0;
+        }
+        double2 vx = make_double2(0.0, 0.0), vlb = vx, vub = vx, vs = vx, vg = vx;
+        double Ga[MR], Gb[MR];
+#pragma unroll
+        for (int i = 0; i < MR; ++i) { Ga[i] = 0.0; Gb[i] = 0.0; }
+        const bool has = !(mt.flags & 4u);
+        if (has) {
+            const double2 *t = s_tile + (size_t) st * NARR * kChunkPairs + sub * 32 + lane;
+            vx = t[0]; vlb = t[kChunkPairs]; vub = t[2 * kChunkPairs]; vs = t[3 * kChunkPairs]; vg = t[4 * kChunkPairs];
+#pragma unroll
+            for (int i = 0; i < MAXM; ++i) { const double2 g2 = t[(5 + i) * kChunkPairs]; Ga[i] = g2.x; Gb[i] = g2.y; }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_empty[st]);             // operands are in registers: release the stage
+        if (++st == STAGES) { st = 0; phase ^= 1u; }
+        ++consumed;
+        if (has) {
+            double2 xc;
+            if (VARIANT == 0) {
+                xc.x = mma_point<MAXM, true>(mu, vx.x, vlb.x, vub.x, vs.x, vg.x, Ga, acc);
+                xc.y = mma_point<MAXM, true>(mu, vx.y, vlb.y, vub.y, vs.y, vg.y, Gb, acc);
+            } else {
+                xc.x = ccsaq_point<MAXM, true>(mu, vx.x, vlb.x, vub.x, vs.x, vg.x, Ga, acc);
+                xc.y = ccsaq_point<MAXM, true>(mu, vx.y, vlb.y, vub.y, vs.y, vg.y, Gb, acc);
+            }
+            if (store) st_stream(reinterpret_cast<double2 *>(a.xcur) + mt.p + sub * 32 + lane, xc);
+        }
+        if (mt.flags & 2u) {
+            warp_fold<NV>(acc);
+            double *srec = s_rec[parity];
+            if (lane == 0) {
+#pragma unroll
+                for (int k = 0; k < NV; ++k) srec[sub * NV + k] = acc[k];
+            }
+            asm volatile("bar.sync 1, %0;" ::"r"(32 * kGroupWarps) : "memory");
+            parity ^= 1;
+            if (sub == 0) put_group_record<NV>(srec, a.grouptags, ngroups, mt.gl, sa.tag0 | my_gen, lane);
+        }
+    }
+    // ---- leaving: stop the producer, then wait for every copy it has issued (the stage we hold is complete) ----
+    if (threadIdx.x == 0) {
+        s_stop = 1;
+        while (!s_prod_done) __nanosleep(20);
+        __threadfence_block();
+        const unsigned long long issued = s_issued;
+        unsigned long long done = consumed + 1;               // stages whose full barrier we have already passed
+        if (++st == STAGES) { st = 0; phase ^= 1u; }
+        for (; done < issued; ++done) {
+            mbar_wait(&s_full[st], phase);
+            if (++st == STAGES) { st = 0; phase ^= 1u; }
+        }
+    }
+    asm volatile("bar.sync 1, %0;" ::"r"(32 * kGroupWarps) : "memory");
 }
 
 // Gradient of the augmented-Lagrangian objective (auglag.c:47-48, :59-60): g_j += coef_k * row_k[j] for the

@@ -211,7 +211,7 @@ void DeviceBackend::free_state()
     if (xtol_abs_dev_) cudaFree(xtol_abs_dev_);
     for (const Owned &o : owned_) BlockCache::get().give(o.pinned, o.bytes, o.p, device_);   // every small buffer
     owned_.clear();
-    if (xfull_dev_) cudaFree(xfull_dev_);
+    if (xfull_dev_) BlockCache::get().give(false, (size_t) Comm::instance().world * shard_cap_ * sizeof(double), xfull_dev_, device_);
     solve_state_ = nullptr;
     vs2_dev_ = vs2_host_ = halo_edges_ = nullptr;
     halo_ptr_ = nullptr;
@@ -431,7 +431,7 @@ bool DeviceBackend::setup(const BackendConfig &cfg)
             NB_CUDA(cudaEventCreateWithFlags(&h_grad_done_[b], cudaEventDisableTiming));
         }
         if (Comm::instance().active())
-            NB_CUDA(cudaMalloc(&xfull_dev_, (size_t) Comm::instance().world * shard_cap_ * sizeof(double)));
+            NB_CUDA(cached_malloc(&xfull_dev_, (size_t) Comm::instance().world * shard_cap_ * sizeof(double)));
     }
     if (Comm::instance().active()) {
         scalar_cap_ = 1 + (size_t) m_;
@@ -1060,6 +1060,18 @@ SolveKernel pick_solve_kernel(int maxm)
     default: return dual_solve_kernel<VARIANT, 16, FULL, POL, 256, 1, 2>;
     }
 }
+// TMA-staged form (full-m, 1 / 2 / 4 rows): {stages, bytes of dynamic shared memory}; 3 CTAs per SM
+template <int VARIANT>
+SolveKernel pick_solve_tma_kernel(int maxm, size_t *smem)
+{
+    switch (maxm) {
+    case 1: *smem = (size_t) 3 * 6 * kChunkBytes; return dual_solve_tma_kernel<VARIANT, 1, 3, 3>;
+    case 2: *smem = (size_t) 2 * 7 * kChunkBytes; return dual_solve_tma_kernel<VARIANT, 2, 2, 3>;
+    case 4: *smem = (size_t) 2 * 9 * kChunkBytes; return dual_solve_tma_kernel<VARIANT, 4, 2, 3>;
+    default: *smem = 0; return nullptr;
+    }
+}
+
 template <int VARIANT>
 SolveKernel pick_solve_kernel2(int maxm, bool full, bool pol)
 {
@@ -1115,9 +1127,22 @@ bool DeviceBackend::dual_solve(double *y, const double *lo, const double *hi, co
     const int maxm = pick_maxm((int) m_);
     const bool full = (int) m_ == maxm && (variant_ == kCCSAQ || sa.d.active == ((1u << m_) - 1u));
     const bool use_pol = sa.d.l2_keep != 0u;
-    SolveKernel fn = variant_ == kMMA ? pick_solve_kernel2<0>(maxm, full, use_pol) : pick_solve_kernel2<1>(maxm, full, use_pol);
+    // Small shards are latency-bound in the register form (a CTA walks a handful of chunks, one dependent load ->
+    // compute step each): there the TMA-staged form, whose producer warp runs ahead across generations, is the default
+    // (knob b200_solve_tma: 1 always, 0 never).  Large shards stream at ~97 % of the HBM peak in the register form.
+    const size_t operand_bytes = (5 + (size_t) m_) * geo_.ld * sizeof(double);
+    const bool tma_auto = solve_tma_ < 0 && operand_bytes <= ((size_t) 400 << 20);
+    size_t smem = 0;
+    int block = 256;
+    SolveKernel fn = nullptr;
+    if ((solve_tma_ > 0 || tma_auto) && full && !use_pol && (maxm == 1 || maxm == 2 || maxm == 4)) {
+        fn = variant_ == kMMA ? pick_solve_tma_kernel<0>(maxm, &smem) : pick_solve_tma_kernel<1>(maxm, &smem);
+        block = kTmaBlock;
+        NB_CUDA(cudaFuncSetAttribute((const void *) fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+    } else
+        fn = variant_ == kMMA ? pick_solve_kernel2<0>(maxm, full, use_pol) : pick_solve_kernel2<1>(maxm, full, use_pol);
     int per_sm = 0;
-    NB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, 256, 0));
+    NB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, block, smem));
     if (per_sm < 1) return fail("dual_solve_kernel does not fit on an SM");
     long long grid = (long long) per_sm * sm_count_;          // all co-resident: sweepers + the folder CTA (the last one)
     if (grid > (long long) geo_.nseg_local + 1) grid = (long long) geo_.nseg_local + 1;
@@ -1138,7 +1163,7 @@ bool DeviceBackend::dual_solve(double *y, const double *lo, const double *hi, co
     }
     void *params[] = {&sa};
     {
-        cudaError_t le = cudaLaunchCooperativeKernel((const void *) fn, dim3((unsigned) grid), dim3(256), params, 0, stream_);
+        cudaError_t le = cudaLaunchCooperativeKernel((const void *) fn, dim3((unsigned) grid), dim3((unsigned) block), params, smem, stream_);
         if (le != cudaSuccess) {
             // e.g. co-residency not available (MPS, another context): not fatal -- switch this object to one
             // launch per evaluation; the caller sees supports_dual_solve() == false and takes the host loop
@@ -1292,7 +1317,7 @@ bool DeviceBackend::fetch_x(double *x_out)
         return true;
     }
     if (!h_x_) NB_CUDA(cached_host_alloc(&h_x_, (size_t) geo_.n * sizeof(double)));
-    if (!xfull_dev_) NB_CUDA(cudaMalloc(&xfull_dev_, (size_t) comm.world * shard_cap_ * sizeof(double)));
+    if (!xfull_dev_) NB_CUDA(cached_malloc(&xfull_dev_, (size_t) comm.world * shard_cap_ * sizeof(double)));
     h_x_slot_ = -1;
     if (!host_x_for(kBase)) return false;
     std::memcpy(x_out, h_x_, (size_t) geo_.n * sizeof(double));
@@ -1372,8 +1397,19 @@ bool DeviceBackend::configure(const char *key, long long value)
     if (k == "kernel_cfg") { kernel_cfg_ = (int) value; return true; }
     if (k == "ctas_per_sm") { ctas_per_sm_ = (int) value; return true; }
     if (k == "fused_solve") { fused_solve_ok_ = value != 0; return true; }
+    if (k == "solve_tma") { solve_tma_ = (int) value; return true; }
     if (k == "prefetch_chunks") { prefetch_chunks_ = value < 0 ? 0u : (unsigned) value; prefetch_forced_ = true; return true; }
-    if (k == "l2_keep_mb") { l2_keep_bytes_ = value <= 0 ? 0 : (size_t) value << 20; return true; }
+    if (k == "l2_keep_mb") {
+        l2_keep_bytes_ = value <= 0 ? 0 : (size_t) value << 20;
+        // evict_last lines are only protected inside the persisting carve-out of the L2: size it to the request
+        int maxp = 0;
+        if (cudaDeviceGetAttribute(&maxp, cudaDevAttrMaxPersistingL2CacheSize, device_) == cudaSuccess && maxp > 0) {
+            size_t want = l2_keep_bytes_ < (size_t) maxp ? l2_keep_bytes_ : (size_t) maxp;
+            cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want);
+            cudaGetLastError();
+        }
+        return true;
+    }
     if (k == "pmax" || k == "target_chunks" || k == "fill_div" || k == "group_base" || k == "geometry_rule") {
         if (value < 1 && k != "geometry_rule") return fail("bad value");
         if (k == "pmax") pmax_ = (unsigned) value;
@@ -1518,6 +1554,55 @@ int nlopt_b200_dual_eval(nlopt_b200_dual h, const double *y, int want_xcur, doub
     out[0] = -val;
     out[1] = h->f0 + s.gval;
     out[2] = s.wval;
+    return 0;
+}
+
+int nlopt_b200_dual_solve(nlopt_b200_dual h, double *y, const double *lo, const double *hi, double ftol_rel, int maxeval,
+                          double *out, int *result, long *nevals, double *kernel_ms)
+{
+    nb200::DualScalars sc;
+    sc.fval = h->f0;
+    sc.rho = h->rho;
+    sc.fcval = h->c0.data();
+    sc.rhoc = h->rhoc.data();
+    nb200::DualSums s;
+    s.gc = h->gc.data();
+    const unsigned m = h->be.m();
+    h->be.configure("time_kernels", 1);
+    const long long ns0 = h->be.query("kernel_ns");
+    auto add_constants = [&](const double *yy, double *grad) {      // mma.c:75-78, :135
+        double val = h->f0;
+        for (unsigned i = 0; i < m; ++i) {
+            const double ci = (h->be.is_mma() && std::isnan(h->c0[i])) ? 0.0 : h->c0[i];
+            val += yy[i] * ci;
+            if (out) out[3 + i] = ci + s.gc[i];
+            if (grad) grad[i] = -(ci + s.gc[i]);
+        }
+        val += s.val;
+        if (out) { out[0] = -val; out[1] = h->f0 + s.gval; out[2] = s.wval; }
+        return -val;
+    };
+    if (m >= 1 && h->be.supports_dual_solve()) {
+        const double stop6[6] = {ftol_rel, 0.0, 0.0, 0.0, (double) maxeval, 0.0};
+        if (!h->be.dual_solve(y, lo, hi, stop6, sc, &s, result, nevals)) return ok(h, false);
+        ++*nevals;
+        add_constants(y, nullptr);
+    } else {
+        nb200::DualMMA dual(m);
+        nb200::DualStop ds;
+        ds.ftol_rel = ftol_rel; ds.ftol_abs = 0; ds.xtol_rel = 0; ds.xtol_abs = 0; ds.maxeval = maxeval; ds.maxtime = 0;
+        double dmin = 0;
+        bool good = true;
+        *result = m ? dual.solve([&](const double *yy, double *grad, bool *okp) {
+            if (!h->be.dual_eval(yy, sc, false, &s)) { *okp = false; good = false; return 0.0; }
+            return add_constants(yy, grad);
+        }, y, lo, hi, ds, &dmin, nevals) : 1;
+        if (!good) return ok(h, false);
+        if (!h->be.dual_eval(y, sc, true, &s)) return ok(h, false);
+        ++*nevals;
+        add_constants(y, nullptr);
+    }
+    if (kernel_ms) *kernel_ms = (double) (h->be.query("kernel_ns") - ns0) * 1e-6;
     return 0;
 }
 

@@ -60,7 +60,10 @@ struct Geometry {
                 want = 0;
                 for (unsigned long long f = 8; f >= 1; f >>= 1)
                     if (kV * base * f * 2 <= nchunks) { want = base * f; break; }
-                if (!want) want = nchunks / kV < base ? nchunks / kV : base;               // one chunk (or less) per group
+                if (!want) {                                                              // at most one chunk per group
+                    const unsigned long long one = (nchunks + kV - 1) / kV;
+                    want = one < base ? one : base;
+                }
             }
         }
         if (want < 1) want = 1;

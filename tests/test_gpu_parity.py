@@ -317,12 +317,12 @@ def test_fused_dual_solve_equals_one_launch_per_evaluation(built, variant):
     cons = [P.lin_constraint(k, n) for k in range(m)]
     lb, ub = np.full(n, -2.0), np.full(n, 2.0)
     runs = []
-    for fused in (1, 0):
-        r = _run(alg, n, P.rosen_f, cons, [1e-8] * m, lb, ub, P.rosen_x0(n), maxeval=15, b200_fused_solve=fused)
+    for fused, tma in ((1, 1), (1, 0), (0, 0)):     # persistent kernel: TMA-staged and register form; host-driven
+        r = _run(alg, n, P.rosen_f, cons, [1e-8] * m, lb, ub, P.rosen_x0(n), maxeval=15, b200_fused_solve=fused, b200_solve_tma=tma)
         st = r["opt"].get_stats()
         runs.append((r["ret"], r["numevals"], r["minf"], r["x"].tobytes(), st["dual_evals"]))
         assert st["kernel_launches"] < st["dual_evals"] if fused else st["kernel_launches"] >= st["dual_evals"]
-    assert runs[0] == runs[1]
+    assert runs[0] == runs[1] == runs[2]
     # tutorial problem (m = 2, infeasible start -> capped multipliers) and a 1-constraint problem
     for kw in (dict(xtol_rel=1e-4), dict(stopval=P.TUT_FSTAR + 1e-3)):
         pair = [_run(alg, 2, P.tut_f, [P.tut_c(2, 0), P.tut_c(-1, 1)], [1e-8, 1e-8], [-np.inf, 0.0], [np.inf, np.inf],
@@ -444,13 +444,31 @@ def test_fused_solve_stop_rules_equal_host_driven(built, variant, opts):
     n, m = 30000, 4
     cons = [P.lin_constraint(k, n) for k in range(m)]
     lb, ub = np.full(n, -2.0), np.full(n, 2.0)
-    pair = [_run(alg, n, P.rosen_f, cons, [1e-8] * m, lb, ub, P.rosen_x0(n), maxeval=12, b200_fused_solve=f, **opts) for f in (1, 0)]
-    a, b = pair
-    assert a["ret"] == b["ret"] and a["numevals"] == b["numevals"] and a["minf"] == b["minf"] and np.array_equal(a["x"], b["x"])
-    assert a["opt"].get_stats()["dual_evals"] == b["opt"].get_stats()["dual_evals"]
+    trio = [_run(alg, n, P.rosen_f, cons, [1e-8] * m, lb, ub, P.rosen_x0(n), maxeval=12, b200_fused_solve=f, b200_solve_tma=t, **opts)
+            for f, t in ((1, 1), (1, 0), (0, 0))]
+    a, b = trio[0], trio[2]
+    for r in trio[1:]:
+        assert a["ret"] == r["ret"] and a["numevals"] == r["numevals"] and a["minf"] == r["minf"] and np.array_equal(a["x"], r["x"])
+        assert a["opt"].get_stats()["dual_evals"] == r["opt"].get_stats()["dual_evals"]
     ref = ob.port_minimize(variant, P.rosen_f, cons, [1e-8] * m, lb, ub, P.rosen_x0(n), maxeval=12, **opts)
     assert a["ret"] == ref["ret"] and a["numevals"] == ref["numevals"]
     assert abs(a["minf"] - ref["minf"]) <= 1e-6 * abs(ref["minf"])
+
+
+@pytest.mark.parametrize("variant", [ob.MMA, ob.CCSAQ])
+@pytest.mark.parametrize("n,m", [(3, 1), (700, 2), (5000, 4), (100001, 1), (300000, 4), (1500000, 2)])
+def test_tma_staged_solve_equals_register_solve(built, variant, n, m):
+    """dual_solve_tma_kernel (producer warp + shared-memory ring, running ahead across generations) against the
+    register-form persistent kernel: bit-identical runs, including groups without data (tiny n) and ragged tails."""
+    alg = nl.LD_MMA if variant == ob.MMA else nl.LD_CCSAQ
+    cons = [P.lin_constraint(k, n) for k in range(m)]
+    lb, ub = np.full(n, -2.0), np.full(n, 2.0)
+    x0 = P.rosen_x0(n) if n > 1 else np.array([-1.2])
+    f = P.rosen_f if n > 1 else (lambda x, g: (g.__setitem__(0, 2 * x[0]) if g.size else None, float(x[0] ** 2))[1])
+    pair = [_run(alg, n, f, cons, [1e-8] * m, lb, ub, x0, maxeval=8, b200_solve_tma=t) for t in (1, 0)]
+    a, b = pair
+    assert a["ret"] == b["ret"] and a["numevals"] == b["numevals"] and a["minf"] == b["minf"] and np.array_equal(a["x"], b["x"])
+    assert a["opt"].get_stats()["dual_evals"] == b["opt"].get_stats()["dual_evals"]
 
 
 def test_sharded_host_callbacks_equal_plain_host_callbacks(built):
