@@ -375,6 +375,7 @@ __device__ __forceinline__ void fold_generation(const double *grouptags, unsigne
     const unsigned fw_all = (P + 31u) / 32u;
     const unsigned fw_per = fw_all < (unsigned) kGroupWarps ? fw_all : (unsigned) kGroupWarps;      // non-empty fold warps per shard
     const unsigned nitems = local_vshards * fw_per;
+    // (Polling two items per round trip was tried and measured slower: profiles/r02_summary.md.)
     for (unsigned item = sub; item < nitems; item += kGroupWarps) {
         const unsigned v = item / fw_per, w = item % fw_per;
         double acc[NV];
@@ -408,15 +409,16 @@ __device__ __forceinline__ void fold_generation(const double *grouptags, unsigne
         }
     }
     fold_barrier();
-    if (sub == 0 && lane < NV) {
-        for (unsigned v = 0; v < local_vshards; ++v) {
-            double t = s_w[(v * kGroupWarps) * NV + lane];
+    // the 8 fold-warp results of every (shard, sum) pair in warp order: one thread per pair (a single lane walking all
+    // shards cost 64 dependent shared-memory adds, ~1.3 us of every generation's serial tail)
+    if (threadIdx.x < local_vshards * NV) {
+        const unsigned v = threadIdx.x / NV, k = threadIdx.x % NV;
+        double t = s_w[(v * kGroupWarps) * NV + k];
 #pragma unroll
-            for (int w = 1; w < kGroupWarps; ++w) t = addx(t, s_w[(v * kGroupWarps + w) * NV + lane]);
-            s_vs[v * NV + lane] = t;
-        }
+        for (int w = 1; w < kGroupWarps; ++w) t = addx(t, s_w[(v * kGroupWarps + w) * NV + k]);
+        s_vs[v * NV + k] = t;
     }
-    __syncwarp();
+    fold_barrier();
 }
 
 // The folder CTA of the one-evaluation kernels (the last CTA of the grid; sweepers never wait for it, so it may start

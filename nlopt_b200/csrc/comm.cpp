@@ -3,6 +3,11 @@
 #include "comm.hpp"
 
 #include <dlfcn.h>
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <unistd.h>
+
+#include <chrono>
 
 #include <cstdio>
 #include <cstdlib>
@@ -184,12 +189,103 @@ void Comm::teardown_p2p()
     p2p_ready = false;
 }
 
+// ---- host memory shared by the ranks (see comm.hpp) ------------------------------------------------------------------
+void Comm::release_shared_host()
+{
+    if (shm_base_) {
+        cudaHostUnregister(shm_base_);
+        cudaGetLastError();
+        munmap(shm_base_, shm_bytes_);
+    }
+    shm_base_ = nullptr;
+    shm_bytes_ = 0;
+}
+
+double *Comm::shared_host(size_t doubles, std::string *err)
+{
+    constexpr size_t kHeader = 4096;
+    const size_t want = kHeader + doubles * sizeof(double);
+    if (!active() || shm_failed_) return nullptr;
+    if (shm_base_ && shm_bytes_ >= want) return reinterpret_cast<double *>(static_cast<char *>(shm_base_) + kHeader);
+    // (re)create: every rank takes every step, whatever its local outcome; the verdict is collective
+    cudaDeviceSynchronize();
+    release_shared_host();
+    double *tmp = nullptr;
+    if (cudaMalloc(&tmp, 2 * sizeof(double)) != cudaSuccess) { shm_failed_ = true; return nullptr; }
+    auto exchange = [&](double v) -> double {          // sum over ranks of one double (also a barrier)
+        cudaMemcpy(tmp, &v, sizeof v, cudaMemcpyHostToDevice);
+        std::string e;
+        all_reduce_sum(tmp, 1, 0, &e);
+        cudaStreamSynchronize(0);
+        cudaMemcpy(&v, tmp, sizeof v, cudaMemcpyDeviceToHost);
+        return v;
+    };
+    const double pid0 = exchange(rank == 0 ? (double) getpid() : 0.0);
+    char name[96];
+    std::snprintf(name, sizeof name, "/nlopt_b200_%ld_%u", (long) pid0, ++shm_gen_);
+    const size_t bytes = (want + ((size_t) 2 << 20) - 1) / ((size_t) 2 << 20) * ((size_t) 2 << 20);
+    bool ok = true;
+    int fd = -1;
+    if (rank == 0) {
+        fd = shm_open(name, O_CREAT | O_EXCL | O_RDWR, 0600);
+        if (fd < 0 || ftruncate(fd, (off_t) bytes) != 0) ok = false;
+    }
+    const double created = exchange(rank == 0 && ok ? 1.0 : 0.0);          // barrier: the segment exists (or not)
+    if (created != 1.0) ok = false;
+    if (ok && rank != 0) {
+        fd = shm_open(name, O_RDWR, 0600);
+        if (fd < 0) ok = false;
+    }
+    void *base = nullptr;
+    if (ok) {
+        base = mmap(nullptr, bytes, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+        if (base == MAP_FAILED) { base = nullptr; ok = false; }
+    }
+    if (fd >= 0) close(fd);
+    if (ok && rank == 0) std::memset(base, 0, kHeader);
+    if (ok && cudaHostRegister(base, bytes, cudaHostRegisterPortable) != cudaSuccess) { cudaGetLastError(); munmap(base, bytes); base = nullptr; ok = false; }
+    const double bad = exchange(ok ? 0.0 : 1.0);                             // everyone has mapped (or someone failed)
+    if (rank == 0) shm_unlink(name);                                          // the mapping outlives the name
+    cudaFree(tmp);
+    if (bad != 0.0) {
+        if (base) { cudaHostUnregister(base); munmap(base, bytes); }
+        shm_failed_ = true;
+        if (err) *err = "shared host segment unavailable on some rank (ranks on different nodes?)";
+        return nullptr;
+    }
+    shm_base_ = base;
+    shm_bytes_ = bytes;
+    shm_sense_ = 0;
+    return reinterpret_cast<double *>(static_cast<char *>(shm_base_) + kHeader);
+}
+
+bool Comm::host_barrier()
+{
+    if (!shm_base_) return false;
+    volatile unsigned *count = static_cast<volatile unsigned *>(shm_base_);
+    volatile unsigned *sense = count + 16;                                   // its own cache line
+    shm_sense_ ^= 1;
+    const unsigned mine = (unsigned) shm_sense_;
+    if (__atomic_add_fetch(const_cast<unsigned *>(count), 1u, __ATOMIC_ACQ_REL) == (unsigned) world) {
+        __atomic_store_n(const_cast<unsigned *>(count), 0u, __ATOMIC_RELAXED);
+        __atomic_store_n(const_cast<unsigned *>(sense), mine, __ATOMIC_RELEASE);
+        return true;
+    }
+    const auto t0 = std::chrono::steady_clock::now();
+    unsigned long spins = 0;
+    while (__atomic_load_n(const_cast<unsigned *>(sense), __ATOMIC_ACQUIRE) != mine)
+        if ((++spins & 0xfffff) == 0 && std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > 120.0) return false;
+    return true;
+}
+
 int Comm::finalize()
 {
     if (comm_) {
         cudaDeviceSynchronize();
         teardown_p2p();
+        release_shared_host();
     }
+    shm_failed_ = false;
     if (comm_) api().destroy(comm_);
     comm_ = nullptr;
     rank = 0; world = 1;

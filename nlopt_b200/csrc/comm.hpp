@@ -40,6 +40,14 @@ struct Comm {
     unsigned long long next_seq() { return ++seq_counter_; }
     void advance_seq(unsigned long long by) { seq_counter_ += by; }   // a dual-solve kernel used `by` numbers
 
+    // Host memory shared by the ranks of a node (POSIX shm, page-locked in every process): with plain nlopt_func host
+    // callbacks every rank needs the full x on the host; each rank copies only ITS shard down, into this segment, and a
+    // host-side barrier makes the whole vector visible to all -- n/world instead of n doubles over each PCIe link.
+    // Collective: every rank calls with the same size; returns nullptr on all ranks if any rank failed (the caller
+    // falls back to gathering on the device).  host_barrier() returns false after 120 s (a peer died).
+    double *shared_host(size_t doubles, std::string *err);
+    bool host_barrier();
+
     // collectives on a stream; return 0 on success
     int all_gather_inplace(double *buf, size_t count_per_rank, cudaStream_t s, std::string *err);
     int all_reduce_sum(double *buf, size_t count, cudaStream_t s, std::string *err);
@@ -50,6 +58,12 @@ private:
     double *box_local_ = nullptr;
     unsigned long long seq_counter_ = 0;
     bool force_nccl_ = false;
+    void *shm_base_ = nullptr;          // mapping: 4 KB header (barrier words) + payload
+    size_t shm_bytes_ = 0;
+    unsigned shm_gen_ = 0;
+    int shm_sense_ = 0;
+    bool shm_failed_ = false;
+    void release_shared_host();
     void *handle_ = nullptr;   // dlopen handle
     void *comm_ = nullptr;     // ncclComm_t
 };

@@ -173,6 +173,7 @@ cudaError_t cached_host_alloc(double **p, size_t bytes)
     return cudaHostAlloc(p, bytes, cudaHostAllocMapped);
 }
 
+constexpr int kEndNvp = 4;          // end_outer_kernel: record stride (3 sums)
 constexpr size_t kGuard = 8;        // doubles of guard around x and xcur (halo cells)
 
 int pick_maxm(int m) { return m == 0 ? 0 : m <= 1 ? 1 : m <= 2 ? 2 : m <= 4 ? 4 : m <= 8 ? 8 : 16; }
@@ -329,7 +330,7 @@ bool DeviceBackend::alloc_workspace()
     }
     const size_t ng = geo_.nseg_local;
     const size_t rec = (size_t) (nvp_ > 24 ? nvp_ : 24);
-    if (!small_dev((void **) &partials_, ng * 4 * sizeof(double))) return false;   // end_outer_kernel: one record (3 sums) per group
+    if (!small_dev((void **) &partials_, ng * kEndNvp * sizeof(double))) return false;   // end_outer_kernel: one record (3 sums, stride 4) per group
     // tagged group records {value, tag} of the dual kernels: [nvp][local groups]; tags never repeat (launch ids), so
     // the slots only have to start from zero once
     {
@@ -502,14 +503,28 @@ double *DeviceBackend::staging(unsigned rows)
 bool DeviceBackend::host_x_for(Slot slot)
 {
     // Host callbacks see the full x.  Single rank: one D2H of the shard (= everything).
-    // Several ranks: all-gather the shards on the device, then each rank copies all of it down.
+    // Several ranks: every rank copies its shard into host memory shared by the ranks of the node (Comm::shared_host);
+    // without that, all-gather the shards on the device and copy all of it down on every rank.
     if (h_x_slot_ == (int) slot && h_x_epoch_ == x_epoch_) return true;    // already mirrored
     double *src = slot == kBase ? x_ : xcur_view();
     Comm &comm = Comm::instance();
     if (!comm.active()) {
+        h_x_view_ = h_x_;
         NB_CUDA(cudaMemcpyAsync(h_x_, src, geo_.n_local * sizeof(double), cudaMemcpyDeviceToHost, stream_));
         stats_->d2h_bytes += geo_.n_local * sizeof(double);
+    } else if (double *shared = comm.shared_host(geo_.n, &err_)) {
+        // every rank copies ITS shard into host memory shared by all ranks of the node: n / world doubles per PCIe link
+        if (!comm.host_barrier()) return fail("host barrier timed out (a peer rank died?)");    // the previous x has been read by everyone
+        NB_CUDA(cudaMemcpyAsync(shared + geo_.j0, src, geo_.n_local * sizeof(double), cudaMemcpyDeviceToHost, stream_));
+        NB_CUDA(cudaStreamSynchronize(stream_));
+        if (!comm.host_barrier()) return fail("host barrier timed out (a peer rank died?)");    // every shard has landed
+        stats_->d2h_bytes += geo_.n_local * sizeof(double);
+        h_x_view_ = shared;
+        h_x_slot_ = (int) slot;
+        h_x_epoch_ = x_epoch_;
+        return true;
     } else {
+        h_x_view_ = h_x_;
         NB_CUDA(cudaMemcpyAsync(xfull_dev_ + (size_t) comm.rank * shard_cap_, src, geo_.n_local * sizeof(double),
                                 cudaMemcpyDeviceToDevice, stream_));
         if (comm.all_gather_inplace(xfull_dev_, shard_cap_, stream_, &err_)) return false;
@@ -566,8 +581,8 @@ bool DeviceBackend::eval_penalty_objective(Slot slot, bool want_grad, double *va
                 if (!host_x_for(slot)) return false;
                 double *grad = want_grad ? staging(fs.m) : nullptr;
                 const double t0 = wall_seconds();
-                if (fs.f) vals[row] = fs.f((unsigned) geo_.n, h_x_, grad, fs.data);        // nlopt_eval_constraint, stop.c:178-184
-                else fs.mf(fs.m, &vals[row], (unsigned) geo_.n, h_x_, grad, fs.data);
+                if (fs.f) vals[row] = fs.f((unsigned) geo_.n, h_x_view_, grad, fs.data);        // nlopt_eval_constraint, stop.c:178-184
+                else fs.mf(fs.m, &vals[row], (unsigned) geo_.n, h_x_view_, grad, fs.data);
                 cb_seconds_ += wall_seconds() - t0;
                 if (want_grad && !push_rows_to(pen_rows_ + (size_t) row * geo_.ld, fs.m, grad)) return false;
             }
@@ -663,7 +678,7 @@ bool DeviceBackend::eval_user_objective(Slot slot, bool want_grad, double *value
     if (!host_x_for(slot)) return false;
     double *grad = want_grad ? staging(1) : nullptr;
     const double t0 = wall_seconds();
-    *value = fs.f((unsigned) geo_.n, h_x_, grad, fs.data);
+    *value = fs.f((unsigned) geo_.n, h_x_view_, grad, fs.data);
     cb_seconds_ += wall_seconds() - t0;
     if (want_grad) return push_grad_rows(slot, 0, 1, true, grad);
     return true;
@@ -695,8 +710,8 @@ bool DeviceBackend::eval_constraint(Slot slot, unsigned ic, unsigned row0, bool 
     if (!host_x_for(slot)) return false;       // usually a no-op: the objective call mirrored x already
     double *grad = want_grad ? staging(fs.m) : nullptr;
     const double t0 = wall_seconds();
-    if (fs.f) values[0] = fs.f((unsigned) geo_.n, h_x_, grad, fs.data);        // nlopt_eval_constraint, stop.c:178-184
-    else fs.mf(fs.m, values, (unsigned) geo_.n, h_x_, grad, fs.data);
+    if (fs.f) values[0] = fs.f((unsigned) geo_.n, h_x_view_, grad, fs.data);        // nlopt_eval_constraint, stop.c:178-184
+    else fs.mf(fs.m, values, (unsigned) geo_.n, h_x_view_, grad, fs.data);
     cb_seconds_ += wall_seconds() - t0;
     if (want_grad) return push_grad_rows(slot, (int) row0, fs.m, false, grad);
     return true;
@@ -1281,7 +1296,7 @@ bool DeviceBackend::end_outer(unsigned k, double sigma_min, double *dnorm, doubl
     a.out_host = out_host_; a.flag_host = flag_host_;
     a.seq = seq_ = Comm::instance().active() ? Comm::instance().next_seq() : seq_ + 1;
     a.publish_host = Comm::instance().active() ? 0 : 1;
-    a.nvp = nvp_;
+    a.nvp = kEndNvp;               // records of this kernel: 3 sums, stride 4 (its own stride: nvp_ belongs to the dual kernels)
     a.update_sigma = k > 1;
     a.kappa = variant_ == kMMA ? 0.01 : 1e-8;
     a.sigma_min = sigma_min;
@@ -1289,8 +1304,8 @@ bool DeviceBackend::end_outer(unsigned k, double sigma_min, double *dnorm, doubl
     ++stats_->kernel_launches;
     NB_CUDA(cudaGetLastError());
     if (!a.publish_host) {
-        if (Comm::instance().all_gather_inplace(out_dev_, (size_t) geo_.local_vshards * nvp_, stream_, &err_)) return false;
-        publish_kernel<<<1, 32, 0, stream_>>>(out_dev_, 3, nvp_, out_host_, flag_host_, a.seq);
+        if (Comm::instance().all_gather_inplace(out_dev_, (size_t) geo_.local_vshards * kEndNvp, stream_, &err_)) return false;
+        publish_kernel<<<1, 32, 0, stream_>>>(out_dev_, 3, kEndNvp, out_host_, flag_host_, a.seq);
         ++stats_->kernel_launches;
         NB_CUDA(cudaGetLastError());
     }
@@ -1320,7 +1335,7 @@ bool DeviceBackend::fetch_x(double *x_out)
     if (!xfull_dev_) NB_CUDA(cached_malloc(&xfull_dev_, (size_t) comm.world * shard_cap_ * sizeof(double)));
     h_x_slot_ = -1;
     if (!host_x_for(kBase)) return false;
-    std::memcpy(x_out, h_x_, (size_t) geo_.n * sizeof(double));
+    std::memcpy(x_out, h_x_view_, (size_t) geo_.n * sizeof(double));
     return true;
 }
 

@@ -124,6 +124,7 @@ private:
 
     // staging for host callbacks
     double *h_x_ = nullptr;
+    double *h_x_view_ = nullptr;                     // what the callbacks read: h_x_, or the node-shared segment
     double *h_grad_[2] = {nullptr, nullptr};
     size_t h_grad_cap_ = 0;
     int h_grad_next_ = 0;

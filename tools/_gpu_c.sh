@@ -1,8 +1,11 @@
-M="lts__t_sector_hit_rate.pct,dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum,lts__t_sectors_srcunit_tex_op_read.sum,lts__t_sectors_srcunit_tex_op_read_lookup_hit.sum"
-for extra in "" "--param b200_l2_keep_mb=40" "--param b200_l2_keep_mb=70" "--param b200_prefetch_chunks=0"; do
-  echo "== ncu n=1250000 $extra"
-  timeout 300 ncu --metrics $M --clock-control none -k regex:dual_solve -c 3 --csv python bench.py --n 1250000 --steps 2 --warmup 1 --no-cpu --no-e2e --no-parity --param dual_maxeval=40 $extra 2>/dev/null | grep -E "dual_solve" | awk -F'","' '{print $(NF-2), $(NF)}' | tr -d '"' | paste - - - - - - | head -3
-done
+P='import json,sys; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print(d["config"]["algorithm"], d["config"]["n"], "evals/s", round(d["value"]), "ms/step", round(d["ms_per_step"],3), "evals", d["dual_evals"], "us/eval", round(d["roofline"]["avg_launch_us"],2), "frac", round(d["roofline"]["frac"],4), "f", d["f_after_steps"], "eval_wall", round(d["wall_breakdown_s"]["seconds_eval_wall"]*1e3/d["steps"],3))'
+b() { echo "== bench $*"; timeout 300 python bench.py --steps 8 --warmup 3 --no-cpu --no-e2e --no-parity "$@" 2>&1 | tail -1 | python -c "$P"; }
+for n in 1250000 2500000 10000000; do for u in 1 2; do b --n $n --param b200_solve_unroll=$u; done; done
+b --alg mma --param b200_solve_unroll=2
+b --alg mma --n 1250000 --param b200_solve_unroll=1
+b --alg mma --n 1250000 --param b200_solve_unroll=2
+b --n 1250000 --param b200_l2_keep_mb=100
+b --n 100000
+b --n 10000
 python tools/trace_solve.py run 1250000 ccsaq
-head -6 gpurun_out/trace_ccsaq_1250000.txt | cut -c1-400
-timeout 1500 python -m pytest tests -m gpu -q -x 2>&1 | tail -15
+timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -q -x 2>&1 | tail -4
