@@ -72,17 +72,33 @@ __device__ __forceinline__ double2 ld_stream_pol(const double2 *p, unsigned long
     asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;" : "=d"(v.x), "=d"(v.y) : "l"(p), "l"(pol));
     return v;
 }
+// L1 prefetch experiment (b200_l1_prefetch): bit 31 of the mask.  The sweep then asks the L1 for the NEXT chunk of every
+// operand array (prefetch.global.L1, no register cost) while it works on the current one, and loads with L1 allocation,
+// so that the dependent load -> compute chain of a small shard finds its operands a few cycles away.
+constexpr unsigned kL1PrefetchBit = 1u << 31;
+__device__ __forceinline__ double2 ld_alloc(const double2 *p)
+{
+    double2 v;
+    asm volatile("ld.global.nc.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
 struct L2Policies {
     unsigned long long keep, stream;
     unsigned mask;                      // bit k set: operand array k (0 x, 1 lb, 2 ub, 3 sigma, 4 grad f, 5+i row i) is kept
+    bool l1pf;
     __device__ __forceinline__ void init(unsigned m)
     {
+        l1pf = (m & kL1PrefetchBit) != 0u;
+        m &= ~kL1PrefetchBit;
         mask = m;
         asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(keep));
         asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(stream));
     }
     __device__ __forceinline__ double2 ld(const double2 *p, int k) const
     {
+        if (l1pf) return ld_alloc(p);
         if (mask == 0u) return ld_stream(p);          // nothing to protect: the plain streaming load (no policy operand)
         return ld_stream_pol(p, ((mask >> k) & 1u) ? keep : stream);
     }
@@ -507,6 +523,16 @@ __device__ __forceinline__ void sweep_group(const DualArgs &a, const MU &mu, con
             vs[u] = make_double2(0.0, 0.0);      // sigma = 0 lanes are skipped by both formulas
             vx[u] = vlb[u] = vub[u] = vg[u] = make_double2(0.0, 0.0);
             if (live) {
+                if (POL && pol.l1pf && u == UNROLL - 1) {
+                    const unsigned long long pn = p + kChunkPairs;                  // this lane's pair of the next chunk
+                    if (pn < p_hi) {
+                        prefetch_l1(x2 + pn); prefetch_l1(lb2 + pn); prefetch_l1(ub2 + pn); prefetch_l1(s2v + pn); prefetch_l1(g2 + pn);
+#pragma unroll
+                        for (int i = 0; i < MR; ++i)
+                            if (MAXM > 0 && (FULL || i < mu.m))
+                                prefetch_l1(reinterpret_cast<const double2 *>(a.G + (unsigned long long) i * a.ld) + pn);
+                    }
+                }
                 if (POL) {
                     vx[u] = pol.ld(x2 + p, 0); vlb[u] = pol.ld(lb2 + p, 1); vub[u] = pol.ld(ub2 + p, 2);
                     vs[u] = pol.ld(s2v + p, 3); vg[u] = pol.ld(g2 + p, 4);

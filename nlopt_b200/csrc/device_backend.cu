@@ -939,7 +939,7 @@ void DeviceBackend::fill_dual_args(DualArgs &a, const double *y, const DualScala
         // the mailbox holds records of <= 19 sums: the wide kernel exchanges through ncclAllGather
         for (int r = 0; r < 8; ++r) a.box[r] = (cm.active() && cm.use_p2p() && !wide && r < cm.world) ? cm.box_peer[r] : nullptr;
     }
-    a.l2_keep = l2_keep_mask();
+    a.l2_keep = l2_keep_mask() | (l1_prefetch_ ? kL1PrefetchBit : 0u);
     // the L2 prefetch of a waiting sweeper only pays when the operands of a generation do not stay in the L2 anyway
     a.prefetch_chunks = (prefetch_forced_ || (5 + (size_t) m_) * geo_.ld * sizeof(double) >= (64u << 20)) ? prefetch_chunks_ : 0u;
     a.m = (int) m_;
@@ -1413,6 +1413,7 @@ bool DeviceBackend::configure(const char *key, long long value)
     if (k == "ctas_per_sm") { ctas_per_sm_ = (int) value; return true; }
     if (k == "fused_solve") { fused_solve_ok_ = value != 0; return true; }
     if (k == "solve_tma") { solve_tma_ = (int) value; return true; }
+    if (k == "l1_prefetch") { l1_prefetch_ = value != 0; return true; }
     if (k == "prefetch_chunks") { prefetch_chunks_ = value < 0 ? 0u : (unsigned) value; prefetch_forced_ = true; return true; }
     if (k == "l2_keep_mb") {
         l2_keep_bytes_ = value <= 0 ? 0 : (size_t) value << 20;

@@ -99,6 +99,7 @@ private:
     std::vector<double> wide_host_;
     size_t l2_keep_bytes_ = 0;        // operand bytes to load evict_last (knob b200_l2_keep_mb)
     int solve_tma_ = 0;               // knob b200_solve_tma: 0 register form (default: faster at every size measured, profiles/r02_solve_tma_ab.txt), 1 TMA-staged form, -1 by size
+    bool l1_prefetch_ = false;        // knob b200_l1_prefetch (experiment): L1 prefetch of the next chunk inside the sweep
     bool prefetch_forced_ = false;
     unsigned prefetch_chunks_ = 3;    // knob b200_prefetch_chunks (solve kernel: L2 prefetch of a waiting sweeper's next group)
     size_t out_rec_ = 0;              // doubles per result record (>= 24, >= 3 + m)

@@ -86,3 +86,86 @@ def test_two_rank_fold_is_bit_identical_to_one_rank(built, variant):
     whole = ob.port_dual(variant, dict(inst, f0=0.0, c0=np.zeros(M)))
     ref = np.array([-whole["ret"], whole["g0"], whole["w"], *whole["gc"]])
     assert np.allclose(single, ref, rtol=1e-12, atol=1e-9)
+
+
+# ---- the rank-count-independent protocol of the device callbacks (include/nlopt_b200.h: nlopt_b200_dfunc2) ----------
+class ShardGeo(C.Structure):
+    _fields_ = [("n", C.c_ulonglong), ("n_local", C.c_ulonglong), ("j0", C.c_ulonglong), ("nchunks", C.c_ulonglong),
+                ("chunk0", C.c_ulonglong), ("groups_total", C.c_uint), ("group0", C.c_uint), ("groups_local", C.c_uint),
+                ("groups_per_vshard", C.c_uint), ("vshard0", C.c_uint), ("local_vshards", C.c_uint), ("rank", C.c_int),
+                ("world", C.c_int)]
+
+
+def geometry(n, rank, world):
+    g = ShardGeo()
+    _capi.default_library().nlopt_b200_shard_geometry(n, rank, world, C.byref(g))
+    return g
+
+
+def group_range(g, k):
+    """variables [lo, hi) of global group k, relative to the start of the rank that owns it"""
+    lo = (k * g.nchunks // g.groups_total - g.chunk0) * 512
+    hi = ((k + 1) * g.nchunks // g.groups_total - g.chunk0) * 512
+    return lo, min(hi, g.n_local)
+
+
+def test_shard_geometry_groups_tile_and_do_not_depend_on_the_world_size(built):
+    for n in (1, 511, 513, 100003, 1250000, 10**7):
+        g1 = geometry(n, 0, 1)
+        assert g1.groups_total == 8 * g1.groups_per_vshard and g1.groups_local == g1.groups_total
+        cover = 0
+        for k in range(g1.groups_total):
+            lo, hi = group_range(g1, k)
+            assert lo == min(cover, max(lo, 0)) or lo >= cover
+            cover = max(cover, hi)
+        assert cover == n
+        for world in (2, 4, 8):
+            tot = 0
+            for r in range(world):
+                g = geometry(n, r, world)
+                assert (g.groups_total, g.groups_per_vshard, g.nchunks) == (g1.groups_total, g1.groups_per_vshard, g1.nchunks)
+                assert g.vshard0 == r * (8 // world) and g.local_vshards == 8 // world and g.group0 == g.vshard0 * g.groups_per_vshard
+                for k in range(g.group0, g.group0 + g.groups_local):       # the same global variables as on one rank
+                    lo, hi = group_range(g, k)
+                    lo1, hi1 = group_range(g1, k)
+                    assert (g.j0 + lo, g.j0 + max(hi, lo)) == (lo1, max(hi1, lo1))
+                tot += g.n_local
+            assert tot == n
+
+
+def _value_worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    n = 100003
+    x = synth.u01(7, n)
+    g = geometry(n, rank, world)
+    block = np.zeros((3, 8))                                     # [1 + m][8] virtual-shard sums, this rank's slots only
+    for f in range(3):
+        for v in range(g.vshard0, g.vshard0 + g.local_vshards):
+            s = 0.0
+            for k in range(v * g.groups_per_vshard, (v + 1) * g.groups_per_vshard):
+                lo, hi = group_range(g, k)
+                s += float(np.sum(x[g.j0 + lo:g.j0 + hi] ** (f + 1))) if hi > lo else 0.0
+            block[f, v] = s
+    t = torch.from_numpy(block)
+    dist.all_reduce(t)                                           # every slot is non-zero on exactly one rank: exact
+    out[rank] = [float(np.add.reduce(t.numpy()[f])) if False else float(sum_in_order(t.numpy()[f])) for f in range(3)]
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def sum_in_order(a):
+    s = a[0]
+    for v in a[1:]:
+        s = s + v
+    return s
+
+
+def test_device_callback_values_are_bit_identical_for_two_ranks(built):
+    mgr = mp.Manager()
+    one, two = mgr.dict(), mgr.dict()
+    port = 31500 + (os.getpid() % 2000)
+    mp.spawn(_value_worker, args=(1, port, one), nprocs=1, join=True)
+    mp.spawn(_value_worker, args=(2, port + 1, two), nprocs=2, join=True)
+    assert list(two[0]) == list(one[0]) and list(two[1]) == list(one[0])

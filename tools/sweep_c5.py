@@ -108,7 +108,7 @@ def main():
                 cross = [r["n"] for r in pts if r["speedup_vs_cpu"] > 1.0]
                 if pts:
                     summary[f"{vname}_m{m}_crossover_n"] = min(cross) if cross else None
-        outp = os.path.join(ROOT, "gpurun_out", f"sweep_c5_n{world}.json")
+        outp = os.path.join(ROOT, "gpurun_out", f"sweep_c5_n{world}{os.environ.get('SWEEP_TAG', '')}.json")
         os.makedirs(os.path.dirname(outp), exist_ok=True)
         json.dump({"n_gpus": world, "peak_gbs": peak, "rows": rows, "crossover": summary,
                    "what": "one whole dual solve of 60 + 1 evaluations per point (nlopt_b200_dual_solve), best of 2 after a warm-up"}, open(outp, "w"), indent=1)
