@@ -206,6 +206,8 @@ double *Comm::shared_host(size_t doubles, std::string *err)
     constexpr size_t kHeader = 4096;
     const size_t want = kHeader + doubles * sizeof(double);
     if (!active() || shm_failed_) return nullptr;
+    if (const char *e = std::getenv("NLOPT_B200_SHARED_HOST_X"))
+        if (e[0] == '0') return nullptr;                 // every rank gathers x on the device and copies all of it down
     if (shm_base_ && shm_bytes_ >= want) return reinterpret_cast<double *>(static_cast<char *>(shm_base_) + kHeader);
     // (re)create: every rank takes every step, whatever its local outcome; the verdict is collective
     cudaDeviceSynchronize();
