@@ -32,6 +32,19 @@
 #include <cstdint>
 
 #include "dual_mma.hpp"
+#include "pair_math.cuh"
+
+// NB200_PAIR = 1 (default): the sweep evaluates the two variables of a 128-bit load with the straight-line closed forms
+// of pair_math.cuh / mma_pair / ccsaq_pair; 0: one variable after the other through mma_point / ccsaq_point (the A/B
+// build of tools/ab_build.py).  Both give the same bits.
+#ifndef NB200_PAIR
+#define NB200_PAIR 1
+#endif
+// NB200_PRELOAD = 1 (default): the persistent solve kernel requests the first chunk of a group before it waits for the
+// generation's multipliers (load_chunk / sweep_group_preloaded); 0: loads start after the multipliers have arrived.
+#ifndef NB200_PRELOAD
+#define NB200_PRELOAD 1
+#endif
 
 namespace nb200 {
 
@@ -350,6 +363,161 @@ __device__ __forceinline__ double ccsaq_point(const MU &a, double x, double lb, 
     return xc;
 }
 
+// Where the pair form of MMA is used.  Measured on the B200 (profiles/r02b_ab_pair_preload.txt): CCSAQ gains at every size
+// and row count; MMA gains with <= 2 gradient rows, but with 4 or more rows the two interleaved variables no longer fit
+// the 80-register budget of 3 CTAs/SM (spills: 162.9 vs 134.5 us per evaluation at n = 1e7, m = 4) -- there the
+// sequential form stays.
+#ifndef NB200_PAIR_MMA_MAXM
+#define NB200_PAIR_MMA_MAXM 2
+#endif
+template <int MAXM>
+constexpr bool kPairMMA = MAXM <= NB200_PAIR_MMA_MAXM;
+
+// ---- the same closed forms for the two variables of one 128-bit load, as straight-line code (pair_math.cuh) -------
+// Every value is produced by the same operation on the same operands as in mma_point / ccsaq_point; only the divisions,
+// the square root and the reciprocal come from the written-out fast paths, with the builtins as the fallback.
+template <int MAXM, bool FULL, class MU>
+__device__ __forceinline__ double2 mma_pair(const MU &a, const double2 x, const double2 lb, const double2 ub, const double2 s,
+                                            const double2 g, const double (&Ga)[MAXM > 0 ? MAXM : 1],
+                                            const double (&Gb)[MAXM > 0 ? MAXM : 1], double (&acc)[3 + (MAXM > 0 ? MAXM : 1)])
+{
+    double2 xc;
+    if (s.x == 0 || s.y == 0) {                              // a fixed variable or a padding lane in the pair (mma.c:96-99)
+        xc.x = mma_point<MAXM, FULL>(a, x.x, lb.x, ub.x, s.x, g.x, Ga, acc);
+        xc.y = mma_point<MAXM, FULL>(a, x.y, lb.y, ub.y, s.y, g.y, Gb, acc);
+        return xc;
+    }
+    // u, v (mma.c:101-106)
+    const double v0A = addx(mulx(fabs(g.x), s.x), a.half_rho), v0B = addx(mulx(fabs(g.y), s.y), a.half_rho);
+    double uA = g.x, uB = g.y, vA = v0A, vB = v0B;
+#pragma unroll
+    for (int i = 0; i < MAXM; ++i)
+        if (FULL || (i < a.m && ((a.active >> i) & 1u))) {
+            const double yi = a.y[i], hi = a.half_rhoc[i];
+            uA = addx(uA, mulx(Ga[i], yi));
+            uB = addx(uB, mulx(Gb[i], yi));
+            vA = addx(vA, mulx(addx(mulx(fabs(Ga[i]), s.x), hi), yi));
+            vB = addx(vB, mulx(addx(mulx(fabs(Gb[i]), s.y), hi), yi));
+        }
+    const double s2A = mulx(s.x, s.x), s2B = mulx(s.y, s.y);
+    uA = mulx(uA, s2A);
+    uB = mulx(uB, s2B);
+    // dx (mma.c:108): four independent divisions, two square roots, two more divisions
+    unsigned bad = 0u;
+    const double rA = div_fast(uA, mulx(vA, s.x), bad), rB = div_fast(uB, mulx(vB, s.y), bad);
+    const double qA = div_fast(uA, vA, bad), qB = div_fast(uB, vB, bad);
+    const double sqA = sqrt_fast(fabs(subx(1.0, mulx(rA, rA))), bad), sqB = sqrt_fast(fabs(subx(1.0, mulx(rB, rB))), bad);
+    double dxA = div_fast(qA, subx(-1.0, sqA), bad), dxB = div_fast(qB, subx(-1.0, sqB), bad);
+    if (bad) {                                               // some operand outside the fast paths' range: the builtins
+        const double r1 = divx(uA, mulx(vA, s.x)), r2 = divx(uB, mulx(vB, s.y));
+        dxA = divx(divx(uA, vA), subx(-1.0, __dsqrt_rn(fabs(subx(1.0, mulx(r1, r1))))));
+        dxB = divx(divx(uB, vB), subx(-1.0, __dsqrt_rn(fabs(subx(1.0, mulx(r2, r2))))));
+    }
+    // clamps (mma.c:109-114)
+    double xA = addx(x.x, dxA), xB = addx(x.y, dxB);
+    if (xA > ub.x) xA = ub.x; else if (xA < lb.x) xA = lb.x;
+    if (xB > ub.y) xB = ub.y; else if (xB < lb.y) xB = lb.y;
+    const double limA = mulx(0.9, s.x), limB = mulx(0.9, s.y);
+    const double hiA = addx(x.x, limA), loA = subx(x.x, limA), hiB = addx(x.y, limB), loB = subx(x.y, limB);
+    if (xA > hiA) xA = hiA; else if (xA < loA) xA = loA;
+    if (xB > hiB) xB = hiB; else if (xB < loB) xB = loB;
+    dxA = subx(xA, x.x);
+    dxB = subx(xB, x.y);
+    const double dx2A = mulx(dxA, dxA), dx2B = mulx(dxB, dxB);
+    const double dA = subx(s2A, dx2A), dB = subx(s2B, dx2B);
+    unsigned bad2 = 0u;
+    double dinvA = rcp_fast(dA, bad2), dinvB = rcp_fast(dB, bad2);
+    if (bad2) {
+        dinvA = divx(1.0, dA);
+        dinvB = divx(1.0, dB);
+    }
+    // the sums (mma.c:119-129): first variable, then second, as the sequential form adds them
+    const double cA = mulx(s2A, dxA), cB = mulx(s2B, dxB);
+    acc[0] = addx(acc[0], mulx(addx(mulx(uA, dxA), mulx(vA, dx2A)), dinvA));
+    acc[0] = addx(acc[0], mulx(addx(mulx(uB, dxB), mulx(vB, dx2B)), dinvB));
+    acc[1] = addx(acc[1], mulx(addx(mulx(g.x, cA), mulx(v0A, dx2A)), dinvA));
+    acc[1] = addx(acc[1], mulx(addx(mulx(g.y, cB), mulx(v0B, dx2B)), dinvB));
+    acc[2] = addx(acc[2], mulx(mulx(0.5, dx2A), dinvA));
+    acc[2] = addx(acc[2], mulx(mulx(0.5, dx2B), dinvB));
+#pragma unroll
+    for (int k = 0; k < MAXM; ++k)
+        if (FULL || (k < a.m && ((a.active >> k) & 1u))) {
+            const double hk = a.half_rhoc[k];
+            acc[3 + k] = addx(acc[3 + k], mulx(addx(mulx(Ga[k], cA), mulx(addx(mulx(fabs(Ga[k]), s.x), hk), dx2A)), dinvA));
+            acc[3 + k] = addx(acc[3 + k], mulx(addx(mulx(Gb[k], cB), mulx(addx(mulx(fabs(Gb[k]), s.y), hk), dx2B)), dinvB));
+        }
+    xc.x = xA;
+    xc.y = xB;
+    return xc;
+}
+
+// CCSAQ: the divisor of the first division is u = rho + sum rhoc_i y_i, the same for every variable
+// (ccsa_quadratic.c:116-122): its reciprocal is prepared once per group (`U`); the other two divisions of a variable
+// share the divisor sigma^2 (:134-138) and one prepared reciprocal.
+template <int MAXM, bool FULL, class MU>
+__device__ __forceinline__ double2 ccsaq_pair(const MU &a, const DivBy &U, const double2 x, const double2 lb, const double2 ub,
+                                              const double2 s, const double2 g, const double (&Ga)[MAXM > 0 ? MAXM : 1],
+                                              const double (&Gb)[MAXM > 0 ? MAXM : 1], double (&acc)[3 + (MAXM > 0 ? MAXM : 1)])
+{
+    double2 xc;
+    if (s.x == 0 || s.y == 0) {                              // ccsa_quadratic.c:111-114
+        xc.x = ccsaq_point<MAXM, FULL>(a, x.x, lb.x, ub.x, s.x, g.x, Ga, acc);
+        xc.y = ccsaq_point<MAXM, FULL>(a, x.y, lb.y, ub.y, s.y, g.y, Gb, acc);
+        return xc;
+    }
+    double vA = g.x, vB = g.y;
+#pragma unroll
+    for (int i = 0; i < MAXM; ++i)
+        if (FULL || i < a.m) {
+            const double yi = a.y[i];
+            vA = addx(vA, mulx(Ga[i], yi));
+            vB = addx(vB, mulx(Gb[i], yi));
+        }
+    const double u = U.b;
+    const double s2A = mulx(s.x, s.x), s2B = mulx(s.y, s.y);
+    const double nA = mulx(-s2A, vA), nB = mulx(-s2B, vB);
+    unsigned bad = 0u;
+    double dxA = div_by(nA, U, bad), dxB = div_by(nB, U, bad);        // ccsa_quadratic.c:122
+    if (bad) {
+        dxA = divx(nA, u);
+        dxB = divx(nB, u);
+    }
+    if (fabs(dxA) > s.x) dxA = copysign(s.x, dxA);          // :126
+    if (fabs(dxB) > s.y) dxB = copysign(s.y, dxB);
+    double xA = addx(x.x, dxA), xB = addx(x.y, dxB);
+    if (xA > ub.x) xA = ub.x; else if (xA < lb.x) xA = lb.x;
+    if (xB > ub.y) xB = ub.y; else if (xB < lb.y) xB = lb.y;
+    dxA = subx(xA, x.x);
+    dxB = subx(xB, x.y);
+    const double dx2A = mulx(dxA, dxA), dx2B = mulx(dxB, dxB);
+    const double hu = mulx(0.5, u);
+    const double n0A = mulx(hu, dx2A), n0B = mulx(hu, dx2B), n1A = mulx(0.5, dx2A), n1B = mulx(0.5, dx2B);
+    const DivBy SA = prep_div(s2A), SB = prep_div(s2B);
+    unsigned bad2 = 0u;
+    double t0A = div_by(n0A, SA, bad2), t0B = div_by(n0B, SB, bad2);
+    double qA = div_by(n1A, SA, bad2), qB = div_by(n1B, SB, bad2);
+    if (bad2) {
+        t0A = divx(n0A, s2A); t0B = divx(n0B, s2B);
+        qA = divx(n1A, s2A); qB = divx(n1B, s2B);
+    }
+    acc[0] = addx(acc[0], addx(mulx(vA, dxA), t0A));        // :134
+    acc[0] = addx(acc[0], addx(mulx(vB, dxB), t0B));
+    acc[1] = addx(acc[1], addx(mulx(g.x, dxA), mulx(a.rho, qA)));   // :137
+    acc[1] = addx(acc[1], addx(mulx(g.y, dxB), mulx(a.rho, qB)));
+    acc[2] = addx(acc[2], qA);                               // :138
+    acc[2] = addx(acc[2], qB);
+#pragma unroll
+    for (int k = 0; k < MAXM; ++k)
+        if (FULL || k < a.m) {
+            const double rk = a.rhoc[k];
+            acc[3 + k] = addx(acc[3 + k], addx(mulx(Ga[k], dxA), mulx(rk, qA)));     // :139-140
+            acc[3 + k] = addx(acc[3 + k], addx(mulx(Gb[k], dxB), mulx(rk, qB)));
+        }
+    xc.x = xA;
+    xc.y = xB;
+    return xc;
+}
+
 template <int NV>
 __device__ __forceinline__ void warp_fold(double (&acc)[NV])
 {
@@ -512,6 +680,10 @@ __device__ __forceinline__ void sweep_group(const DualArgs &a, const MU &mu, con
     const double2 *g2 = reinterpret_cast<const double2 *>(a.g);
     unsigned long long p_lo, p_hi;
     group_pairs(a.nchunks, a.nseg_total, a.chunk0, a.seg0 + gl, &p_lo, &p_hi);
+#if NB200_PAIR
+    DivBy U;
+    if (VARIANT != 0) U = prep_div(mu.u());                  // CCSAQ: every variable divides by the same u
+#endif
 
     for (unsigned long long p0 = p_lo + sub * 32 + lane; p0 < p_hi; p0 += (unsigned long long) kChunkPairs * UNROLL) {
         double2 vx[UNROLL], vlb[UNROLL], vub[UNROLL], vs[UNROLL], vg[UNROLL];
@@ -558,6 +730,14 @@ __device__ __forceinline__ void sweep_group(const DualArgs &a, const MU &mu, con
             const unsigned long long p = p0 + (unsigned long long) kChunkPairs * u;
             const bool live = u == 0 || p < p_hi;
             double2 xc;
+#if NB200_PAIR
+            if (VARIANT == 0 && kPairMMA<MAXM>) xc = mma_pair<MAXM, FULL>(mu, vx[u], vlb[u], vub[u], vs[u], vg[u], Ga[u], Gb[u], acc);
+            else if (VARIANT != 0) xc = ccsaq_pair<MAXM, FULL>(mu, U, vx[u], vlb[u], vub[u], vs[u], vg[u], Ga[u], Gb[u], acc);
+            else {
+                xc.x = mma_point<MAXM, FULL>(mu, vx[u].x, vlb[u].x, vub[u].x, vs[u].x, vg[u].x, Ga[u], acc);
+                xc.y = mma_point<MAXM, FULL>(mu, vx[u].y, vlb[u].y, vub[u].y, vs[u].y, vg[u].y, Gb[u], acc);
+            }
+#else
             if (VARIANT == 0) {
                 xc.x = mma_point<MAXM, FULL>(mu, vx[u].x, vlb[u].x, vub[u].x, vs[u].x, vg[u].x, Ga[u], acc);
                 xc.y = mma_point<MAXM, FULL>(mu, vx[u].y, vlb[u].y, vub[u].y, vs[u].y, vg[u].y, Gb[u], acc);
@@ -565,8 +745,99 @@ __device__ __forceinline__ void sweep_group(const DualArgs &a, const MU &mu, con
                 xc.x = ccsaq_point<MAXM, FULL>(mu, vx[u].x, vlb[u].x, vub[u].x, vs[u].x, vg[u].x, Ga[u], acc);
                 xc.y = ccsaq_point<MAXM, FULL>(mu, vx[u].y, vlb[u].y, vub[u].y, vs[u].y, vg[u].y, Gb[u], acc);
             }
+#endif
             if (store && live) st_stream(reinterpret_cast<double2 *>(a.xcur) + p, xc);
         }
+    }
+}
+
+// ---- the same sweep in two halves: the operand loads of a chunk, and the arithmetic on them --------------------------
+// The persistent solve kernel issues the loads of the FIRST chunk of a group before it looks for the multipliers of the
+// generation (the operands do not depend on y): while warp 0 polls the published slots and the CTA meets at its barrier
+// the 5+m loads of every thread are already in flight, so one load latency (~1 us from HBM, ~0.7 us from the L2) leaves
+// the critical path of every generation.  Same lanes, same order of operations as sweep_group: the same bits.
+template <int MAXM>
+struct ChunkOperands {
+    double2 x, lb, ub, s, g;
+    double Ga[MAXM > 0 ? MAXM : 1], Gb[MAXM > 0 ? MAXM : 1];
+};
+
+template <int MAXM, bool FULL, bool POL>
+__device__ __forceinline__ void load_chunk(const DualArgs &a, int m, const L2Policies &pol, unsigned long long p, bool live,
+                                           ChunkOperands<MAXM> &r)
+{
+    constexpr int MR = MAXM > 0 ? MAXM : 1;
+    r.s = make_double2(0.0, 0.0);                 // sigma = 0 lanes are skipped by both formulas
+    r.x = r.lb = r.ub = r.g = make_double2(0.0, 0.0);
+    if (live) {
+        const double2 *x2 = reinterpret_cast<const double2 *>(a.x) + p;
+        const double2 *lb2 = reinterpret_cast<const double2 *>(a.lb) + p;
+        const double2 *ub2 = reinterpret_cast<const double2 *>(a.ub) + p;
+        const double2 *s2v = reinterpret_cast<const double2 *>(a.sigma) + p;
+        const double2 *g2 = reinterpret_cast<const double2 *>(a.g) + p;
+        if (POL) {
+            r.x = pol.ld(x2, 0); r.lb = pol.ld(lb2, 1); r.ub = pol.ld(ub2, 2); r.s = pol.ld(s2v, 3); r.g = pol.ld(g2, 4);
+        } else {
+            r.x = ld_stream(x2); r.lb = ld_stream(lb2); r.ub = ld_stream(ub2); r.s = ld_stream(s2v); r.g = ld_stream(g2);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < MR; ++i) {
+        r.Ga[i] = 0.0;
+        r.Gb[i] = 0.0;
+        if (MAXM > 0 && (FULL || i < m) && live) {
+            const double2 *gp = reinterpret_cast<const double2 *>(a.G + (unsigned long long) i * a.ld) + p;
+            const double2 t = POL ? pol.ld(gp, 5 + i) : ld_stream(gp);
+            r.Ga[i] = t.x;
+            r.Gb[i] = t.y;
+        }
+    }
+}
+
+// PAIR_MMA: the MMA pair form (callers with a 128-register budget set it for any row count)
+template <int VARIANT, int MAXM, bool FULL, bool PAIR_MMA, class MU>
+__device__ __forceinline__ double2 compute_chunk(const MU &mu, const DivBy &U, const ChunkOperands<MAXM> &r,
+                                                 double (&acc)[3 + (MAXM > 0 ? MAXM : 1)])
+{
+    double2 xc;
+#if NB200_PAIR
+    if (VARIANT == 0 && PAIR_MMA) xc = mma_pair<MAXM, FULL>(mu, r.x, r.lb, r.ub, r.s, r.g, r.Ga, r.Gb, acc);
+    else if (VARIANT != 0) xc = ccsaq_pair<MAXM, FULL>(mu, U, r.x, r.lb, r.ub, r.s, r.g, r.Ga, r.Gb, acc);
+    else {
+        xc.x = mma_point<MAXM, FULL>(mu, r.x.x, r.lb.x, r.ub.x, r.s.x, r.g.x, r.Ga, acc);
+        xc.y = mma_point<MAXM, FULL>(mu, r.x.y, r.lb.y, r.ub.y, r.s.y, r.g.y, r.Gb, acc);
+    }
+#else
+    if (VARIANT == 0) {
+        xc.x = mma_point<MAXM, FULL>(mu, r.x.x, r.lb.x, r.ub.x, r.s.x, r.g.x, r.Ga, acc);
+        xc.y = mma_point<MAXM, FULL>(mu, r.x.y, r.lb.y, r.ub.y, r.s.y, r.g.y, r.Gb, acc);
+    } else {
+        xc.x = ccsaq_point<MAXM, FULL>(mu, r.x.x, r.lb.x, r.ub.x, r.s.x, r.g.x, r.Ga, acc);
+        xc.y = ccsaq_point<MAXM, FULL>(mu, r.x.y, r.lb.y, r.ub.y, r.s.y, r.g.y, r.Gb, acc);
+    }
+#endif
+    return xc;
+}
+
+// the rest of a group whose first chunk (pair index p_first of this lane, `first`) is already on its way
+template <int VARIANT, int MAXM, bool FULL, bool POL, bool PAIR_MMA, class MU>
+__device__ __forceinline__ void sweep_group_preloaded(const DualArgs &a, const MU &mu, const L2Policies &pol, bool store,
+                                                      unsigned long long p_first, unsigned long long p_hi, ChunkOperands<MAXM> &r,
+                                                      double (&acc)[3 + (MAXM > 0 ? MAXM : 1)])
+{
+    DivBy U;
+    U.b = 1.0; U.r = 1.0; U.hb = 0x3ff00000; U.zero_ok = 1u;
+#if NB200_PAIR
+    if (VARIANT != 0) U = prep_div(mu.u());                  // CCSAQ: every variable divides by the same u
+#endif
+    unsigned long long p = p_first;
+    bool live = p < p_hi;
+    while (live) {
+        const double2 xc = compute_chunk<VARIANT, MAXM, FULL, PAIR_MMA>(mu, U, r, acc);
+        if (store) st_stream(reinterpret_cast<double2 *>(a.xcur) + p, xc);
+        p += kChunkPairs;
+        live = p < p_hi;
+        if (live) load_chunk<MAXM, FULL, POL>(a, mu.m, pol, p, true, r);
     }
 }
 
@@ -1035,6 +1306,20 @@ constexpr int kTraceGens = 512;
 // lane and every lane executes the same scalar control flow.  Sums over i are taken in index order through shuffles,
 // so every operation and its order are those of the host machine: the two produce the same bits
 // (tests/test_gpu_parity.py::test_fused_solve_equals_host_driven).
+// MAXM bounds m at compile time: with NB200_MACH_UNROLL the index-order sums over the multipliers are unrolled with a
+// predicate, so that their shuffles are issued back to back instead of one per loop trip (they sit on the serial path
+// of every generation).
+#ifndef NB200_MACH_UNROLL
+#define NB200_MACH_UNROLL 1
+#endif
+#if NB200_MACH_UNROLL
+#define NB_MACH_FOR(i, MAXM, m) _Pragma("unroll") for (int i = 0; i < (MAXM); ++i)
+#define NB_MACH_IF(i, m) if ((i) < (m))
+#else
+#define NB_MACH_FOR(i, MAXM, m) for (int i = 0; i < (m); ++i)
+#define NB_MACH_IF(i, m)
+#endif
+template <int MAXM>
 struct WarpDualMachine {
     double y, g, sigma, ycur, yprev, yprevprev, lo, hi;          // lane i: element i (lanes >= m: sigma = 0)
     double rho, fbase, fmin, fcur, fprev, gval, wval;
@@ -1081,8 +1366,10 @@ struct WarpDualMachine {
     {
         const double d = fabs(subx(ycur, yprev)), a = fabs(ycur);
         double dn = 0.0, xn = 0.0;
-        for (int i = 0; i < m; ++i) dn = addx(dn, __shfl_sync(0xffffffffu, d, i));
-        for (int i = 0; i < m; ++i) xn = addx(xn, __shfl_sync(0xffffffffu, a, i));
+        NB_MACH_FOR(i, MAXM, m) {
+            const double di = __shfl_sync(0xffffffffu, d, i), ai = __shfl_sync(0xffffffffu, a, i);
+            NB_MACH_IF(i, m) { dn = addx(dn, di); xn = addx(xn, ai); }
+        }
         if (dn < mulx(st.xtol_rel, xn)) return true;
         return !__any_sync(0xffffffffu, lane < m && d >= st.xtol_abs);
     }
@@ -1161,9 +1448,10 @@ struct WarpDualMachine {
             wt = mulx(mulx(0.5, dy2), dinv);
         }
         double gs = fbase, ws = 0.0;                      // mma.c:123-125: the terms added in index order
-        for (int i = 0; i < m; ++i) {
+        NB_MACH_FOR(i, MAXM, m) {
             const double gi = __shfl_sync(0xffffffffu, gt, i), wi = __shfl_sync(0xffffffffu, wt, i);
-            if (__shfl_sync(0xffffffffu, (int) has, i)) { gs = addx(gs, gi); ws = addx(ws, wi); }
+            const int hi_ = __shfl_sync(0xffffffffu, (int) has, i);
+            NB_MACH_IF(i, m) if (hi_) { gs = addx(gs, gi); ws = addx(ws, wi); }
         }
         gval = gs;
         wval = ws;
@@ -1212,11 +1500,17 @@ __device__ __noinline__ void solve_folder(const SolveArgs &sa, double *s_vs, dou
     const int sub = threadIdx.x >> 5;
     const unsigned ngroups = a.segs_per_vshard * a.local_vshards;
     __shared__ int s_exit;
-    WarpDualMachine mach;                             // meaningful in warp 0 only
-    int final_pass = 0;
+    constexpr int MAXM = NV - 3;
+    // The dual optimiser's state belongs to warp 0 and is needed for ~1 us per generation.  It rests in shared memory
+    // and is brought into registers only for that turn, so that it does not weigh on the poll-and-fold loop that all
+    // eight warps run in between (at the 80-register budget of the 3-CTAs/SM kernels it used to be spilled there:
+    // ~400 bytes of local-memory traffic on the serial path of every generation).
+    __shared__ WarpDualMachine<MAXM> s_mach[32];
+    __shared__ int s_final_pass;
     const unsigned long long t_start = nb_globaltimer();
-    if (threadIdx.x == 0) s_exit = 0;
+    if (threadIdx.x == 0) { s_exit = 0; s_final_pass = 0; }
     if (sub == 0) {
+        WarpDualMachine<MAXM> mach;
         const double y0 = lane < a.m ? a.y[lane] : 0.0, lo = lane < a.m ? sa.lo[lane] : 0.0, hi = lane < a.m ? sa.hi[lane] : 0.0;
         const int rc = mach.start(a.m, y0, lo, hi, sa.stop, lane);       // d.y carries the warm start
         if (rc != kRetSuccess) {          // start point outside the box: report, publish nothing
@@ -1230,7 +1524,10 @@ __device__ __noinline__ void solve_folder(const SolveArgs &sa, double *s_vs, dou
             }
         } else {
             double u = a.rho;
-            for (int i = 0; i < a.m; ++i) u = addx(u, mulx(a.rhoc[i], __shfl_sync(0xffffffffu, mach.y, i)));
+            NB_MACH_FOR(i, MAXM, a.m) {
+                const double yi = __shfl_sync(0xffffffffu, mach.y, i);
+                NB_MACH_IF(i, a.m) u = addx(u, mulx(a.rhoc[i], yi));
+            }
             NB_TR(if (lane == 0) sa.trace[16] = nb_globaltimer();)
             if (lane < a.m) slot_put(st->pub + 2 * lane, mach.y, sa.tag0 | 1ull);
             if (lane == 0) {
@@ -1238,6 +1535,7 @@ __device__ __noinline__ void solve_folder(const SolveArgs &sa, double *s_vs, dou
                 slot_put(st->pub + 2 * (kMaxParamM + 1), __longlong_as_double(0ll), sa.tag0 | 1ull);
             }
         }
+        s_mach[lane] = mach;
     }
     fold_init<NV>(s_w);
     if (s_exit) return;
@@ -1247,6 +1545,8 @@ __device__ __noinline__ void solve_folder(const SolveArgs &sa, double *s_vs, dou
         // ---- warp 0: totals (exchange if sharded), the dual optimiser's turn, publication ----
         if (sub == 0) {
             NB_TR(if (lane == 0 && gen < kTraceGens) sa.trace[16 * gen + 5] = nb_globaltimer();)
+            WarpDualMachine<MAXM> mach = s_mach[lane];
+            const int final_pass = s_final_pass;
             double total = 0.0;               // lane k < NV holds sum k
             int timed_out = 0;
             // the time limit: a rank-local clock test, made collective by the exchange (see box_exchange)
@@ -1269,8 +1569,10 @@ __device__ __noinline__ void solve_folder(const SolveArgs &sa, double *s_vs, dou
                 const double gsum = __shfl_sync(0xffffffffu, total, (lane + 3) & 31);      // lane i < m: sum 3 + i
                 const double grad = lane < a.m ? -addx(cv, gsum) : 0.0;                     // -g_i(y)
                 double val = sa.fval;
-                for (int i = 0; i < a.m; ++i)
-                    val = addx(val, mulx(__shfl_sync(0xffffffffu, yt, i), __shfl_sync(0xffffffffu, cv, i)));
+                NB_MACH_FOR(i, MAXM, a.m) {
+                    const double yi = __shfl_sync(0xffffffffu, yt, i), ci = __shfl_sync(0xffffffffu, cv, i);
+                    NB_MACH_IF(i, a.m) val = addx(val, mulx(yi, ci));
+                }
                 val = addx(val, __shfl_sync(0xffffffffu, total, 0));
                 finished = timed_out ? 1 : (mach.feed_pre(-val, grad, time_up != 0, lane) ? 1 : 0);
                 if (timed_out) mach.ret = kRetFailure;
@@ -1300,14 +1602,18 @@ __device__ __noinline__ void solve_folder(const SolveArgs &sa, double *s_vs, dou
                 const double trial = next_final ? mach.y : mach.ycur;
                 const unsigned long long ntag = sa.tag0 | (gen + 1);
                 double u = a.rho;
-                for (int i = 0; i < a.m; ++i) u = addx(u, mulx(a.rhoc[i], __shfl_sync(0xffffffffu, trial, i)));
+                NB_MACH_FOR(i, MAXM, a.m) {
+                    const double ti = __shfl_sync(0xffffffffu, trial, i);
+                    NB_MACH_IF(i, a.m) u = addx(u, mulx(a.rhoc[i], ti));
+                }
                 NB_TR(if (lane == 0 && gen + 1 < kTraceGens) sa.trace[16 * (gen + 1)] = nb_globaltimer();)
                 if (lane < a.m) slot_put(st->pub + 2 * lane, trial, ntag);
                 if (lane == 0) {
                     slot_put(st->pub + 2 * kMaxParamM, u, ntag);
                     slot_put(st->pub + 2 * (kMaxParamM + 1), __longlong_as_double((long long) next_final), ntag);
                 }
-                final_pass = next_final;
+                if (lane == 0) s_final_pass = next_final;
+                s_mach[lane] = mach;
             }
         }
         fold_barrier();
@@ -1354,6 +1660,14 @@ __global__ void __launch_bounds__(BLOCK, MINB) dual_solve_kernel(const __grid_co
         const unsigned long long c = s_claim[it & 1];
         const unsigned long long want = c / ngroups + 1;
         const unsigned gl = (unsigned) (c % ngroups);
+#if NB200_PRELOAD
+        // the first chunk's operands are requested before anything else: they do not depend on the multipliers
+        unsigned long long p_lo, p_hi;
+        group_pairs(a.nchunks, a.nseg_total, a.chunk0, a.seg0 + gl, &p_lo, &p_hi);
+        const unsigned long long p_first = p_lo + sub * 32 + lane;
+        ChunkOperands<MAXM> first;
+        load_chunk<MAXM, FULL, POL>(a, a.m, pol, p_first, p_first < p_hi, first);
+#endif
         // wait until generation `want` is published (or the solve has finished); refresh the multipliers
         if (want != my_gen) {
             // ... with the head of the group on its way from HBM to the L2 meanwhile
@@ -1394,7 +1708,12 @@ __global__ void __launch_bounds__(BLOCK, MINB) dual_solve_kernel(const __grid_co
 #pragma unroll
         for (int k = 0; k < NV; ++k) acc[k] = 0.0;
         NB_TR(const unsigned long long tr_s0 = nb_globaltimer();)
+#if NB200_PRELOAD
+        // (the 128-register instantiations, MINB <= 2, have room for the MMA pair form with 4 rows)
+        sweep_group_preloaded<VARIANT, MAXM, FULL, POL, kPairMMA<MAXM> || (MINB <= 2 && MAXM <= 4)>(a, mu, pol, s_store != 0, p_first, p_hi, first, acc);
+#else
         sweep_group<VARIANT, MAXM, FULL, UNROLL, POL>(a, mu, pol, s_store != 0, gl, sub, lane, acc);
+#endif
 
         warp_fold<NV>(acc);
         double *srec = s_rec[parity];
@@ -1403,6 +1722,196 @@ __global__ void __launch_bounds__(BLOCK, MINB) dual_solve_kernel(const __grid_co
             for (int k = 0; k < NV; ++k) srec[sub * NV + k] = acc[k];
         }
         if (threadIdx.x == 0) s_claim[(it + 1) & 1] = next_c;
+        __syncthreads();
+        parity ^= 1;
+        if (sub == 0) put_group_record<NV>(srec, a.grouptags, ngroups, gl, sa.tag0 | my_gen, lane);
+        NB_TR(if (sub == 0 && lane == 0 && my_gen < kTraceGens) { const unsigned long long t = nb_globaltimer(); unsigned long long *r = sa.trace + 16 * my_gen;
+                  atomicMax(r + 3, ~t); atomicMax(r + 4, t); atomicAdd(r + 8, t - tr_s0); atomicAdd(r + 9, 1ull); })
+    }
+}
+
+// ---- the persistent dual-solve kernel with a per-thread asynchronous operand pipeline ---------------------------------
+// The register form above walks a group one chunk at a time: request (5+m) x 16 bytes per thread, wait for them, compute,
+// next chunk.  All resident warps of an SM do this in step, so the load latency and the arithmetic of a chunk add up
+// instead of overlapping (at the 8-GPU shard of n = 1e7 a generation is ~5 such steps per CTA: latency-bound, not
+// HBM-bound -- profiles/r02_summary.md).  Here every thread copies ITS OWN 16 bytes of each operand array of the chunks
+// ahead with cp.async (LDGSTS: global -> shared without passing through registers) into its private column of a ring
+// of STAGES shared-memory stages, and reads the stage back (LDS.128) when it gets there.  A thread only ever reads what
+// it copied itself, so the ring needs no barrier, no mbarrier and no producer warp (the TMA-staged form below has all
+// three and measured slower than the register form); the only synchronisation is cp.async.wait_group on the thread's
+// own copies.  The prefetch cursor runs ahead of the arithmetic across chunk, GROUP and GENERATION boundaries: the
+// operands do not depend on the multipliers, so while the folder CTA folds, exchanges, steps the dual optimiser and
+// publishes y_{g+1}, the first STAGES chunks of every sweeper's next group are already on their way.
+// Same lanes, same per-warp accumulators, same fold tree as every other kernel here: the same bits.
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int VARIANT, int MAXM, bool FULL, int STAGES, int MINB>
+__global__ void __launch_bounds__(kBlock, MINB) dual_solve_async_kernel(const __grid_constant__ SolveArgs sa)
+{
+    constexpr int MR = MAXM > 0 ? MAXM : 1;
+    constexpr int NV = 3 + MR;
+    constexpr int NARR = 5 + MAXM;
+    static_assert(MAXM >= 1 && STAGES >= 2 && STAGES <= 4, "ring of 2..4 stages");
+    extern __shared__ __align__(16) unsigned char s_ring[];    // [STAGES][NARR][kBlock] double2: thread t owns column t
+    if (blockIdx.x == gridDim.x - 1) {                          // the folder CTA: its ring holds the fold scratch
+        double *scratch = reinterpret_cast<double *>(s_ring);
+        static_assert((size_t) STAGES * NARR * kChunkBytes >= (size_t) (kVirtualShards * NV + kVirtualShards * kGroupWarps * NV) * sizeof(double), "fold scratch fits the ring");
+        solve_folder<NV>(sa, scratch, scratch + kVirtualShards * NV);
+        return;
+    }
+    const DualArgs &a = sa.d;
+    SolveState *st = sa.st;
+    const int lane = threadIdx.x & 31;
+    const int sub = threadIdx.x >> 5;
+    const unsigned ngroups = a.segs_per_vshard * a.local_vshards;
+    __shared__ double s_rec[2][kGroupWarps * NV];
+    __shared__ double s_y[kMaxParamM];
+    __shared__ double s_u;
+    __shared__ int s_store, s_exit;
+    __shared__ volatile unsigned long long s_clm[4];            // claim of the CTA's group number `it` at [it & 3] ...
+    __shared__ volatile int s_clm_it[4];                        // ... valid iff this says `it`
+    double2 *const col = reinterpret_cast<double2 *>(s_ring) + threadIdx.x;      // element (stage s, array k): col[(s * NARR + k) * kBlock]
+
+    const double *src[NARR];
+    src[0] = a.x; src[1] = a.lb; src[2] = a.ub; src[3] = a.sigma; src[4] = a.g;
+#pragma unroll
+    for (int i = 0; i < MAXM; ++i) src[5 + i] = a.G + (unsigned long long) i * a.ld;
+
+    unsigned long long next_c = 0;
+    if (threadIdx.x < 4) s_clm_it[threadIdx.x] = -1;
+    __syncthreads();
+    if (threadIdx.x == 0) { s_exit = 0; s_store = 0; s_clm[0] = atomicAdd(&st->claim, 1ull); s_clm_it[0] = 0; }
+    NB_TR(if (threadIdx.x == 0) { const unsigned long long t = nb_globaltimer(); atomicMax(&sa.trace[1], ~t); atomicMax(&sa.trace[2], t); })
+    __syncthreads();
+
+    // the prefetch cursor: the next chunk to request is pair pf_p (this lane's) of the CTA's group number pf_it
+    unsigned issued = 0, consumed = 0;
+    int pf_it = -1;
+    unsigned long long pf_p = 0, pf_hi = 0;
+    auto pump = [&]() {
+        while (issued - consumed < (unsigned) STAGES) {
+            if (pf_p >= pf_hi) {                                // this group is fully requested: move on to the next claim, if known
+                const int nit = pf_it + 1;
+                if (s_clm_it[nit & 3] != nit) break;
+                const unsigned long long c = s_clm[nit & 3];
+                unsigned long long lo, hi;
+                group_pairs(a.nchunks, a.nseg_total, a.chunk0, a.seg0 + (unsigned) (c % ngroups), &lo, &hi);
+                pf_it = nit;
+                pf_p = lo + sub * 32 + lane;
+                pf_hi = hi;
+                continue;
+            }
+            double2 *dst = col + (size_t) (issued % STAGES) * NARR * kBlock;
+#pragma unroll
+            for (int k = 0; k < NARR; ++k)
+                if (k < 5 || FULL || k - 5 < a.m) cp_async16(dst + (size_t) k * kBlock, reinterpret_cast<const double2 *>(src[k]) + pf_p);
+            cp_async_commit();
+            ++issued;
+            pf_p += kChunkPairs;
+        }
+    };
+
+    int parity = 0;
+    unsigned long long my_gen = 0;        // generation whose multipliers are in s_y
+    for (int it = 0;; ++it) {
+        const unsigned long long c = s_clm[it & 3];
+        const unsigned long long want = c / ngroups + 1;
+        const unsigned gl = (unsigned) (c % ngroups);
+        unsigned long long p_lo, p_hi;
+        group_pairs(a.nchunks, a.nseg_total, a.chunk0, a.seg0 + gl, &p_lo, &p_hi);
+        pump();                               // the head of this group is requested before we look for the multipliers
+        if (want != my_gen) {
+            if (sub == 0) {                   // warp 0 polls, warp-uniformly: lane i < m: y_i, lane m: u, the others: flags
+                const int slot = lane < a.m ? lane : (lane == a.m ? kMaxParamM : kMaxParamM + 1);
+                const unsigned long long tag = sa.tag0 | want;
+                double v;
+                int ex = 0;
+                unsigned spins = 0;
+                for (;;) {
+                    if (__all_sync(0xffffffffu, slot_get(st->pub + 2 * slot, tag, &v))) break;
+                    if ((++spins & 7u) == 0u && __any_sync(0xffffffffu, ld_gpu_s32(&st->done))) {
+                        ex = !__all_sync(0xffffffffu, slot_get(st->pub + 2 * slot, tag, &v));     // published before done was raised?
+                        break;
+                    }
+                    __nanosleep(20);
+                }
+                if (ex) s_exit = 1;
+                else if (lane < a.m) s_y[lane] = v;
+                else if (lane == a.m) s_u = v;
+                else if (lane == a.m + 1) s_store = (int) (__double_as_longlong(v) & 1ll);
+            }
+            __syncthreads();
+            if (s_exit) {
+                cp_async_wait<0>();           // a CTA must not retire with copies into its shared memory in flight
+                return;
+            }
+            NB_TR(if (threadIdx.x == 0 && want < kTraceGens) { const unsigned long long t = nb_globaltimer();
+                      atomicMax(&sa.trace[16 * want + 1], ~t); atomicMax(&sa.trace[16 * want + 2], t); })
+            my_gen = want;
+        }
+        // claim the next group now; thread 0 publishes it to the CTA after its first chunk (the atomic's latency hides
+        // behind that chunk's arithmetic), so that the cursors can cross into the next group while this one is computed
+        if (threadIdx.x == 0) next_c = atomicAdd(&st->claim, 1ull);
+        bool claim_pending = threadIdx.x == 0;
+
+        SharedMultipliers mu;
+        mu.y = s_y; mu.rhoc = a.rhoc; mu.half_rhoc = a.half_rhoc; mu.u_ccsaq = s_u;
+        mu.rho = a.rho; mu.half_rho = a.half_rho;
+        mu.active = a.active; mu.m = a.m;
+        DivBy U;
+        U.b = 1.0; U.r = 1.0; U.hb = 0x3ff00000; U.zero_ok = 1u;
+#if NB200_PAIR
+        if (VARIANT != 0) U = prep_div(mu.u());
+#endif
+        const bool store = s_store != 0;
+        double acc[NV];
+#pragma unroll
+        for (int k = 0; k < NV; ++k) acc[k] = 0.0;
+        NB_TR(const unsigned long long tr_s0 = nb_globaltimer();)
+        for (unsigned long long p = p_lo + sub * 32 + lane; p < p_hi; p += kChunkPairs) {
+            // this chunk is the oldest outstanding copy group of the thread: wait until at most the newer ones are pending
+            const unsigned newer = issued - consumed - 1u;
+            if (newer == 0u) cp_async_wait<0>();
+            else if (newer == 1u) cp_async_wait<1>();
+            else if (newer == 2u) cp_async_wait<2>();
+            else cp_async_wait<3>();
+            const double2 *t = col + (size_t) (consumed % STAGES) * NARR * kBlock;
+            ChunkOperands<MAXM> r;
+            r.x = t[0]; r.lb = t[kBlock]; r.ub = t[2 * kBlock]; r.s = t[3 * kBlock]; r.g = t[4 * kBlock];
+#pragma unroll
+            for (int i = 0; i < MR; ++i) {
+                r.Ga[i] = 0.0; r.Gb[i] = 0.0;
+                if (FULL || i < a.m) { const double2 g2 = t[(5 + i) * kBlock]; r.Ga[i] = g2.x; r.Gb[i] = g2.y; }
+            }
+            const double2 xc = compute_chunk<VARIANT, MAXM, FULL, (MINB <= 2 && MAXM <= 4) || kPairMMA<MAXM>>(mu, U, r, acc);
+            if (store) st_stream(reinterpret_cast<double2 *>(a.xcur) + p, xc);
+            ++consumed;
+            if (claim_pending) {
+                s_clm[(it + 1) & 3] = next_c;
+                __threadfence_block();
+                s_clm_it[(it + 1) & 3] = it + 1;
+                claim_pending = false;
+            }
+            pump();
+        }
+
+        warp_fold<NV>(acc);
+        double *srec = s_rec[parity];
+        if (lane == 0) {
+#pragma unroll
+            for (int k = 0; k < NV; ++k) srec[sub * NV + k] = acc[k];
+        }
+        if (claim_pending) {                  // an empty group
+            s_clm[(it + 1) & 3] = next_c;
+            __threadfence_block();
+            s_clm_it[(it + 1) & 3] = it + 1;
+        }
         __syncthreads();
         parity ^= 1;
         if (sub == 0) put_group_record<NV>(srec, a.grouptags, ngroups, gl, sa.tag0 | my_gen, lane);

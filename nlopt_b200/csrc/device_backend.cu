@@ -1064,13 +1064,24 @@ typedef void (*SolveKernel)(const SolveArgs);
 // One configuration per row count.  Two alternatives were measured on the box and removed (profiles/r01_summary.md):
 // two chunks in flight per sweep step (slower at n = 1e7 over 8 GPUs, 39.3 vs 32.3 us per evaluation) and
 // 4 CTAs/SM at 64 registers (spills: 149 vs 129 us per CCSAQ evaluation at n = 1e7, m = 4).
+#ifndef NB200_SOLVE_MINB4
+#define NB200_SOLVE_MINB4 3      // A/B switch (tools/ab_build.py): resident CTAs per SM of the solve kernel with <= 4 rows
+#endif
+// `roomy`: the 2-CTAs/SM instantiation (128 registers, no spills in the sweep or in the folder's optimiser turn) -- used
+// when the grid does not need a third CTA per SM anyway (small and mid-size shards), see DeviceBackend::dual_solve
 template <int VARIANT, bool FULL, bool POL>
-SolveKernel pick_solve_kernel(int maxm)
+SolveKernel pick_solve_kernel(int maxm, bool roomy)
 {
+    if (roomy) switch (maxm) {
+        case 1: return dual_solve_kernel<VARIANT, 1, FULL, POL, 256, 1, 2>;
+        case 2: return dual_solve_kernel<VARIANT, 2, FULL, POL, 256, 1, 2>;
+        case 4: return dual_solve_kernel<VARIANT, 4, FULL, POL, 256, 1, 2>;
+        default: break;
+        }
     switch (maxm) {
-    case 1: return dual_solve_kernel<VARIANT, 1, FULL, POL, 256, 1, 3>;
-    case 2: return dual_solve_kernel<VARIANT, 2, FULL, POL, 256, 1, 3>;
-    case 4: return dual_solve_kernel<VARIANT, 4, FULL, POL, 256, 1, 3>;
+    case 1: return dual_solve_kernel<VARIANT, 1, FULL, POL, 256, 1, NB200_SOLVE_MINB4>;
+    case 2: return dual_solve_kernel<VARIANT, 2, FULL, POL, 256, 1, NB200_SOLVE_MINB4>;
+    case 4: return dual_solve_kernel<VARIANT, 4, FULL, POL, 256, 1, NB200_SOLVE_MINB4>;
     case 8: return dual_solve_kernel<VARIANT, 8, FULL, POL, 256, 1, 2>;
     default: return dual_solve_kernel<VARIANT, 16, FULL, POL, 256, 1, 2>;
     }
@@ -1087,11 +1098,31 @@ SolveKernel pick_solve_tma_kernel(int maxm, size_t *smem)
     }
 }
 
-template <int VARIANT>
-SolveKernel pick_solve_kernel2(int maxm, bool full, bool pol)
+// asynchronous operand pipeline (dual_solve_async_kernel): {stages} x (5 + rows) x 4 KB of dynamic shared memory per CTA.
+// <= 2 rows: 3 CTAs/SM at 80 registers; 4 or 8 rows: the ring leaves room for 2 CTAs/SM, which get 128 registers.
+template <int VARIANT, bool FULL, int STAGES>
+SolveKernel pick_solve_async_kernel(int maxm)
 {
-    return full ? (pol ? pick_solve_kernel<VARIANT, true, true>(maxm) : pick_solve_kernel<VARIANT, true, false>(maxm))
-                : (pol ? pick_solve_kernel<VARIANT, false, true>(maxm) : pick_solve_kernel<VARIANT, false, false>(maxm));
+    switch (maxm) {
+    case 1: return dual_solve_async_kernel<VARIANT, 1, FULL, STAGES, 3>;
+    case 2: return dual_solve_async_kernel<VARIANT, 2, FULL, STAGES, 3>;
+    case 4: return dual_solve_async_kernel<VARIANT, 4, FULL, STAGES, 2>;
+    case 8: return dual_solve_async_kernel<VARIANT, 8, FULL, STAGES, 2>;
+    default: return nullptr;
+    }
+}
+template <int VARIANT>
+SolveKernel pick_solve_async_kernel2(int maxm, bool full, int stages)
+{
+    if (stages == 2) return full ? pick_solve_async_kernel<VARIANT, true, 2>(maxm) : pick_solve_async_kernel<VARIANT, false, 2>(maxm);
+    return full ? pick_solve_async_kernel<VARIANT, true, 3>(maxm) : pick_solve_async_kernel<VARIANT, false, 3>(maxm);
+}
+
+template <int VARIANT>
+SolveKernel pick_solve_kernel2(int maxm, bool full, bool pol, bool roomy)
+{
+    return full ? (pol ? pick_solve_kernel<VARIANT, true, true>(maxm, roomy) : pick_solve_kernel<VARIANT, true, false>(maxm, roomy))
+                : (pol ? pick_solve_kernel<VARIANT, false, true>(maxm, roomy) : pick_solve_kernel<VARIANT, false, false>(maxm, roomy));
 }
 }  // namespace
 
@@ -1154,8 +1185,16 @@ bool DeviceBackend::dual_solve(double *y, const double *lo, const double *hi, co
         fn = variant_ == kMMA ? pick_solve_tma_kernel<0>(maxm, &smem) : pick_solve_tma_kernel<1>(maxm, &smem);
         block = kTmaBlock;
         NB_CUDA(cudaFuncSetAttribute((const void *) fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-    } else
-        fn = variant_ == kMMA ? pick_solve_kernel2<0>(maxm, full, use_pol) : pick_solve_kernel2<1>(maxm, full, use_pol);
+    } else if (solve_async_ >= 2 && !use_pol && maxm <= 8) {
+        const int stages = solve_async_ >= 3 ? 3 : 2;
+        fn = variant_ == kMMA ? pick_solve_async_kernel2<0>(maxm, full, stages) : pick_solve_async_kernel2<1>(maxm, full, stages);
+        smem = (size_t) stages * (5 + (size_t) maxm) * kChunkBytes;
+        NB_CUDA(cudaFuncSetAttribute((const void *) fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+    } else {
+        // 2 CTAs/SM with 128 registers when that many CTAs already cover the rank's groups (knob b200_solve_minb: 2 / 3 force)
+        const bool roomy = solve_minb_ == 2 || (solve_minb_ != 3 && (long long) geo_.nseg_local + 1 <= 2ll * sm_count_);
+        fn = variant_ == kMMA ? pick_solve_kernel2<0>(maxm, full, use_pol, roomy) : pick_solve_kernel2<1>(maxm, full, use_pol, roomy);
+    }
     int per_sm = 0;
     NB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, block, smem));
     if (per_sm < 1) return fail("dual_solve_kernel does not fit on an SM");
@@ -1413,6 +1452,8 @@ bool DeviceBackend::configure(const char *key, long long value)
     if (k == "ctas_per_sm") { ctas_per_sm_ = (int) value; return true; }
     if (k == "fused_solve") { fused_solve_ok_ = value != 0; return true; }
     if (k == "solve_tma") { solve_tma_ = (int) value; return true; }
+    if (k == "solve_async") { solve_async_ = (int) value; return true; }
+    if (k == "solve_minb") { solve_minb_ = (int) value; return true; }
     if (k == "l1_prefetch") { l1_prefetch_ = value != 0; return true; }
     if (k == "prefetch_chunks") { prefetch_chunks_ = value < 0 ? 0u : (unsigned) value; prefetch_forced_ = true; return true; }
     if (k == "l2_keep_mb") {

@@ -87,3 +87,15 @@ class DualHandle:
         self.check(self.lib.nlopt_b200_dual_end_outer(self.h, int(k), float(sigma_min), _p(w), _p(t), _p(norms),
                                                       C.byref(below)))
         return norms[0], norms[1], bool(below.value)
+
+    def solve(self, y0, lo=None, hi=None, ftol_rel=0.0, maxeval=6):
+        """one whole dual solve inside the persistent kernel (nlopt_b200_dual_solve); x*(y) of the final pass is left in xcur"""
+        m = max(self.m, 1)
+        y = np.ascontiguousarray(y0, dtype=np.float64).copy()
+        lo = np.zeros(m) if lo is None else np.ascontiguousarray(lo, dtype=np.float64)
+        hi = np.full(m, 1e40) if hi is None else np.ascontiguousarray(hi, dtype=np.float64)
+        out = np.zeros(3 + m)
+        res, nev, kms = C.c_int(0), C.c_long(0), C.c_double(0.0)
+        self.check(self.lib.nlopt_b200_dual_solve(self.h, _p(y), _p(lo), _p(hi), float(ftol_rel), int(maxeval), _p(out),
+                                                  C.byref(res), C.byref(nev), C.byref(kms)))
+        return dict(y=y, out=out, result=res.value, nevals=nev.value, xcur=self.download("xcur"))

@@ -156,6 +156,97 @@ def test_dual_kernel_special_lanes(built):
         check_dual(v, inst)
 
 
+def _bits_equal_where_finite(a, b):
+    """bit patterns equal (the sign of a zero included); a NaN must meet a NaN"""
+    a = np.ascontiguousarray(a); b = np.ascontiguousarray(b)
+    nan = np.isnan(a) | np.isnan(b)
+    return np.array_equal(np.isnan(a), np.isnan(b)) and np.array_equal(a.view(np.uint64)[~nan], b.view(np.uint64)[~nan])
+
+
+@pytest.mark.parametrize("variant", [ob.MMA, ob.CCSAQ])
+@pytest.mark.parametrize("m", [1, 3, 4])
+def test_pair_forms_on_degenerate_operands(built, variant, m):
+    """The straight-line closed forms (pair_math.cuh) write out the fast paths of the IEEE division / square root /
+    reciprocal and fall back to the builtins outside their range.  Operands that sit on the edges of that range --
+    zero gradient entries (zero numerators, both signs), variables parked on a bound (dx = 0), fixed variables next
+    to free ones inside one 128-bit pair, -0.0 coordinates -- must give the oracle's bits, sums included."""
+    n = 40001
+    inst = synth.kernel_instance(n, m)
+    j = np.arange(n)
+    inst["grad_f"][j % 5 == 0] = 0.0
+    inst["grad_c"][:, j % 5 == 0] = 0.0                      # u = v-part = 0: 0 / v, sqrt(1), 0 / (-2)
+    inst["grad_f"][j % 35 == 0] = -0.0
+    inst["grad_c"][0, j % 7 == 1] = 0.0                      # some zero rows only
+    parked = (j % 11 == 3) & np.isfinite(inst["ub"])          # on the upper bound, pushed outwards: x* = x, dx = 0
+    inst["x"][parked] = inst["ub"][parked]
+    inst["grad_f"][parked] = -np.abs(inst["grad_f"][parked]) - 50.0
+    low = (j % 13 == 5) & np.isfinite(inst["lb"])             # on the lower bound, pushed outwards
+    inst["x"][low] = inst["lb"][low]
+    inst["grad_f"][low] = np.abs(inst["grad_f"][low]) + 50.0
+    fixed = j % 17 == 2                                       # odd and even lanes: both halves of a pair get fixed neighbours
+    inst["sigma"][fixed] = 0.0
+    inst["lb"][fixed] = inst["x"][fixed]; inst["ub"][fixed] = inst["x"][fixed]
+    negz = j % 19 == 4
+    inst["x"][negz] = -0.0
+    inst["lb"][negz] = -1.0; inst["ub"][negz] = 1.0
+    got = check_dual(variant, inst)
+    want = ob.port_dual(variant, inst)
+    assert _bits_equal_where_finite(got["xcur"], want["xcur"])
+    # multipliers that are exactly zero: every constraint term is a zero numerator
+    got0 = check_dual(variant, inst, y=np.zeros(m))
+    assert _bits_equal_where_finite(got0["xcur"], ob.port_dual(variant, inst, np.zeros(m))["xcur"])
+    # the persistent solve kernel's forms on the same operands; x*(y) of the final pass against the oracle at the final y
+    a = _solve_forms_agree(variant, inst, inst["y"])
+    assert _bits_equal_where_finite(a["xcur"], ob.port_dual(variant, inst, a["y"])["xcur"])
+
+
+def _solve_forms_agree(variant, inst, y0):
+    """the solve kernel's forms (3 CTAs/SM: MMA with 4 rows in the sequential form; 2 CTAs/SM: pair form everywhere; the
+    cp.async ring) end a short dual solve on the same multipliers, sums and x*(y), bit for bit, NaNs in the same places"""
+    runs = []
+    for key, val in (("solve_minb", 3), ("solve_minb", 2), ("solve_async", 3)):
+        h = DualHandle(variant, inst)
+        h.configure(key, val)
+        with np.errstate(all="ignore"):
+            runs.append(h.solve(y0, maxeval=5))
+    a = runs[0]
+    for b in runs[1:]:
+        assert a["result"] == b["result"] and a["nevals"] == b["nevals"]
+        assert _bits_equal_where_finite(a["y"], b["y"]) and _bits_equal_where_finite(a["out"], b["out"])
+        assert _bits_equal_where_finite(a["xcur"], b["xcur"])
+    return a
+
+
+@pytest.mark.parametrize("variant", [ob.MMA, ob.CCSAQ])
+@pytest.mark.parametrize("m", [2, 4])
+def test_pair_forms_on_extreme_operands(built, variant, m):
+    """Magnitudes far outside the fast paths' range (1e-300 ... 1e300, denormals, infinities in the gradient): the
+    builtins take over lane by lane; x*(y) keeps the oracle's bits (the sums overflow here and are not compared)."""
+    n = 30011
+    inst = synth.kernel_instance(n, m, special_lanes=False)
+    j = np.arange(n)
+    scales = np.array([1e-300, 1e-200, 1e-120, 1e-37, 1e-20, 1.0, 1e20, 1e100, 1e200, 1e300, 5e-324, 1e-310])
+    inst["grad_f"] *= scales[j % len(scales)]
+    for i in range(m):
+        inst["grad_c"][i] *= scales[(j // 3 + i) % len(scales)]
+    sig = np.array([1e-150, 1e-20, 1.0, 1e10, 1e150, 1e-300, 1.0, 1.0])
+    inst["sigma"] *= sig[(j // 5) % len(sig)]
+    inst["lb"][:] = -np.inf; inst["ub"][:] = np.inf
+    inst["lb"][j % 4 == 0] = inst["x"][j % 4 == 0] - 1e-3
+    inst["ub"][j % 6 == 1] = inst["x"][j % 6 == 1] + 1e-9
+    inst["grad_f"][j % 101 == 7] = np.inf
+    inst["grad_f"][j % 103 == 9] = np.nan
+    for y in (inst["y"], inst["y"] * 1e-200, inst["y"] * 1e150):
+        h = DualHandle(variant, inst)
+        with np.errstate(all="ignore"):
+            got = h.eval(y, want_xcur=True)
+            want = ob.port_dual(variant, inst, y)
+        assert _bits_equal_where_finite(got["xcur"], want["xcur"])
+    with np.errstate(all="ignore"):
+        a = _solve_forms_agree(variant, inst, inst["y"])
+        assert _bits_equal_where_finite(a["xcur"], ob.port_dual(variant, inst, a["y"])["xcur"])
+
+
 @pytest.mark.parametrize("variant", [ob.MMA, ob.CCSAQ])
 def test_segment_geometry_does_not_change_x_and_barely_changes_sums(built, variant):
     inst = synth.kernel_instance(300000, 4)
@@ -469,6 +560,24 @@ def test_tma_staged_solve_equals_register_solve(built, variant, n, m):
     a, b = pair
     assert a["ret"] == b["ret"] and a["numevals"] == b["numevals"] and a["minf"] == b["minf"] and np.array_equal(a["x"], b["x"])
     assert a["opt"].get_stats()["dual_evals"] == b["opt"].get_stats()["dual_evals"]
+
+
+@pytest.mark.parametrize("variant", [ob.MMA, ob.CCSAQ])
+@pytest.mark.parametrize("n,m", [(3, 1), (700, 2), (5000, 4), (100001, 1), (300000, 4), (1500000, 2), (200000, 3), (150000, 8), (90000, 6)])
+def test_solve_kernel_variants_equal_the_default(built, variant, n, m):
+    """Every form of the persistent solve kernel gives the same run, bit for bit: the per-thread cp.async operand ring
+    (dual_solve_async_kernel, 2 and 3 stages: cursors running ahead across chunk, group and generation boundaries;
+    m not a power of two exercises the row predicates) and the 2- / 3-CTAs-per-SM instantiations of the register form."""
+    alg = nl.LD_MMA if variant == ob.MMA else nl.LD_CCSAQ
+    cons = [P.lin_constraint(k, n) for k in range(m)]
+    lb, ub = np.full(n, -2.0), np.full(n, 2.0)
+    x0 = P.rosen_x0(n) if n > 1 else np.array([-1.2])
+    runs = [_run(alg, n, P.rosen_f, cons, [1e-8] * m, lb, ub, x0, maxeval=8, **kw)
+            for kw in (dict(), dict(b200_solve_async=2), dict(b200_solve_async=3), dict(b200_solve_minb=2), dict(b200_solve_minb=3))]
+    a = runs[0]
+    for b in runs[1:]:
+        assert a["ret"] == b["ret"] and a["numevals"] == b["numevals"] and a["minf"] == b["minf"] and np.array_equal(a["x"], b["x"])
+        assert a["opt"].get_stats()["dual_evals"] == b["opt"].get_stats()["dual_evals"]
 
 
 def test_sharded_host_callbacks_equal_plain_host_callbacks(built):

@@ -58,6 +58,10 @@ def main():
                 h = L.nlopt_b200_dual_create(variant, n, m)
                 if not h:
                     continue
+                for kv in filter(None, os.environ.get("SWEEP_CFG", "").split(",")):      # e.g. SWEEP_CFG=solve_async=3,group_base=288
+                    k, v = kv.split("=")
+                    if L.nlopt_b200_dual_configure(h, k.encode(), int(v)) != 0:
+                        print("configure failed", kv, L.nlopt_b200_dual_errmsg(h).decode(), flush=True)
                 L.nlopt_b200_dual_fill_synthetic(h, 0x5EED0000)
                 i = np.arange(m, dtype=np.float64)
                 c0, rhoc = -0.1 * (i + 1.0), 1.0 + 0.1 * i
