@@ -177,38 +177,64 @@ __device__ __forceinline__ bool slot_get(const double *slot, unsigned long long 
 // that every rank takes the SAME decision -- a rank-local clock test would let one rank stop while its peers wait
 // for its next record.  Returns the total in lanes < nv; *timed_out (a peer died) is warp-uniform.
 // vsums: the shard sums written by this CTA (shared memory): plain loads.
+// Polling: the 8 x (nv + 1) awaited slots are dealt out over the 32 lanes (slot s = 8 k + v to lane s % 32, register
+// s / 32), so a poll round costs a lane ceil(8 (nv + 1) / 32) strong loads -- 2 for m = 4 -- instead of the 8 it cost when
+// lane k fetched all 8 records of its own sum: strong (system-scope) loads of one thread complete one after the other,
+// ~0.3 us each (profiles/r01_summary.md), and this round trip is on the serial path of every generation on several GPUs.
+// The records then travel to the lane that owns their sum by shuffles and are added in the same index order as before.
+constexpr int kBoxPollRegs = (8 * (kMaxNV + 1) + 31) / 32;      // 5
 __device__ __forceinline__ double box_exchange(double *const *box, int rank, int world, unsigned long long seq,
                                                const double *vsums, int nvp, unsigned local_vshards, unsigned v0,
                                                int nv, int lane, double flag, int *any_flag, int *timed_out)
 {
     const int buf = (int) (seq & 1ull);
-    double total = 0.0;
-    int to = 0;
-    const bool mine_lane = lane < nv || lane == kBoxFlagSlot;
-    if (mine_lane) {
+    if (lane < nv || lane == kBoxFlagSlot) {
         for (unsigned v = 0; v < local_vshards; ++v) {
             const double val = lane < nv ? vsums[(unsigned long long) v * nvp + lane] : flag;
             for (int r = 0; r < world; ++r)
                 box_put(box[r] + 2ull * (((unsigned long long) buf * 8 + v0 + v) * kBoxStride + lane), val, seq);
         }
-        const double *mine = box[rank] + 2ull * ((unsigned long long) buf * 8 * kBoxStride + lane);
-        const unsigned long long t0 = nb_globaltimer();
-        double x[kVirtualShards];
-        for (;;) {                         // all 8 slots are fetched together: one L2 round trip per poll
-            bool ok[kVirtualShards];
-#pragma unroll
-            for (int v = 0; v < kVirtualShards; ++v) ok[v] = box_get(mine + 2ull * v * kBoxStride, seq, &x[v]);
-            bool all = true;
-#pragma unroll
-            for (int v = 0; v < kVirtualShards; ++v) all = all && ok[v];
-            if (all) break;
-            if (nb_globaltimer() - t0 > 10000000000ull) { to = 1; break; }          // 10 s: a peer died
-        }
-        total = x[0];
-#pragma unroll
-        for (int v = 1; v < kVirtualShards; ++v) total = addx(total, x[v]);
     }
-    *timed_out = __any_sync(0xffffffffu, to);
+    const int nslots = 8 * (nv + 1);
+    const int nreg = (nslots + 31) >> 5;
+    const double *mine = box[rank] + 2ull * ((unsigned long long) buf * 8 * kBoxStride);
+    const double *slot[kBoxPollRegs];
+#pragma unroll
+    for (int j = 0; j < kBoxPollRegs; ++j) {
+        const int sidx = lane + 32 * j;
+        const int k = sidx >> 3, v = sidx & 7;
+        slot[j] = mine + 2ull * ((unsigned long long) v * kBoxStride + (k < nv ? k : kBoxFlagSlot));
+    }
+    double x[kBoxPollRegs];
+#pragma unroll
+    for (int j = 0; j < kBoxPollRegs; ++j) x[j] = 0.0;
+    const unsigned long long t0 = nb_globaltimer();
+    int to = 0;
+    for (;;) {
+        bool all = true;
+#pragma unroll
+        for (int j = 0; j < kBoxPollRegs; ++j)
+            if (j < nreg && lane + 32 * j < nslots) all = box_get(slot[j], seq, &x[j]) && all;
+        if (__all_sync(0xffffffffu, all)) break;
+        if (__any_sync(0xffffffffu, nb_globaltimer() - t0 > 10000000000ull)) { to = 1; break; }      // 10 s: a peer died
+    }
+    // lane kd's sum: records (kd, v), v = 0..7, in index order
+    const int kd = lane < nv ? lane : (lane == kBoxFlagSlot ? nv : -1);
+    double total = 0.0;
+#pragma unroll
+    for (int v = 0; v < kVirtualShards; ++v) {
+        const int sidx = kd >= 0 ? 8 * kd + v : 0;
+        double pick = 0.0;
+#pragma unroll
+        for (int j = 0; j < kBoxPollRegs; ++j)
+            if (j < nreg) {
+                const double t = __shfl_sync(0xffffffffu, x[j], sidx & 31);
+                if ((sidx >> 5) == j) pick = t;
+            }
+        total = v == 0 ? pick : addx(total, pick);
+    }
+    if (kd < 0) total = 0.0;
+    *timed_out = to;
     *any_flag = __shfl_sync(0xffffffffu, total, kBoxFlagSlot) > 0.0 ? 1 : 0;
     return total;
 }
@@ -1492,7 +1518,7 @@ struct SharedMultipliers {                // what the point functions read in th
 // s_vs [8 x NV] (the shard sums of the generation in flight) and s_w [8 x 8 x NV] (per shard: the 8 fold-warp results)
 // are provided by the caller: the TMA-staged kernel's folder CTA lends its (otherwise unused) stage ring.
 template <int NV>
-__device__ __noinline__ void solve_folder(const SolveArgs &sa, double *s_vs, double *s_w)
+__device__ __noinline__ void solve_folder(const SolveArgs &sa, double *s_vs, double *s_w, void *mach_storage)
 {
     const DualArgs &a = sa.d;
     SolveState *st = sa.st;
@@ -1505,7 +1531,7 @@ __device__ __noinline__ void solve_folder(const SolveArgs &sa, double *s_vs, dou
     // and is brought into registers only for that turn, so that it does not weigh on the poll-and-fold loop that all
     // eight warps run in between (at the 80-register budget of the 3-CTAs/SM kernels it used to be spilled there:
     // ~400 bytes of local-memory traffic on the serial path of every generation).
-    __shared__ WarpDualMachine<MAXM> s_mach[32];
+    WarpDualMachine<MAXM> *const s_mach = static_cast<WarpDualMachine<MAXM> *>(mach_storage);      // [32], shared memory of the caller
     __shared__ int s_final_pass;
     const unsigned long long t_start = nb_globaltimer();
     if (threadIdx.x == 0) { s_exit = 0; s_final_pass = 0; }
@@ -1631,7 +1657,8 @@ __global__ void __launch_bounds__(BLOCK, MINB) dual_solve_kernel(const __grid_co
     if (blockIdx.x == gridDim.x - 1) {
         __shared__ double s_vs[kVirtualShards * NV];
         __shared__ double s_w[kVirtualShards * kGroupWarps * NV];
-        solve_folder<NV>(sa, s_vs, s_w);
+        __shared__ __align__(16) unsigned char s_mach[32 * sizeof(WarpDualMachine<NV - 3>)];
+        solve_folder<NV>(sa, s_vs, s_w, s_mach);
         return;
     }
     const DualArgs &a = sa.d;
@@ -1761,8 +1788,9 @@ __global__ void __launch_bounds__(kBlock, MINB) dual_solve_async_kernel(const __
     extern __shared__ __align__(16) unsigned char s_ring[];    // [STAGES][NARR][kBlock] double2: thread t owns column t
     if (blockIdx.x == gridDim.x - 1) {                          // the folder CTA: its ring holds the fold scratch
         double *scratch = reinterpret_cast<double *>(s_ring);
-        static_assert((size_t) STAGES * NARR * kChunkBytes >= (size_t) (kVirtualShards * NV + kVirtualShards * kGroupWarps * NV) * sizeof(double), "fold scratch fits the ring");
-        solve_folder<NV>(sa, scratch, scratch + kVirtualShards * NV);
+        constexpr size_t kFoldDoubles = (size_t) kVirtualShards * NV + (size_t) kVirtualShards * kGroupWarps * NV;
+        static_assert((size_t) STAGES * NARR * kChunkBytes >= kFoldDoubles * sizeof(double) + 32 * sizeof(WarpDualMachine<NV - 3>) + 16, "fold scratch fits the ring");
+        solve_folder<NV>(sa, scratch, scratch + kVirtualShards * NV, scratch + ((kFoldDoubles + 1) & ~(size_t) 1));
         return;
     }
     const DualArgs &a = sa.d;
@@ -1975,7 +2003,9 @@ __global__ void __launch_bounds__(kTmaBlock, MINB) dual_solve_tma_kernel(const _
     if (blockIdx.x == gridDim.x - 1) {                        // the folder CTA: its 8 first warps; its stage ring holds the fold scratch
         double *scratch = reinterpret_cast<double *>(s_raw);
         static_assert((size_t) STAGES * NARR * kChunkBytes >= (size_t) (kVirtualShards * NV + kVirtualShards * kGroupWarps * NV) * sizeof(double), "fold scratch fits the ring");
-        if (warp < kGroupWarps) solve_folder<NV>(sa, scratch, scratch + kVirtualShards * NV);
+        constexpr size_t kFoldDoubles = (size_t) kVirtualShards * NV + (size_t) kVirtualShards * kGroupWarps * NV;
+        static_assert((size_t) STAGES * NARR * kChunkBytes >= kFoldDoubles * sizeof(double) + 32 * sizeof(WarpDualMachine<NV - 3>) + 16, "fold scratch + optimiser state fit the ring");
+        if (warp < kGroupWarps) solve_folder<NV>(sa, scratch, scratch + kVirtualShards * NV, scratch + ((kFoldDoubles + 1) & ~(size_t) 1));
         return;
     }
     const DualArgs &a = sa.d;

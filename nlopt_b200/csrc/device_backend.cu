@@ -1237,7 +1237,9 @@ bool DeviceBackend::dual_solve(double *y, const double *lo, const double *hi, co
         static std::vector<unsigned long long> h(16 * kTraceGens);
         cudaStreamSynchronize(stream_);
         cudaMemcpy(h.data(), trace_buf, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
-        if (FILE *f = std::fopen(tf, "a")) {
+        std::string tfn = tf;
+        if (Comm::instance().active()) tfn += ".r" + std::to_string(Comm::instance().rank);      // one file per rank
+        if (FILE *f = std::fopen(tfn.c_str(), "a")) {
             const unsigned long long t00 = ~h[1];
             std::fprintf(f, "solve n_local=%llu m=%u grid=%lld groups=%u cta_start_spread_ns=%llu first_publish_ns=%llu\n", (unsigned long long) geo_.n_local, m_, grid,
                          geo_.nseg_local, h[2] - t00, h[16] - t00);
@@ -1467,11 +1469,12 @@ bool DeviceBackend::configure(const char *key, long long value)
         }
         return true;
     }
-    if (k == "pmax" || k == "target_chunks" || k == "fill_div" || k == "group_base" || k == "geometry_rule") {
+    if (k == "pmax" || k == "target_chunks" || k == "fill_div" || k == "group_base" || k == "geometry_rule" || k == "group_min_chunks") {
         if (value < 1 && k != "geometry_rule") return fail("bad value");
         if (k == "pmax") pmax_ = (unsigned) value;
         else if (k == "target_chunks") target_chunks_ = (unsigned) value;
         else if (k == "group_base") Geometry::group_base() = (unsigned) value;
+        else if (k == "group_min_chunks") Geometry::min_group_chunks() = (unsigned) value;
         else if (k == "geometry_rule") Geometry::rule() = (int) value;
         else Geometry::fill_div() = (unsigned) value;
         if (pool_) {

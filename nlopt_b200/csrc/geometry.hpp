@@ -13,6 +13,10 @@
 
 #include <cstdint>
 
+#ifndef NB200_MIN_GROUP_CHUNKS
+#define NB200_MIN_GROUP_CHUNKS 4
+#endif
+
 namespace nb200 {
 
 constexpr unsigned kV = 8;              // virtual shards (== kVirtualShards in ccsa_kernels.cuh)
@@ -31,6 +35,7 @@ struct Geometry {
     static unsigned &fill_div() { static unsigned v = 888; return v; }      // rule 0: groups wanted before groups start to grow
     static unsigned &group_base() { static unsigned v = 440; return v; }    // rule 1: see below
     static int &rule() { static int v = 1; return v; }
+    static unsigned &min_group_chunks() { static unsigned v = NB200_MIN_GROUP_CHUNKS; return v; }   // rule 1: smallest group, in chunks
 
     static unsigned long long cut(unsigned s, unsigned long long nchunks, unsigned S)
     {
@@ -41,11 +46,14 @@ struct Geometry {
     // Rule 1 (default).  The persistent kernels run 3 CTAs on each of the 148 SMs: 443 sweepers + the folder.  A rank
     // owns S / world groups per generation, so S is chosen from base * {1, 2, 4, 8} with base = 440: 1, 2, 4 or 8 ranks
     // then see a whole number of sweeper "waves" (3520 groups: 7.95 / 3.97 / 1.99 / 0.99 waves) -- the largest such S
-    // that keeps a group at two chunks or more.  Large n (groups would exceed `target_chunks` chunks): S = nchunks /
+    // that keeps a group at min_group_chunks = 4 chunks or more (measured, profiles/r02b_call3_geometry_async.txt: with
+    // 2 the mid-size problems ran two half-length groups per CTA and paid the group boundary twice -- n = 1e6, m = 4:
+    // 16.8 -> 14.2 us per evaluation, n = 1.25e6: 18.6 -> 16.5, n = 5e6: 61.7 -> 59.2).  Large n (groups would exceed `target_chunks` chunks): S = nchunks /
     // target_chunks, small groups even out the tail of a generation.  Small n: one chunk per group.
     // Rule 0 (round 1): about 1000 groups for mid-size n, `target_chunks` chunks per group for large n.
-    static unsigned choose_P(unsigned long long nchunks, unsigned target_chunks, unsigned pmax)
+    static unsigned choose_P(unsigned long long nchunks, unsigned target_chunks, unsigned pmax, unsigned group_base_arg = 0)
     {
+        const unsigned gbase = group_base_arg ? group_base_arg : group_base();
         unsigned long long want;
         if (rule() == 0) {
             unsigned long long fill = nchunks / fill_div();
@@ -53,13 +61,13 @@ struct Geometry {
             if (fill < target_chunks) target_chunks = (unsigned) fill;
             want = (nchunks + (unsigned long long) kV * target_chunks - 1) / ((unsigned long long) kV * target_chunks);
         } else {
-            const unsigned long long base = group_base() / kV ? group_base() / kV : 1;      // P of the smallest candidate
+            const unsigned long long base = gbase / kV ? gbase / kV : 1;                    // P of the smallest candidate
             const unsigned long long big = (nchunks + (unsigned long long) kV * target_chunks - 1) / ((unsigned long long) kV * target_chunks);
             if (big >= 8 * base) want = big;
             else {
                 want = 0;
                 for (unsigned long long f = 8; f >= 1; f >>= 1)
-                    if (kV * base * f * 2 <= nchunks) { want = base * f; break; }
+                    if (kV * base * f * min_group_chunks() <= nchunks) { want = base * f; break; }
                 if (!want) {                                                              // at most one chunk per group
                     const unsigned long long one = (nchunks + kV - 1) / kV;
                     want = one < base ? one : base;
@@ -71,14 +79,16 @@ struct Geometry {
         return (unsigned) want;
     }
 
-    static Geometry make(unsigned long long n, int world, int rank, unsigned target_chunks, unsigned pmax)
+    // group_base = 0: the process-wide default (rule 1: number of sweeper CTAs of the kernel that will run, rounded down
+    // to a multiple of 8; the backends pass the value that matches their solve kernel -- it must be the same on all ranks)
+    static Geometry make(unsigned long long n, int world, int rank, unsigned target_chunks, unsigned pmax, unsigned group_base_arg = 0)
     {
         Geometry g;
         g.n = n;
         const unsigned long long npairs = (n + 1) / 2;
         g.nchunks = (npairs + kChunkVars / 2 - 1) / (kChunkVars / 2);
         if (g.nchunks < 1) g.nchunks = 1;
-        g.P = choose_P(g.nchunks, target_chunks, pmax);
+        g.P = choose_P(g.nchunks, target_chunks, pmax, group_base_arg);
         g.S = kV * g.P;
         g.world = world;
         g.rank = rank;

@@ -11,7 +11,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 G, P = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
-RND = "r02"
+RND = sys.argv[1] if len(sys.argv) > 1 else "r02"      # evidence prefix: r02 (first session), r02b (second session)
 KEYS = ("gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
         "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "launch__registers_per_thread", "launch__grid_size",
         "launch__block_size", "sm__warps_active.avg.pct_of_peak_sustained_active",
@@ -60,7 +60,7 @@ def main():
         out = {"dram_bytes_per_launch": c["dram_bytes_per_evaluation"], "algorithmic_bytes": c["algorithmic_bytes_per_evaluation"],
                "duration_us_under_ncu": c["duration_us_per_evaluation_under_ncu"],
                "note": "per dual evaluation (generation) of dual_solve_kernel, CCSAQ n=1e7 m=4: ncu --set full on one launch of 21 generations "
-                       "(bench.py --param dual_maxeval=20), DRAM read+write bytes / 21; profiles/r02_ncu_solve_key_metrics.json", "captures": key}
+                       "(bench.py --param dual_maxeval=20), DRAM read+write bytes / 21; profiles/" + RND + "_ncu_solve_key_metrics.json", "captures": key}
         json.dump(out, open(os.path.join(P, "ncu_summary.json"), "w"), indent=1)
         for f, o in (("prof_solve_details.csv", f"{RND}_ncu_solve_kernel_details.csv"),):
             if os.path.exists(os.path.join(G, f)):
@@ -90,7 +90,7 @@ def main():
     for f in glob.glob(os.path.join(G, "bench_*.json")) + glob.glob(os.path.join(G, "sweep_c5_n*.json")):
         if os.path.getsize(f) > 10:
             shutil.copy(f, os.path.join(P, f"{RND}_{os.path.basename(f)}"))
-    for f in ("r02_final_n1.log",):
+    for f in (f"{RND}_final_n1.log",):
         if os.path.exists(os.path.join(G, f)):
             shutil.copy(os.path.join(G, f), os.path.join(P, f.replace(".log", ".txt")))
     print(json.dumps(key, indent=1)[:2500])
