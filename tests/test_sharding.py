@@ -133,6 +133,25 @@ def test_shard_geometry_groups_tile_and_do_not_depend_on_the_world_size(built):
             assert tot == n
 
 
+def test_group_rule_wave_aligned_counts_and_smallest_group(built):
+    """geometry.hpp rule 1: between one chunk per group (small n) and 8 chunks per group (large n) the number of groups is
+    440 x {1, 2, 4, 8} -- whole sweeper waves of the 3-CTAs/SM persistent kernels on 1, 2, 4 or 8 ranks -- and the largest
+    of these that keeps every group at 4 chunks or more."""
+    for n, want in ((300_000, 440), (600_000, 440), (1_000_000, 440), (1_250_000, 440), (2_500_000, 880),
+                    (5_000_000, 1760), (10_000_000, 3520)):
+        g = geometry(n, 0, 1)
+        assert g.groups_total == want, (n, g.groups_total)
+        if n >= 1_000_000:
+            sizes = [(k + 1) * g.nchunks // g.groups_total - k * g.nchunks // g.groups_total for k in range(g.groups_total)]
+            assert min(sizes) >= 4
+    for n in (20_000_000, 100_000_000):                           # large n: 8 chunks per group
+        g = geometry(n, 0, 1)
+        assert g.groups_total == (g.nchunks + 63) // 64 * 8
+    for n in (1, 1000, 100_000):                                  # small n: one chunk per group (at least the 8 virtual shards)
+        g = geometry(n, 0, 1)
+        assert g.groups_total == 8 * max(1, (g.nchunks + 7) // 8)
+
+
 def _value_worker(rank, world, port, out):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
