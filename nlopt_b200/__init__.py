@@ -213,6 +213,21 @@ class opt:
         self._check(ret)
         return xa
 
+    def optimize_inplace(self, xa):
+        """The C call itself (nlopt.h: nlopt_optimize(opt, x, &minf)): `xa` is the caller's own contiguous float64 buffer,
+        start point on entry, solution on return -- no Python-side copy of the n doubles.  Returns the nlopt_result."""
+        if not (isinstance(xa, np.ndarray) and xa.dtype == np.float64 and xa.flags["C_CONTIGUOUS"] and xa.size == self._n):
+            raise ValueError("optimize_inplace needs a contiguous float64 array of the problem's dimension")
+        f = C.c_double(0.0)
+        self._exc = None
+        ret = self._lib.nlopt_optimize(self._h, _ptr(xa), C.byref(f))
+        self._last_result, self._last_optf = ret, f.value
+        if ret == FORCED_STOP and self._exc is not None:
+            e, self._exc = self._exc, None
+            raise e
+        self._check(ret)
+        return ret
+
     def last_optimize_result(self):
         return self._last_result
 

@@ -270,6 +270,7 @@ struct DualArgs {
     int rank, world;
     unsigned l2_keep;             // operand arrays to hold in L2 across evaluations (L2Policies::mask)
     unsigned prefetch_chunks;     // solve kernel: chunks of its next group a waiting sweeper asks the L2 to fetch
+    unsigned stagger_ns, sm_count;    // solve kernel: start-of-generation skew between the warps that share an SM sub-partition (0: none)
     // the multipliers and penalties
     int m;                        // total number of constraints (rows of G)
     unsigned active;              // bit i clear: constraint i switched off (MMA, NaN value)            (m <= 16)
@@ -1723,6 +1724,14 @@ __global__ void __launch_bounds__(BLOCK, MINB) dual_solve_kernel(const __grid_co
             NB_TR(if (threadIdx.x == 0 && want < kTraceGens) { const unsigned long long t = nb_globaltimer();
                       atomicMax(&sa.trace[16 * want + 1], ~t); atomicMax(&sa.trace[16 * want + 2], t); })
             my_gen = want;
+            // Skew experiment (knob b200_stagger_ns, default 0).  The 6 warps that share an SM sub-partition (2 per CTA, 3
+            // CTAs) receive the multipliers at the same moment and, under round-robin issue, finish every chunk together,
+            // request the next one together and leave the fp64 pipe idle for a load latency per chunk.  A one-time offset
+            // of slot x stagger_ns at the start of a generation lets them take turns instead.
+            if (a.stagger_ns) {
+                const unsigned slot = (blockIdx.x / (a.sm_count ? a.sm_count : 1u)) * 2u + (unsigned) (sub >> 2);
+                if (slot) __nanosleep(slot * a.stagger_ns);
+            }
         }
         // claim the next group now; the result is parked in a register until the sweep is over
         if (threadIdx.x == 0) next_c = atomicAdd(&st->claim, 1ull);

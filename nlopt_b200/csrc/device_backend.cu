@@ -942,6 +942,8 @@ void DeviceBackend::fill_dual_args(DualArgs &a, const double *y, const DualScala
     a.l2_keep = l2_keep_mask() | (l1_prefetch_ ? kL1PrefetchBit : 0u);
     // the L2 prefetch of a waiting sweeper only pays when the operands of a generation do not stay in the L2 anyway
     a.prefetch_chunks = (prefetch_forced_ || (5 + (size_t) m_) * geo_.ld * sizeof(double) >= (64u << 20)) ? prefetch_chunks_ : 0u;
+    a.stagger_ns = stagger_ns_;
+    a.sm_count = (unsigned) sm_count_;
     a.m = (int) m_;
     a.rho = sc.rho;
     a.half_rho = 0.5 * sc.rho;
@@ -1456,6 +1458,7 @@ bool DeviceBackend::configure(const char *key, long long value)
     if (k == "solve_tma") { solve_tma_ = (int) value; return true; }
     if (k == "solve_async") { solve_async_ = (int) value; return true; }
     if (k == "solve_minb") { solve_minb_ = (int) value; return true; }
+    if (k == "stagger_ns") { stagger_ns_ = value < 0 ? 0u : (unsigned) value; return true; }
     if (k == "l1_prefetch") { l1_prefetch_ = value != 0; return true; }
     if (k == "prefetch_chunks") { prefetch_chunks_ = value < 0 ? 0u : (unsigned) value; prefetch_forced_ = true; return true; }
     if (k == "l2_keep_mb") {

@@ -144,6 +144,24 @@ def test_vector_constraint_equals_scalar_constraints(hosttest_lib):
     assert np.array_equal(x, a["x"]) and o.last_optimum_value() == a["minf"]
 
 
+def test_optimize_inplace_is_the_c_call_on_the_callers_buffer(hosttest_lib):
+    """opt.optimize_inplace(x): nlopt_optimize(opt, x, &minf) on the caller's own array -- same run as opt.optimize(),
+    the solution left in the array, nothing copied; anything but a contiguous float64 array of the right size is refused."""
+    lb = [-np.inf, 0.0]
+    a = run(hosttest_lib, nl.LD_CCSAQ, 2, P.tut_f, [P.tut_c(2, 0), P.tut_c(-1, 1)], [1e-8, 1e-8], lb, [np.inf, np.inf], P.TUT_X0,
+            xtol_rel=1e-4)
+    o = nl.opt(nl.LD_CCSAQ, 2, library=hosttest_lib)
+    o.set_lower_bounds(lb); o.set_min_objective(P.tut_f); o.set_xtol_rel(1e-4)
+    o.add_inequality_constraint(P.tut_c(2, 0), 1e-8); o.add_inequality_constraint(P.tut_c(-1, 1), 1e-8)
+    x = np.array(P.TUT_X0, dtype=np.float64)
+    ret = o.optimize_inplace(x)
+    assert ret == a["ret"] == o.last_optimize_result() and o.get_numevals() == a["numevals"]
+    assert np.array_equal(x, a["x"]) and o.last_optimum_value() == a["minf"]
+    for bad in ([1.0, 2.0], np.zeros(3), np.zeros(2, dtype=np.float32), np.zeros(4)[::2]):
+        with pytest.raises(ValueError):
+            o.optimize_inplace(bad)
+
+
 def test_maximize_flips_sign(hosttest_lib):
     lb, ub = [-np.inf, 0.0], [np.inf, np.inf]
     a = run(hosttest_lib, nl.LD_CCSAQ, 2, P.tut_f, [P.tut_c(2, 0), P.tut_c(-1, 1)], [1e-8, 1e-8], lb, ub, P.TUT_X0,
